@@ -1,0 +1,851 @@
+// gnn_kernels.cu - hand-written sm_100a kernels + the C ABI of include/gnn_b200.h.
+//
+// Path: LADIES-layer aggregation SpMM (forward A.X, backward A^T.G), adjacency
+// construction, placement remap and input-feature gather of HPC-Research-Lab/GNN
+// (reference spmm_cpp/cuda_spmm.cu, spmm_cpp/spmm.cpp, custom_sparse_ops.py,
+// sampler.py:133-158, main.py:129-134).  Built from scratch for B200: no torch
+// types, no host synchronisation, no allocation, every launch on the caller's
+// stream.  The path is sparse, fp32 and bandwidth/LSU-bound: SIMT kernels with
+// 128-bit coalesced row loads, warp-shuffle broadcast of the (col,val) stream,
+// nnz-balanced chunking with a fixed-order fix-up instead of atomics.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <atomic>
+
+#include "gnn_b200.h"
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+#define GNN_LAUNCH_CHECK()                         \
+  do {                                             \
+    g_launches.fetch_add(1, std::memory_order_relaxed); \
+    cudaError_t e_ = cudaGetLastError();           \
+    if (e_ != cudaSuccess) return (int)e_;         \
+  } while (0)
+
+#define GNN_CUDA(call)                             \
+  do {                                             \
+    cudaError_t e_ = (call);                       \
+    if (e_ != cudaSuccess) return (int)e_;         \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// vector helpers
+// ---------------------------------------------------------------------------
+template <int VEC> struct Vec;
+template <> struct Vec<4> { float4 v; };
+template <> struct Vec<2> { float2 v; };
+template <> struct Vec<1> { float v; };
+
+template <int VEC>
+__device__ __forceinline__ void vzero(float (&a)[VEC]) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) a[i] = 0.f;
+}
+
+// read-only (non-coherent) vector load of VEC floats; p is VEC*4-byte aligned
+template <int VEC>
+__device__ __forceinline__ void ldg_vec(const float *p, float (&x)[VEC]) {
+  if constexpr (VEC == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+    x[0] = t.x; x[1] = t.y;
+  } else {
+    x[0] = __ldg(p);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Row-split CSR SpMM
+//
+// Work item = (chunk of C consecutive nonzeros, column slab).  One warp per item.
+// The warp walks the rows its chunk touches; a row that lies inside one chunk is
+// stored directly, a row that spans several chunks is written as a partial to the
+// workspace and the warp that arrives last adds the partials in ascending chunk
+// order (fixed order => bit-reproducible), then stores the row.  Rows without
+// nonzeros are zero-filled by the chunk that finishes the preceding non-empty row
+// (chunk 0 also covers leading empty rows), so every output row is written once.
+//
+// Lane layout, LPR == 32: lane l owns VEC floats at column slab0 + (n*32 + l)*VEC
+// for n < NV.  LPR < 32 (narrow D): the warp holds 32/LPR row-groups; group g takes
+// nonzeros k = g (mod 32/LPR) and the groups are combined by xor-shuffles.
+// ---------------------------------------------------------------------------
+template <bool GATHER>
+struct XSrc {
+  const float *X;
+  int64_t ldx;
+  const float *const *xrows;
+  __device__ __forceinline__ const float *row(int c) const {
+    if constexpr (GATHER) return reinterpret_cast<const float *>(__ldg(reinterpret_cast<const unsigned long long *>(xrows) + c));
+    else return X + (int64_t)c * ldx;
+  }
+};
+
+template <int VEC, int NV, int LPR, bool GATHER>
+__device__ __forceinline__ void accumulate_segment(const int *__restrict__ colidx, const float *__restrict__ vals,
+                                                   const XSrc<GATHER> &xs, int s, int e, int lane, int col0, int D,
+                                                   float (&acc)[NV][VEC]) {
+  constexpr int G = 32 / LPR;                       // row groups in the warp
+  constexpr int U = (NV >= 5) ? 1 : (NV >= 3 ? 2 : (NV == 2 ? 4 : 8));
+  const int g = lane / LPR;
+  bool colok[NV];
+#pragma unroll
+  for (int n = 0; n < NV; ++n) colok[n] = col0 + n * LPR * VEC + VEC <= D + (GATHER ? 3 : 0);
+
+  for (int base = s; base < e; base += 32) {
+    const int i = base + lane;
+    int cl = 0;
+    float vl = 0.f;
+    if (i < e) { cl = __ldg(colidx + i); vl = __ldg(vals + i); }
+    const int n_here = min(32, e - base);
+    // each group visits k = t*G + g
+    const int steps = (n_here + G - 1) / G;
+    int t = 0;
+    for (; t + U <= steps; t += U) {
+      int c[U]; float v[U]; bool ok[U];
+      float x[U][NV][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = (t + u) * G + g;
+        c[u] = __shfl_sync(kFull, cl, k & 31);
+        v[u] = __shfl_sync(kFull, vl, k & 31);
+        ok[u] = k < n_here;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float *xr = xs.row(c[u]) + col0;
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+          if (ok[u] && colok[n]) ldg_vec<VEC>(xr + n * LPR * VEC, x[u][n]);
+          else vzero<VEC>(x[u][n]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float vv = ok[u] ? v[u] : 0.f;
+#pragma unroll
+        for (int n = 0; n < NV; ++n)
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[n][q] = fmaf(vv, x[u][n][q], acc[n][q]);
+      }
+    }
+    for (; t < steps; ++t) {
+      const int k = t * G + g;
+      const int c = __shfl_sync(kFull, cl, k & 31);
+      const float v = __shfl_sync(kFull, vl, k & 31);
+      if (k < n_here) {
+        const float *xr = xs.row(c) + col0;
+        float x[NV][VEC];
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+          if (colok[n]) ldg_vec<VEC>(xr + n * LPR * VEC, x[n]);
+          else vzero<VEC>(x[n]);
+        }
+#pragma unroll
+        for (int n = 0; n < NV; ++n)
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[n][q] = fmaf(v, x[n][q], acc[n][q]);
+      }
+    }
+  }
+  if constexpr (G > 1) {
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+      for (int n = 0; n < NV; ++n)
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc[n][q] += __shfl_xor_sync(kFull, acc[n][q], off);
+  }
+}
+
+// store VEC floats per (lane, n) to a row; scalar when the row is not VEC-aligned
+template <int VEC, int NV, int LPR>
+__device__ __forceinline__ void store_row(float *row, bool vec_ok, int lane, int col0, int D, const float (&acc)[NV][VEC]) {
+  if (lane >= LPR) return;
+#pragma unroll
+  for (int n = 0; n < NV; ++n) {
+    const int col = col0 + n * LPR * VEC;
+    if (col >= D) continue;
+    if (VEC == 4 && vec_ok && col + 4 <= D) {
+      *reinterpret_cast<float4 *>(row + col) = make_float4(acc[n][0], acc[n][1 % VEC], acc[n][2 % VEC], acc[n][3 % VEC]);
+    } else if (VEC == 2 && vec_ok && col + 2 <= D) {
+      *reinterpret_cast<float2 *>(row + col) = make_float2(acc[n][0], acc[n][1 % VEC]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < VEC; ++q)
+        if (col + q < D) row[col + q] = acc[n][q];
+    }
+  }
+}
+
+template <int VEC, int NV, int LPR>
+__device__ __forceinline__ void zero_row(float *row, bool vec_ok, int lane, int col0, int D) {
+  float z[NV][VEC];
+#pragma unroll
+  for (int n = 0; n < NV; ++n) vzero<VEC>(z[n]);
+  store_row<VEC, NV, LPR>(row, vec_ok, lane, col0, D, z);
+}
+
+struct SpmmParams {
+  const int *rowptr;
+  const int *colidx;
+  const float *vals;
+  int M;
+  int nnz;
+  int D;
+  int C;          // nonzeros per chunk
+  int nchunks;
+  int nslabs;
+  float *Y;
+  int64_t ldy;
+  float *partials;   // [2*nchunks][Dp]
+  int *counters;     // [M*nslabs], zero on entry
+  int Dp;
+};
+
+template <int VEC, int NV, int LPR, bool GATHER>
+__global__ void __launch_bounds__(kThreads)
+spmm_rowsplit_kernel(const SpmmParams p, const XSrc<GATHER> xs) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t item = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+  if (item >= (int64_t)p.nchunks * p.nslabs) return;
+  const int slab = (int)(item / p.nchunks);
+  const int chunk = (int)(item % p.nchunks);
+  constexpr int W = NV * LPR * VEC;                 // slab width in floats
+  const int sl = lane % LPR;
+  const int col0 = slab * W + sl * VEC;
+  const bool y_vec_ok = ((reinterpret_cast<uintptr_t>(p.Y) | (uintptr_t)(p.ldy * 4)) & (VEC * 4 - 1)) == 0;
+
+  int s = chunk * p.C;
+  const int e = min(s + p.C, p.nnz);
+
+  // first row with rowptr[r+1] > s  (binary search; rowptr is non-decreasing, rowptr[M] == nnz > s)
+  int lo = 0, hi = p.M - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(p.rowptr + mid + 1) > s) hi = mid; else lo = mid + 1;
+  }
+  int r = lo;
+  if (chunk == 0) {  // leading empty rows
+    for (int z = 0; z < r; ++z) zero_row<VEC, NV, LPR>(p.Y + (int64_t)z * p.ldy, y_vec_ok, lane, col0, p.D);
+  }
+
+  while (s < e) {
+    const int row_start = __ldg(p.rowptr + r);
+    const int row_end = __ldg(p.rowptr + r + 1);
+    const int seg_end = min(row_end, e);
+    float acc[NV][VEC];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) vzero<VEC>(acc[n]);
+    accumulate_segment<VEC, NV, LPR, GATHER>(p.colidx, p.vals, xs, s, seg_end, lane, col0, p.D, acc);
+
+    const int c_first = row_start / p.C;
+    const int c_last = (row_end - 1) / p.C;
+    float *yrow = p.Y + (int64_t)r * p.ldy;
+    if (c_first == c_last) {
+      store_row<VEC, NV, LPR>(yrow, y_vec_ok, lane, col0, p.D, acc);
+    } else {
+      // partial of (row r, chunk): slot 2*chunk + (row starts strictly inside this chunk)
+      float *slot = p.partials + ((int64_t)2 * chunk + (row_start > chunk * p.C ? 1 : 0)) * p.Dp;
+      store_row<VEC, NV, LPR>(slot, true, lane, col0, p.D, acc);
+      __threadfence();
+      __syncwarp();
+      int last = 0;
+      if (lane == 0) last = (atomicAdd(p.counters + (int64_t)r * p.nslabs + slab, 1) == c_last - c_first);
+      last = __shfl_sync(kFull, last, 0);
+      if (last) {
+        __threadfence();
+#pragma unroll
+        for (int n = 0; n < NV; ++n) vzero<VEC>(acc[n]);
+        if (lane < LPR) {
+          for (int ch = c_first; ch <= c_last; ++ch) {
+            const float *ps = p.partials + ((int64_t)2 * ch + (row_start > ch * p.C ? 1 : 0)) * p.Dp;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+              const int col = col0 + n * LPR * VEC;
+#pragma unroll
+              for (int q = 0; q < VEC; ++q)
+                if (col + q < p.D) acc[n][q] += __ldcg(ps + col + q);
+            }
+          }
+        }
+        store_row<VEC, NV, LPR>(yrow, y_vec_ok, lane, col0, p.D, acc);
+      }
+    }
+    s = seg_end;
+    if (seg_end == row_end) {
+      // this chunk finished row r: it also owns the empty rows that follow
+      ++r;
+      while (r < p.M && __ldg(p.rowptr + r + 1) == row_end) {
+        zero_row<VEC, NV, LPR>(p.Y + (int64_t)r * p.ldy, y_vec_ok, lane, col0, p.D);
+        ++r;
+      }
+    }
+  }
+}
+
+// chunk size: a function of (nnz, D) only so that the workspace query and the launch agree
+inline int spmm_chunk(int64_t nnz, int64_t D) {
+  const int64_t slabs_est = cdiv(D, 256);
+  int64_t want = nnz * slabs_est / 16384;
+  int c = 64;
+  while (c < 2048 && c * 2 <= want) c *= 2;
+  return c;
+}
+
+struct SpmmPlan { int vec, nv, lpr, nslabs, C, nchunks, Dp; };
+
+inline SpmmPlan make_plan(int64_t nnz, int64_t D, int vec) {
+  SpmmPlan pl;
+  pl.vec = vec;
+  pl.C = spmm_chunk(nnz, D);
+  pl.nchunks = (int)cdiv(nnz, pl.C);
+  pl.Dp = (int)(cdiv(D, 4) * 4);
+  const int64_t nvec = cdiv(D, vec);               // vectors per row
+  if (vec == 4 && nvec <= 16) {                    // narrow rows: several nonzeros per warp step
+    pl.lpr = nvec <= 4 ? 4 : (nvec <= 8 ? 8 : 16);
+    pl.nv = 1;
+    pl.nslabs = 1;
+    return pl;
+  }
+  pl.lpr = 32;
+  const int64_t n = cdiv(nvec, 32);                // vector columns per lane
+  static const int cand[] = {1, 2, 3, 4, 5, 6, 8};
+  double best = 1e30;
+  pl.nv = 1;
+  for (int nv : cand) {
+    const int64_t slabs = cdiv(n, nv);
+    const double cost = (double)(nv * slabs) + 0.5 * (double)slabs;
+    if (cost < best - 1e-9 || (cost < best + 1e-9 && nv > pl.nv)) { best = cost; pl.nv = nv; }
+  }
+  pl.nslabs = (int)cdiv(n, pl.nv);
+  return pl;
+}
+
+// counters: one int per (row, slab); vec == 1 gives the largest slab count of the three layouts
+inline size_t spmm_counter_bytes(int64_t M, int64_t nnz, int64_t D) {
+  return ((size_t)M * (size_t)make_plan(nnz, D, 1).nslabs * sizeof(int) + 255) / 256 * 256;
+}
+
+template <int VEC, int NV, int LPR, bool GATHER>
+int launch_spmm_t(const SpmmParams &p, const XSrc<GATHER> &xs, cudaStream_t st) {
+  const int64_t items = (int64_t)p.nchunks * p.nslabs;
+  const unsigned grid = (unsigned)cdiv(items, kWarpsPerCta);
+  spmm_rowsplit_kernel<VEC, NV, LPR, GATHER><<<grid, kThreads, 0, st>>>(p, xs);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int VEC, bool GATHER>
+int launch_spmm_nv(const SpmmPlan &pl, const SpmmParams &p, const XSrc<GATHER> &xs, cudaStream_t st) {
+  if (pl.lpr != 32) {
+    if constexpr (VEC == 4) {
+      switch (pl.lpr) {
+        case 4: return launch_spmm_t<4, 1, 4, GATHER>(p, xs, st);
+        case 8: return launch_spmm_t<4, 1, 8, GATHER>(p, xs, st);
+        default: return launch_spmm_t<4, 1, 16, GATHER>(p, xs, st);
+      }
+    } else {
+      return GNN_E_BADARG;
+    }
+  }
+  switch (pl.nv) {
+    case 1: return launch_spmm_t<VEC, 1, 32, GATHER>(p, xs, st);
+    case 2: return launch_spmm_t<VEC, 2, 32, GATHER>(p, xs, st);
+    case 3: return launch_spmm_t<VEC, 3, 32, GATHER>(p, xs, st);
+    case 4: return launch_spmm_t<VEC, 4, 32, GATHER>(p, xs, st);
+    case 5: return launch_spmm_t<VEC, 5, 32, GATHER>(p, xs, st);
+    case 6: return launch_spmm_t<VEC, 6, 32, GATHER>(p, xs, st);
+    default: return launch_spmm_t<VEC, 8, 32, GATHER>(p, xs, st);
+  }
+}
+
+__global__ void zero_rows_kernel(float *Y, int64_t ldy, int64_t M, int64_t D) {
+  const int64_t n = M * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    Y[(i / D) * ldy + (i % D)] = 0.f;
+}
+
+template <bool GATHER>
+int spmm_entry(const int32_t *rowptr, const int32_t *colidx, const float *vals, int64_t M, int64_t K, int64_t nnz,
+               int64_t D, const float *X, int64_t ldx, const float *const *xrows, float *Y, int64_t ldy,
+               void *workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (M < 0 || K < 0 || nnz < 0 || D < 0) return GNN_E_BADARG;
+  if (M == 0 || D == 0) return 0;
+  if (!Y || ldy < D) return GNN_E_BADARG;
+  if (M >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 2048 || K >= (1ll << 31) || D >= (1ll << 24)) return GNN_E_RANGE;
+  if (nnz == 0) {
+    zero_rows_kernel<<<(unsigned)std::min<int64_t>(cdiv(M * D, 256), 148 * 16), 256, 0, st>>>(Y, ldy, M, D);
+    GNN_LAUNCH_CHECK();
+    return 0;
+  }
+  if (!rowptr || !colidx || !vals) return GNN_E_BADARG;
+  if (GATHER ? (xrows == nullptr) : (X == nullptr || ldx < D)) return GNN_E_BADARG;
+  int vec = 1;
+  if (GATHER) {
+    vec = 4;   // contract: every row pointer is 16-byte aligned and readable up to ceil(D/4)*4 floats
+  } else {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(X) | (uintptr_t)(ldx * 4);
+    if ((a & 15) == 0 && D % 4 == 0) vec = 4;
+    else if ((a & 7) == 0 && D % 2 == 0) vec = 2;
+  }
+  const SpmmPlan pl = make_plan(nnz, D, vec);
+  const size_t need = gnn_csr_spmm_workspace_bytes(M, nnz, D);
+  if (!workspace || workspace_bytes < need) return GNN_E_WORKSPACE;
+
+  SpmmParams p;
+  p.rowptr = rowptr; p.colidx = colidx; p.vals = vals;
+  p.M = (int)M; p.nnz = (int)nnz; p.D = (int)D;
+  p.C = pl.C; p.nchunks = pl.nchunks; p.nslabs = pl.nslabs; p.Dp = pl.Dp;
+  p.Y = Y; p.ldy = ldy;
+  p.counters = reinterpret_cast<int *>(workspace);
+  const size_t counter_bytes = spmm_counter_bytes(M, nnz, D);
+  p.partials = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + counter_bytes);
+  GNN_CUDA(cudaMemsetAsync(p.counters, 0, (size_t)M * pl.nslabs * sizeof(int), st));
+  XSrc<GATHER> xs{X, ldx, xrows};
+  switch (vec) {
+    case 4: return launch_spmm_nv<4, GATHER>(pl, p, xs, st);
+    case 2: if constexpr (!GATHER) return launch_spmm_nv<2, false>(pl, p, xs, st); else return GNN_E_BADARG;
+    default: if constexpr (!GATHER) return launch_spmm_nv<1, false>(pl, p, xs, st); else return GNN_E_BADARG;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// build_adj: one warp per row, lanes stride over the row's entries (coalesced)
+// ---------------------------------------------------------------------------
+template <typename ColT>
+__global__ void __launch_bounds__(256)
+build_adj_kernel(const int *__restrict__ fullrowptr, const int *__restrict__ rowptr, const ColT *__restrict__ colidx,
+                 const float *__restrict__ normfact, int M, int64_t nnz, int64_t *__restrict__ out_idx,
+                 float *__restrict__ out_vals, int *__restrict__ out_col32) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
+    const int b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+    if (b == e) continue;
+    // cuda_spmm.cu:800: `1. / deg * normfact` - double quotient, double product, one rounding to float
+    const double inv_deg = 1. / (double)(__ldg(fullrowptr + r + 1) - __ldg(fullrowptr + r));
+    for (int i = b + lane; i < e; i += 32) {
+      const int c = (int)colidx[i];
+      out_vals[i] = (float)(inv_deg * (double)__ldg(normfact + c));
+      if (out_col32) out_col32[i] = c;
+      if (out_idx) { out_idx[i] = r; out_idx[nnz + i] = c; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// COO -> CSR (foreign sparse tensors)
+// ---------------------------------------------------------------------------
+__global__ void coo_to_csr_kernel(const int64_t *__restrict__ idx, int64_t M, int64_t nnz, int *__restrict__ rowptr,
+                                  int *__restrict__ col32) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nnz) return;
+  // entry i closes rows (prev, cur]: rowptr[r] = i for prev < r <= cur
+  const int64_t prev = (i == 0) ? -1 : idx[i - 1];
+  const int64_t cur = (i == nnz) ? M : idx[i];
+  for (int64_t r = prev + 1; r <= cur; ++r) rowptr[r] = (int)i;
+  if (i < nnz) col32[i] = (int)idx[nnz + i];
+}
+
+// ---------------------------------------------------------------------------
+// CSR transpose through a column-major bitmap (deterministic: bit OR is order-free)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bitmap_set_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx, int M, int words_per_col,
+                  unsigned *__restrict__ bitmap) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
+    const int b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+    const unsigned bit = 1u << (r & 31);
+    const int word = r >> 5;
+    for (int i = b + lane; i < e; i += 32)
+      atomicOr(bitmap + (int64_t)__ldg(colidx + i) * words_per_col + word, bit);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bitmap_count_kernel(const unsigned *__restrict__ bitmap, int K, int words_per_col, int *__restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < K; c += gridDim.x * wpb) {
+    const unsigned *col = bitmap + (int64_t)c * words_per_col;
+    int n = 0;
+    for (int w = lane; w < words_per_col; w += 32) n += __popc(col[w]);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) n += __shfl_xor_sync(kFull, n, off);
+    if (lane == 0) counts[c] = n;
+  }
+}
+
+// exclusive scan of counts[0..n) into out[0..n], out[n] = total; single CTA of 1024 threads
+__global__ void __launch_bounds__(1024)
+exclusive_scan_kernel(const int *__restrict__ counts, int n, int *__restrict__ out) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? counts[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int y = __shfl_up_sync(kFull, x, off);
+      if (lane >= off) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(kFull, w, off);
+        if (lane >= off) w += y;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int incl = x + (warp ? warp_sums[warp - 1] : 0) + carry;
+    if (i < n) out[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+__global__ void __launch_bounds__(256)
+bitmap_enumerate_kernel(const unsigned *__restrict__ bitmap, int K, int words_per_col, const int *__restrict__ rowptr,
+                        const int *__restrict__ colidx, const float *__restrict__ vals, const int *__restrict__ t_rowptr,
+                        int *__restrict__ t_colidx, float *__restrict__ t_vals) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < K; c += gridDim.x * wpb) {
+    const unsigned *col = bitmap + (int64_t)c * words_per_col;
+    int base = __ldg(t_rowptr + c);
+    for (int w0 = 0; w0 < words_per_col; w0 += 32) {
+      const int w = w0 + lane;
+      unsigned word = w < words_per_col ? col[w] : 0u;
+      const int cnt = __popc(word);
+      int incl = cnt;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(kFull, incl, off);
+        if (lane >= off) incl += y;
+      }
+      int pos = base + incl - cnt;
+      while (word) {
+        const int r = w * 32 + (__ffs(word) - 1);
+        word &= word - 1;
+        // position of column c inside row r of the CSR (columns ascending within a row)
+        int lo = __ldg(rowptr + r), hi = __ldg(rowptr + r + 1) - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(colidx + mid) < c) lo = mid + 1; else hi = mid;
+        }
+        t_colidx[pos] = r;
+        t_vals[pos] = __ldg(vals + lo);
+        ++pos;
+      }
+      base += __shfl_sync(kFull, incl, 31);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// placement remap + gathers
+// ---------------------------------------------------------------------------
+__global__ void placement_remap_kernel(const int64_t *__restrict__ input_nodes, int64_t n0,
+                                       const int64_t *__restrict__ dev_of, const int64_t *__restrict__ idx_of,
+                                       const int64_t *__restrict__ devices, int world, const float *const *__restrict__ bases,
+                                       int64_t ld_src, int *__restrict__ src_dev, int64_t *__restrict__ slot,
+                                       const float **__restrict__ xrows, unsigned long long *__restrict__ counts) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n0) return;
+  const int64_t node = input_nodes[j];
+  const int64_t dev = dev_of[node];
+  int s = -2;
+  int64_t sl = -1;
+  if (dev == -1) {
+    s = -1; sl = node;
+  } else {
+    for (int i = 0; i < world; ++i)
+      if (devices[i] == dev) { s = i; sl = idx_of[node]; }
+  }
+  src_dev[j] = s;
+  slot[j] = sl;
+  if (xrows) xrows[j] = (s == -2 || !bases) ? nullptr : bases[s < 0 ? world : s] + sl * ld_src;
+  if (counts) atomicAdd(counts + (s == -2 ? world + 1 : (s < 0 ? world : s)), 1ull);
+}
+
+// one warp per row; each lane keeps up to 4 independent 128-bit loads in flight
+template <bool FILTER, bool INDEX>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float *const *__restrict__ xrows, const int *__restrict__ src_dev, int only_src,
+                   const float *__restrict__ X, int64_t ldx, const int64_t *__restrict__ idx, int64_t n0, int F,
+                   float *__restrict__ out, int64_t ld_out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t j = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); j < n0; j += (int64_t)gridDim.x * wpb) {
+    if (FILTER && src_dev[j] != only_src) continue;
+    const float *src = INDEX ? X + idx[j] * ldx : xrows[j];
+    if (!src) continue;
+    float *dst = out + j * ld_out;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+      const int nv = F >> 2;
+      const float4 *s4 = reinterpret_cast<const float4 *>(src);
+      float4 *d4 = reinterpret_cast<float4 *>(dst);
+      int v = lane;
+      for (; v + 96 < nv; v += 128) {
+        const float4 a = s4[v], b = s4[v + 32], c = s4[v + 64], d = s4[v + 96];
+        d4[v] = a; d4[v + 32] = b; d4[v + 64] = c; d4[v + 96] = d;
+      }
+      for (; v < nv; v += 32) d4[v] = s4[v];
+      for (int t = (nv << 2) + lane; t < F; t += 32) dst[t] = src[t];
+    } else if ((((uintptr_t)src | (uintptr_t)dst) & 7) == 0) {
+      const int nv = F >> 1;
+      const float2 *s2 = reinterpret_cast<const float2 *>(src);
+      float2 *d2 = reinterpret_cast<float2 *>(dst);
+      int v = lane;
+      for (; v + 96 < nv; v += 128) {
+        const float2 a = s2[v], b = s2[v + 32], c = s2[v + 64], d = s2[v + 96];
+        d2[v] = a; d2[v + 32] = b; d2[v + 64] = c; d2[v + 96] = d;
+      }
+      for (; v < nv; v += 32) d2[v] = s2[v];
+      for (int t = (nv << 1) + lane; t < F; t += 32) dst[t] = src[t];
+    } else {
+      for (int t = lane; t < F; t += 32) dst[t] = src[t];
+    }
+  }
+}
+
+inline unsigned warp_grid(int64_t n_warps, int wpb) {
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(n_warps, wpb), 148 * 32));
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int gnn_abi_version(void) { return GNN_B200_ABI_VERSION; }
+
+const char *gnn_error_string(int code) {
+  switch (code) {
+    case 0: return "success";
+    case GNN_E_BADARG: return "gnn_b200: bad argument (null pointer, negative size, unsupported width)";
+    case GNN_E_WORKSPACE: return "gnn_b200: workspace missing or too small";
+    case GNN_E_RANGE: return "gnn_b200: size exceeds the limits of this path";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "gnn_b200: unknown error";
+  }
+}
+
+int64_t gnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int gnn_build_adj(const int32_t *fullrowptr, const int32_t *rowptr, const void *colidx, int colidx_bytes,
+                  const float *normfact, int64_t M, int64_t K, int64_t nnz, int64_t *out_indices, float *out_vals,
+                  int32_t *out_colidx32, gnn_stream_t stream) {
+  (void)K;
+  if (M < 0 || nnz < 0 || (colidx_bytes != 2 && colidx_bytes != 4)) return GNN_E_BADARG;
+  if (M >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1) return GNN_E_RANGE;
+  if (M == 0 || nnz == 0) return 0;
+  if (!fullrowptr || !rowptr || !colidx || !normfact || !out_vals) return GNN_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = warp_grid(M, 8);
+  if (colidx_bytes == 2)
+    build_adj_kernel<int16_t><<<grid, 256, 0, st>>>(fullrowptr, rowptr, (const int16_t *)colidx, normfact, (int)M, nnz,
+                                                    out_indices, out_vals, out_colidx32);
+  else
+    build_adj_kernel<int32_t><<<grid, 256, 0, st>>>(fullrowptr, rowptr, (const int32_t *)colidx, normfact, (int)M, nnz,
+                                                    out_indices, out_vals, out_colidx32);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnn_coo_to_csr(const int64_t *indices, int64_t M, int64_t nnz, int32_t *out_rowptr, int32_t *out_colidx32,
+                   gnn_stream_t stream) {
+  if (M < 0 || nnz < 0 || !out_rowptr) return GNN_E_BADARG;
+  if (M >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1) return GNN_E_RANGE;
+  if (nnz > 0 && (!indices || !out_colidx32)) return GNN_E_BADARG;
+  coo_to_csr_kernel<<<(unsigned)cdiv(nnz + 1, 256), 256, 0, (cudaStream_t)stream>>>(indices, M, nnz, out_rowptr, out_colidx32);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t gnn_csr_spmm_workspace_bytes(int64_t M, int64_t nnz, int64_t D) {
+  if (M <= 0 || nnz <= 0 || D <= 0) return 256;
+  const int C = spmm_chunk(nnz, D);
+  const size_t nchunks = (size_t)cdiv(nnz, C);
+  const size_t Dp = (size_t)cdiv(D, 4) * 4;
+  const size_t counter_bytes = spmm_counter_bytes(M, nnz, D);
+  return counter_bytes + 2 * nchunks * Dp * sizeof(float) + 256;
+}
+
+int gnn_csr_spmm_f32(const int32_t *rowptr, const int32_t *colidx, const float *vals, int64_t M, int64_t K, int64_t nnz,
+                     int64_t D, const float *X, int64_t ldx, float *Y, int64_t ldy, void *workspace,
+                     size_t workspace_bytes, gnn_stream_t stream) {
+  return spmm_entry<false>(rowptr, colidx, vals, M, K, nnz, D, X, ldx, nullptr, Y, ldy, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
+}
+
+int gnn_gather_spmm_f32(const int32_t *rowptr, const int32_t *colidx, const float *vals, int64_t M, int64_t K,
+                        int64_t nnz, int64_t D, const float *const *xrows, float *Y, int64_t ldy, void *workspace,
+                        size_t workspace_bytes, gnn_stream_t stream) {
+  return spmm_entry<true>(rowptr, colidx, vals, M, K, nnz, D, nullptr, 0, xrows, Y, ldy, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+}
+
+size_t gnn_csr_transpose_workspace_bytes(int64_t M, int64_t K, int64_t nnz) {
+  (void)nnz;
+  if (M <= 0 || K <= 0) return 256;
+  const size_t words_per_col = (size_t)cdiv(M, 32);
+  return (size_t)K * words_per_col * 4 + ((size_t)K * 4 + 255) / 256 * 256 + 256;
+}
+
+int gnn_csr_transpose(const int32_t *rowptr, const int32_t *colidx, const float *vals, int64_t M, int64_t K, int64_t nnz,
+                      int32_t *t_rowptr, int32_t *t_colidx, float *t_vals, void *workspace, size_t workspace_bytes,
+                      gnn_stream_t stream) {
+  if (M < 0 || K < 0 || nnz < 0 || !t_rowptr) return GNN_E_BADARG;
+  if (M >= (1ll << 31) - 1 || K >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1) return GNN_E_RANGE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K == 0) { GNN_CUDA(cudaMemsetAsync(t_rowptr, 0, sizeof(int), st)); return 0; }
+  if (nnz == 0 || M == 0) { GNN_CUDA(cudaMemsetAsync(t_rowptr, 0, (size_t)(K + 1) * sizeof(int), st)); return 0; }
+  if (!rowptr || !colidx || !vals || !t_colidx || !t_vals) return GNN_E_BADARG;
+  const size_t need = gnn_csr_transpose_workspace_bytes(M, K, nnz);
+  if (need > ((size_t)4 << 30)) return GNN_E_RANGE;   // bitmap too large: caller falls back to a sort
+  if (!workspace || workspace_bytes < need) return GNN_E_WORKSPACE;
+  const int words_per_col = (int)cdiv(M, 32);
+  int *counts = reinterpret_cast<int *>(workspace);
+  unsigned *bitmap = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(workspace) + ((size_t)K * 4 + 255) / 256 * 256);
+  GNN_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)K * words_per_col * 4, st));
+  bitmap_set_kernel<<<warp_grid(M, 8), 256, 0, st>>>(rowptr, colidx, (int)M, words_per_col, bitmap);
+  GNN_LAUNCH_CHECK();
+  bitmap_count_kernel<<<warp_grid(K, 8), 256, 0, st>>>(bitmap, (int)K, words_per_col, counts);
+  GNN_LAUNCH_CHECK();
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, (int)K, t_rowptr);
+  GNN_LAUNCH_CHECK();
+  bitmap_enumerate_kernel<<<warp_grid(K, 8), 256, 0, st>>>(bitmap, (int)K, words_per_col, rowptr, colidx, vals, t_rowptr,
+                                                          t_colidx, t_vals);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnn_placement_remap(const int64_t *input_nodes, int64_t n0, const int64_t *device_id_of_nodes,
+                        const int64_t *idx_of_nodes_on_device, const int64_t *devices, int64_t world,
+                        const float *const *bases, int64_t ld_src, int32_t *src_dev, int64_t *slot, const float **xrows,
+                        int64_t *counts, gnn_stream_t stream) {
+  if (n0 < 0 || world < 0 || world > 1024) return GNN_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (counts) GNN_CUDA(cudaMemsetAsync(counts, 0, (size_t)(world + 2) * sizeof(int64_t), st));
+  if (n0 == 0) return 0;
+  if (!input_nodes || !device_id_of_nodes || !idx_of_nodes_on_device || (world > 0 && !devices) || !src_dev || !slot)
+    return GNN_E_BADARG;
+  if (xrows && !bases) return GNN_E_BADARG;
+  placement_remap_kernel<<<(unsigned)cdiv(n0, 256), 256, 0, st>>>(input_nodes, n0, device_id_of_nodes,
+                                                                 idx_of_nodes_on_device, devices, (int)world, bases, ld_src,
+                                                                 src_dev, slot, xrows, (unsigned long long *)counts);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnn_gather_rows_f32(const float *const *xrows, int64_t n0, int64_t F, float *out, int64_t ld_out, gnn_stream_t stream) {
+  if (n0 < 0 || F < 0 || F >= (1ll << 31)) return GNN_E_BADARG;
+  if (n0 == 0 || F == 0) return 0;
+  if (!xrows || !out || ld_out < F) return GNN_E_BADARG;
+  gather_rows_kernel<false, false><<<warp_grid(n0, 8), 256, 0, (cudaStream_t)stream>>>(xrows, nullptr, 0, nullptr, 0, nullptr,
+                                                                                      n0, (int)F, out, ld_out);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnn_gather_rows_src_f32(const float *const *xrows, const int32_t *src_dev, int32_t only_src, int64_t n0, int64_t F,
+                            float *out, int64_t ld_out, gnn_stream_t stream) {
+  if (n0 < 0 || F < 0 || F >= (1ll << 31)) return GNN_E_BADARG;
+  if (n0 == 0 || F == 0) return 0;
+  if (!xrows || !src_dev || !out || ld_out < F) return GNN_E_BADARG;
+  gather_rows_kernel<true, false><<<warp_grid(n0, 8), 256, 0, (cudaStream_t)stream>>>(xrows, src_dev, only_src, nullptr, 0,
+                                                                                     nullptr, n0, (int)F, out, ld_out);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnn_index_rows_f32(const float *X, int64_t ldx, const int64_t *idx, int64_t n, int64_t F, float *out, int64_t ld_out,
+                       gnn_stream_t stream) {
+  if (n < 0 || F < 0 || F >= (1ll << 31)) return GNN_E_BADARG;
+  if (n == 0 || F == 0) return 0;
+  if (!X || !idx || !out || ld_out < F || ldx < F) return GNN_E_BADARG;
+  gather_rows_kernel<false, true><<<warp_grid(n, 8), 256, 0, (cudaStream_t)stream>>>(nullptr, nullptr, 0, X, ldx, idx, n,
+                                                                                    (int)F, out, ld_out);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnn_shard_alloc(size_t bytes, void **dev_ptr, unsigned char ipc_handle[64]) {
+  if (!dev_ptr || bytes == 0) return GNN_E_BADARG;
+  GNN_CUDA(cudaMalloc(dev_ptr, bytes));
+  if (ipc_handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *dev_ptr);
+    if (e != cudaSuccess) { cudaFree(*dev_ptr); *dev_ptr = nullptr; return (int)e; }
+    for (int i = 0; i < 64; ++i) ipc_handle[i] = reinterpret_cast<unsigned char *>(&h)[i];
+  }
+  return 0;
+}
+
+int gnn_shard_open(const unsigned char ipc_handle[64], void **dev_ptr) {
+  if (!ipc_handle || !dev_ptr) return GNN_E_BADARG;
+  cudaIpcMemHandle_t h;
+  for (int i = 0; i < 64; ++i) reinterpret_cast<unsigned char *>(&h)[i] = ipc_handle[i];
+  GNN_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int gnn_shard_close(void *dev_ptr) {
+  if (!dev_ptr) return GNN_E_BADARG;
+  GNN_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return 0;
+}
+
+int gnn_shard_free(void *dev_ptr) {
+  if (!dev_ptr) return 0;
+  GNN_CUDA(cudaFree(dev_ptr));
+  return 0;
+}
+
+int gnn_host_register(void *host_ptr, size_t bytes, void **dev_alias) {
+  if (!host_ptr || !dev_alias || bytes == 0) return GNN_E_BADARG;
+  GNN_CUDA(cudaHostRegister(host_ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+  cudaError_t e = cudaHostGetDevicePointer(dev_alias, host_ptr, 0);
+  if (e != cudaSuccess) { cudaHostUnregister(host_ptr); return (int)e; }
+  return 0;
+}
+
+int gnn_host_unregister(void *host_ptr) {
+  if (!host_ptr) return GNN_E_BADARG;
+  GNN_CUDA(cudaHostUnregister(host_ptr));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+// spmm_ext.cpp - thin torch/pybind layer over the C ABI (include/gnn_b200.h).
+//
+// Keeps the reference extension's Python-visible signatures
+// (reference spmm_cpp/spmm.cpp:52-56):
+//     spmm_load_balance(Tensor sparseMat, Tensor denseMat) -> Tensor
+//     spmm_naive(Tensor sparseMat, Tensor denseMat) -> Tensor
+//     create_coo_tensor(Tensor fullrowptr, Tensor rowptr, Tensor colidx, Tensor normfact, int nrows, int ncols) -> Tensor
+// and the same precondition checks (spmm.cpp:10-21: CUDA + coalesced sparse
+// operand, CUDA + contiguous dense operands; colidx deliberately unchecked at
+// spmm.cpp:47 - here it must be int16 or int32).  Differences by design: kernels
+// run on PyTorch's current stream (the reference uses the legacy default stream),
+// nothing synchronises the device, the GIL is released, and CUDA failures raise
+// RuntimeError instead of exit(-1) (cuda_spmm.cu:16-24).
+//
+// Everything below only moves pointers: torch is plumbing (memory, streams).
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <torch/extension.h>
+
+#include <tuple>
+#include <vector>
+
+#include "gnn_b200.h"
+
+namespace {
+
+#define CHECK_CUDA(x) TORCH_CHECK((x).is_cuda(), #x " must be a CUDA tensor")
+#define CHECK_COAL(x) TORCH_CHECK((x).is_coalesced(), #x " must be coalesced")
+#define CHECK_CONTIGUOUS(x) TORCH_CHECK((x).is_contiguous(), #x " must be contiguous")
+#define CHECK_DENSE(x) \
+  CHECK_CUDA(x);       \
+  CHECK_CONTIGUOUS(x)
+#define CHECK_SPARSE(x) \
+  CHECK_CUDA(x);        \
+  CHECK_COAL(x)
+
+inline void check_rc(int rc, const char *what) {
+  TORCH_CHECK(rc == 0, what, " failed: ", gnn_error_string(rc), " (code ", rc, ")");
+}
+
+inline gnn_stream_t cur_stream() { return (gnn_stream_t)c10::cuda::getCurrentCUDAStream().stream(); }
+
+inline torch::Tensor workspace(size_t bytes, const torch::Device &dev) {
+  return torch::empty({(int64_t)bytes}, torch::TensorOptions().dtype(torch::kUInt8).device(dev));
+}
+
+// ---- CSR fast path -------------------------------------------------------
+torch::Tensor csr_spmm(const torch::Tensor &rowptr, const torch::Tensor &colidx, const torch::Tensor &vals, int64_t M,
+                       int64_t K, const torch::Tensor &dense) {
+  CHECK_DENSE(rowptr); CHECK_DENSE(colidx); CHECK_DENSE(vals); CHECK_DENSE(dense);
+  TORCH_CHECK(rowptr.scalar_type() == torch::kInt && colidx.scalar_type() == torch::kInt, "CSR indices must be int32");
+  TORCH_CHECK(vals.scalar_type() == torch::kFloat && dense.scalar_type() == torch::kFloat, "values/dense must be float32");
+  TORCH_CHECK(dense.dim() == 2 && dense.size(0) == K, "dense operand must be [", K, ", D], got ", dense.sizes());
+  TORCH_CHECK(rowptr.numel() == M + 1, "rowptr must have M+1 entries");
+  TORCH_CHECK(vals.device() == dense.device() && rowptr.device() == dense.device() && colidx.device() == dense.device(),
+              "all operands must be on the same device");
+  c10::cuda::CUDAGuard g(dense.device());
+  const int64_t nnz = vals.numel(), D = dense.size(1);
+  auto out = torch::empty({M, D}, dense.options());
+  const size_t wsb = gnn_csr_spmm_workspace_bytes(M, nnz, D);
+  auto ws = workspace(wsb, dense.device());
+  check_rc(gnn_csr_spmm_f32(rowptr.data_ptr<int32_t>(), colidx.data_ptr<int32_t>(), vals.data_ptr<float>(), M, K, nnz, D,
+                            dense.data_ptr<float>(), D, out.data_ptr<float>(), D, ws.data_ptr(), wsb, cur_stream()),
+           "gnn_csr_spmm_f32");
+  return out;
+}
+
+torch::Tensor gather_spmm(const torch::Tensor &rowptr, const torch::Tensor &colidx, const torch::Tensor &vals, int64_t M,
+                          int64_t K, int64_t D, const torch::Tensor &xrows) {
+  CHECK_DENSE(rowptr); CHECK_DENSE(colidx); CHECK_DENSE(vals); CHECK_DENSE(xrows);
+  TORCH_CHECK(xrows.scalar_type() == torch::kLong && xrows.numel() == K, "xrows must be an int64 pointer table of K entries");
+  c10::cuda::CUDAGuard g(vals.device());
+  const int64_t nnz = vals.numel();
+  auto out = torch::empty({M, D}, vals.options());
+  const size_t wsb = gnn_csr_spmm_workspace_bytes(M, nnz, D);
+  auto ws = workspace(wsb, vals.device());
+  check_rc(gnn_gather_spmm_f32(rowptr.data_ptr<int32_t>(), colidx.data_ptr<int32_t>(), vals.data_ptr<float>(), M, K, nnz, D,
+                               reinterpret_cast<const float *const *>(xrows.data_ptr<int64_t>()), out.data_ptr<float>(), D,
+                               ws.data_ptr(), wsb, cur_stream()),
+           "gnn_gather_spmm_f32");
+  return out;
+}
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> csr_transpose(const torch::Tensor &rowptr, const torch::Tensor &colidx,
+                                                                       const torch::Tensor &vals, int64_t M, int64_t K) {
+  CHECK_DENSE(rowptr); CHECK_DENSE(colidx); CHECK_DENSE(vals);
+  c10::cuda::CUDAGuard g(vals.device());
+  const int64_t nnz = vals.numel();
+  auto iopt = rowptr.options();
+  auto t_rowptr = torch::empty({K + 1}, iopt);
+  auto t_colidx = torch::empty({nnz}, iopt);
+  auto t_vals = torch::empty({nnz}, vals.options());
+  const size_t wsb = gnn_csr_transpose_workspace_bytes(M, K, nnz);
+  TORCH_CHECK(wsb <= ((size_t)4 << 30), "gnn_csr_transpose: bitmap workspace of ", wsb, " bytes exceeds the 4 GiB limit");
+  auto ws = workspace(wsb, vals.device());
+  check_rc(gnn_csr_transpose(rowptr.data_ptr<int32_t>(), colidx.data_ptr<int32_t>(), vals.data_ptr<float>(), M, K, nnz,
+                             t_rowptr.data_ptr<int32_t>(), t_colidx.data_ptr<int32_t>(), t_vals.data_ptr<float>(),
+                             ws.data_ptr(), wsb, cur_stream()),
+           "gnn_csr_transpose");
+  return {t_rowptr, t_colidx, t_vals};
+}
+
+std::tuple<torch::Tensor, torch::Tensor> coo_to_csr(const torch::Tensor &sparseMat) {
+  CHECK_SPARSE(sparseMat);
+  TORCH_CHECK(sparseMat.dim() == 2, "sparse operand must be 2-D");
+  c10::cuda::CUDAGuard g(sparseMat.device());
+  auto indices = sparseMat._indices().contiguous();
+  const int64_t M = sparseMat.size(0), nnz = indices.size(1);
+  auto iopt = indices.options().dtype(torch::kInt);
+  auto rowptr = torch::empty({M + 1}, iopt);
+  auto col32 = torch::empty({nnz}, iopt);
+  check_rc(gnn_coo_to_csr(indices.data_ptr<int64_t>(), M, nnz, rowptr.data_ptr<int32_t>(), col32.data_ptr<int32_t>(), cur_stream()),
+           "gnn_coo_to_csr");
+  return {rowptr, col32};
+}
+
+// ---- reference-named entry points ---------------------------------------
+torch::Tensor spmm_load_balance(const torch::Tensor &sparseMat, const torch::Tensor &denseMat) {
+  CHECK_SPARSE(sparseMat);
+  CHECK_DENSE(denseMat);
+  auto csr = coo_to_csr(sparseMat);
+  auto vals = sparseMat._values().contiguous();
+  return csr_spmm(std::get<0>(csr), std::get<1>(csr), vals, sparseMat.size(0), sparseMat.size(1), denseMat);
+}
+
+torch::Tensor spmm_naive(const torch::Tensor &sparseMat, const torch::Tensor &denseMat) {
+  // the reference's v1 differs from v2 only in scheduling; one deterministic kernel serves both names
+  return spmm_load_balance(sparseMat, denseMat);
+}
+
+std::tuple<torch::Tensor, torch::Tensor> build_adj(const torch::Tensor &fullrowptr, const torch::Tensor &rowptr,
+                                                   const torch::Tensor &colidx, const torch::Tensor &normfact, int64_t nrows,
+                                                   int64_t ncols) {
+  CHECK_DENSE(fullrowptr);
+  CHECK_DENSE(rowptr);
+  CHECK_DENSE(colidx);
+  CHECK_DENSE(normfact);
+  TORCH_CHECK(fullrowptr.scalar_type() == torch::kInt && rowptr.scalar_type() == torch::kInt, "row pointers must be int32");
+  TORCH_CHECK(colidx.scalar_type() == torch::kShort || colidx.scalar_type() == torch::kInt, "colidx must be int16 or int32");
+  TORCH_CHECK(normfact.scalar_type() == torch::kFloat, "normfact must be float32");
+  TORCH_CHECK(rowptr.numel() == nrows + 1 && fullrowptr.numel() == nrows + 1, "row pointers must have nrows+1 entries");
+  TORCH_CHECK(normfact.numel() >= ncols, "normfact must have ncols entries");
+  TORCH_CHECK(colidx.scalar_type() != torch::kShort || ncols <= 32768, "int16 colidx cannot address ", ncols, " columns");
+  c10::cuda::CUDAGuard g(colidx.device());
+  const int64_t nnz = colidx.numel();
+  auto indices = torch::empty({2, nnz}, colidx.options().dtype(torch::kLong));
+  auto values = torch::empty({nnz}, normfact.options());
+  auto col32 = torch::empty({nnz}, colidx.options().dtype(torch::kInt));
+  check_rc(gnn_build_adj(fullrowptr.data_ptr<int32_t>(), rowptr.data_ptr<int32_t>(), colidx.data_ptr(),
+                         colidx.scalar_type() == torch::kShort ? 2 : 4, normfact.data_ptr<float>(), nrows, ncols, nnz,
+                         indices.data_ptr<int64_t>(), values.data_ptr<float>(), col32.data_ptr<int32_t>(), cur_stream()),
+           "gnn_build_adj");
+  // rows ascending, columns ascending and unique inside a row: already coalesced (no sort, cuda_spmm.cu:825)
+  auto coo = at::_sparse_coo_tensor_unsafe(indices, values, {nrows, ncols}, values.options().layout(torch::kSparse),
+                                           /*is_coalesced=*/true);
+  return {coo, col32};
+}
+
+torch::Tensor create_coo_tensor(const torch::Tensor &fullrowptr, const torch::Tensor &rowptr, const torch::Tensor &colidx,
+                                const torch::Tensor &normfact, int64_t nrows, int64_t ncols) {
+  return std::get<0>(build_adj(fullrowptr, rowptr, colidx, normfact, nrows, ncols));
+}
+
+// ---- gather path ----------------------------------------------------------
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> placement_remap(
+    const torch::Tensor &input_nodes, const torch::Tensor &device_id_of_nodes, const torch::Tensor &idx_of_nodes_on_device,
+    const torch::Tensor &devices, const torch::Tensor &bases, int64_t ld_src) {
+  CHECK_DENSE(input_nodes); CHECK_DENSE(device_id_of_nodes); CHECK_DENSE(idx_of_nodes_on_device); CHECK_DENSE(devices);
+  CHECK_DENSE(bases);
+  TORCH_CHECK(input_nodes.scalar_type() == torch::kLong && device_id_of_nodes.scalar_type() == torch::kLong &&
+                  idx_of_nodes_on_device.scalar_type() == torch::kLong && devices.scalar_type() == torch::kLong &&
+                  bases.scalar_type() == torch::kLong,
+              "placement tables must be int64");
+  const int64_t world = devices.numel(), n0 = input_nodes.numel();
+  TORCH_CHECK(bases.numel() == world + 1, "bases must hold world+1 pointers (last = host table)");
+  c10::cuda::CUDAGuard g(input_nodes.device());
+  auto src_dev = torch::empty({n0}, input_nodes.options().dtype(torch::kInt));
+  auto slot = torch::empty({n0}, input_nodes.options());
+  auto xrows = torch::empty({n0}, input_nodes.options());
+  auto counts = torch::empty({world + 2}, input_nodes.options());
+  check_rc(gnn_placement_remap(input_nodes.data_ptr<int64_t>(), n0, device_id_of_nodes.data_ptr<int64_t>(),
+                               idx_of_nodes_on_device.data_ptr<int64_t>(), devices.data_ptr<int64_t>(), world,
+                               reinterpret_cast<const float *const *>(bases.data_ptr<int64_t>()), ld_src,
+                               src_dev.data_ptr<int32_t>(), slot.data_ptr<int64_t>(),
+                               reinterpret_cast<const float **>(xrows.data_ptr<int64_t>()), counts.data_ptr<int64_t>(),
+                               cur_stream()),
+           "gnn_placement_remap");
+  return {src_dev, slot, xrows, counts};
+}
+
+torch::Tensor gather_rows(const torch::Tensor &xrows, int64_t F, int64_t ld_out) {
+  CHECK_DENSE(xrows);
+  TORCH_CHECK(xrows.scalar_type() == torch::kLong, "xrows must be an int64 pointer table");
+  TORCH_CHECK(ld_out >= F, "ld_out must be >= F");
+  c10::cuda::CUDAGuard g(xrows.device());
+  const int64_t n0 = xrows.numel();
+  auto buf = torch::empty({n0, ld_out}, xrows.options().dtype(torch::kFloat));
+  check_rc(gnn_gather_rows_f32(reinterpret_cast<const float *const *>(xrows.data_ptr<int64_t>()), n0, F, buf.data_ptr<float>(),
+                               ld_out, cur_stream()),
+           "gnn_gather_rows_f32");
+  return ld_out == F ? buf : buf.narrow(1, 0, F);
+}
+
+void gather_rows_src(const torch::Tensor &xrows, const torch::Tensor &src_dev, int64_t only_src, int64_t F, torch::Tensor out) {
+  CHECK_DENSE(xrows); CHECK_DENSE(src_dev); CHECK_CUDA(out);
+  TORCH_CHECK(out.dim() == 2 && out.stride(1) == 1 && out.size(1) >= F && out.size(0) == xrows.numel(), "bad output buffer");
+  c10::cuda::CUDAGuard g(xrows.device());
+  check_rc(gnn_gather_rows_src_f32(reinterpret_cast<const float *const *>(xrows.data_ptr<int64_t>()), src_dev.data_ptr<int32_t>(),
+                                   (int32_t)only_src, xrows.numel(), F, out.data_ptr<float>(), out.stride(0), cur_stream()),
+           "gnn_gather_rows_src_f32");
+}
+
+torch::Tensor index_rows(const torch::Tensor &X, const torch::Tensor &idx) {
+  CHECK_CUDA(X); CHECK_DENSE(idx);
+  TORCH_CHECK(X.dim() == 2 && X.stride(1) == 1 && X.scalar_type() == torch::kFloat, "X must be a row-major float32 matrix");
+  TORCH_CHECK(idx.scalar_type() == torch::kLong, "idx must be int64");
+  c10::cuda::CUDAGuard g(X.device());
+  auto out = torch::empty({idx.numel(), X.size(1)}, X.options());
+  check_rc(gnn_index_rows_f32(X.data_ptr<float>(), X.stride(0), idx.data_ptr<int64_t>(), idx.numel(), X.size(1),
+                              out.data_ptr<float>(), X.size(1), cur_stream()),
+           "gnn_index_rows_f32");
+  return out;
+}
+
+// ---- peer-mappable feature shards ---------------------------------------
+std::tuple<torch::Tensor, py::bytes> shard_alloc(int64_t rows, int64_t ld, int64_t device_index) {
+  c10::cuda::CUDAGuard g(c10::Device(c10::kCUDA, (c10::DeviceIndex)device_index));
+  void *p = nullptr;
+  unsigned char h[64];
+  check_rc(gnn_shard_alloc((size_t)rows * ld * sizeof(float), &p, h), "gnn_shard_alloc");
+  auto t = torch::from_blob(p, {rows, ld}, [](void *q) { gnn_shard_free(q); },
+                            torch::TensorOptions().dtype(torch::kFloat).device(torch::kCUDA, device_index));
+  py::gil_scoped_acquire acq;
+  return {t, py::bytes(reinterpret_cast<const char *>(h), 64)};
+}
+
+torch::Tensor shard_open(const std::string &handle, int64_t rows, int64_t ld, int64_t device_index) {
+  TORCH_CHECK(handle.size() == 64, "IPC handle must be 64 bytes");
+  c10::cuda::CUDAGuard g(c10::Device(c10::kCUDA, (c10::DeviceIndex)device_index));
+  void *p = nullptr;
+  check_rc(gnn_shard_open(reinterpret_cast<const unsigned char *>(handle.data()), &p), "gnn_shard_open");
+  return torch::from_blob(p, {rows, ld}, [](void *q) { gnn_shard_close(q); },
+                          torch::TensorOptions().dtype(torch::kFloat).device(torch::kCUDA, device_index));
+}
+
+int64_t host_register(const torch::Tensor &host) {
+  TORCH_CHECK(!host.is_cuda() && host.is_contiguous(), "host table must be a contiguous CPU tensor");
+  void *alias = nullptr;
+  check_rc(gnn_host_register(host.data_ptr(), (size_t)host.numel() * host.element_size(), &alias), "gnn_host_register");
+  return (int64_t)reinterpret_cast<uintptr_t>(alias);
+}
+
+void host_unregister(const torch::Tensor &host) { check_rc(gnn_host_unregister(host.data_ptr()), "gnn_host_unregister"); }
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  using rel = py::call_guard<py::gil_scoped_release>;
+  // reference names (spmm.cpp:52-56)
+  m.def("spmm_naive", &spmm_naive, "Sparse-Dense Matrix Multiplication", rel());
+  m.def("spmm_load_balance", &spmm_load_balance, "Sparse-Dense Matrix Multiplication", rel());
+  m.def("create_coo_tensor", &create_coo_tensor, "Create a PyTorch sparse tensor", rel());
+  // B200 path
+  m.def("build_adj", &build_adj, "create_coo_tensor that also returns the int32 column ids (CSR for the kernels)", rel());
+  m.def("coo_to_csr", &coo_to_csr, "coalesced COO -> (rowptr int32, colidx int32)", rel());
+  m.def("csr_spmm", &csr_spmm, "Y = A.X with A in CSR", rel());
+  m.def("csr_transpose", &csr_transpose, "CSR of A^T, deterministic", rel());
+  m.def("gather_spmm", &gather_spmm, "Y = A.gather(xrows) without materialising the gathered rows", rel());
+  m.def("placement_remap", &placement_remap, "device placement remap -> (src_dev, slot, xrows, counts)", rel());
+  m.def("gather_rows", &gather_rows, "out[j] = *xrows[j]", rel());
+  m.def("gather_rows_src", &gather_rows_src, "gather only the rows of one source", rel());
+  m.def("index_rows", &index_rows, "out[i] = X[idx[i]]", rel());
+  m.def("shard_alloc", &shard_alloc, "peer-mappable feature shard + IPC handle", rel());
+  m.def("shard_open", &shard_open, "map a peer's shard", rel());
+  m.def("host_register", &host_register, "pin+map a host table, returns the device alias", rel());
+  m.def("host_unregister", &host_unregister, rel());
+  m.def("launch_count", []() { return gnn_launch_count(); });
+  m.def("abi_version", []() { return gnn_abi_version(); });
+}

@@ -1,0 +1,200 @@
+/*
+ * gnn_b200.h - C ABI of the B200-native LADIES-layer SpMM / feature-gather path.
+ *
+ * Drop-in boundary for HPC-Research-Lab/GNN's `spmm_cpp` extension and the
+ * gather block of its training loop.  Every entry point takes plain device (or
+ * mapped host / peer) pointers, sizes, leading dimensions in ELEMENTS and a
+ * cudaStream_t passed as void*; there are no torch types here.  All functions
+ * are asynchronous on `stream`, never synchronise the device, never allocate,
+ * and are re-entrant (the reference is entered concurrently from trainer and
+ * sampler threads).  The current device must be the one
+ * that owns the output buffers.
+ *
+ * Return value: 0 on success; a positive cudaError_t value if the CUDA runtime
+ * reported an error; a negative GNN_E_* code for argument errors.  The reference
+ * calls exit(-1) on CUDA errors (cuda_spmm.cu:16-24); this library returns.
+ *
+ * Reference interface replaced by each function is cited as file:line relative
+ * to the reference repository.
+ */
+#ifndef GNN_B200_H_
+#define GNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNN_B200_ABI_VERSION 1
+
+#define GNN_E_BADARG   (-1)   /* null pointer, negative size, unsupported width */
+#define GNN_E_WORKSPACE (-2)  /* workspace missing or too small */
+#define GNN_E_RANGE    (-3)   /* size exceeds the 32-bit index limits of the path */
+
+typedef void *gnn_stream_t;   /* cudaStream_t */
+
+/* ABI version of the loaded library (GNN_B200_ABI_VERSION at build time). */
+int gnn_abi_version(void);
+
+/* Human-readable text for a return code of this library. */
+const char *gnn_error_string(int code);
+
+/* Number of kernels this library has launched in the calling process so far
+ * (all threads; used by bench.py for its `gpu_launches` claim). */
+int64_t gnn_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * gnn_build_adj - sampled CSR + LADIES weights -> COO (API) + CSR (kernels).
+ *
+ * Replaces create_coo_tensor: spmm_cpp/spmm.cpp:44-50, cuda_spmm.cu:787-827
+ * (called from sampler.py:139).  For every stored entry i of row r:
+ *     out_indices[0*nnz + i] = r
+ *     out_indices[1*nnz + i] = colidx[i]                 (widened to int64)
+ *     out_vals[i] = (float)( (1.0 / (double)(fullrowptr[r+1]-fullrowptr[r]))
+ *                            * (double)normfact[colidx[i]] )      (cuda_spmm.cu:800)
+ *     out_colidx32[i] = colidx[i]                        (int32 copy for the SpMM kernels)
+ * colidx is int16 when colidx_bytes == 2 (what sampler.py:136 uploads; read as
+ * signed 16-bit exactly like cuda_spmm.cu:792) or int32 when colidx_bytes == 4.
+ * out_indices and out_colidx32 may each be NULL to skip that output.
+ * Rows are already sorted and (row,col) pairs unique, so the result is coalesced
+ * without the reference's trailing .coalesce() (cuda_spmm.cu:825).
+ * ------------------------------------------------------------------------- */
+int gnn_build_adj(const int32_t *fullrowptr, const int32_t *rowptr, const void *colidx, int colidx_bytes,
+                  const float *normfact, int64_t M, int64_t K, int64_t nnz,
+                  int64_t *out_indices, float *out_vals, int32_t *out_colidx32, gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * gnn_coo_to_csr - coalesced COO (int64 [2,nnz], row-major sorted) -> CSR int32.
+ *
+ * Replaces the per-call COO->CSR rebuild of spmm_cuda_v2: the int64->int32 casts
+ * (cuda_spmm.cu:620-621) and _calc_rowptr (cuda_spmm.cu:255-265).  Used only for
+ * sparse tensors that were not produced by gnn_build_adj.
+ * ------------------------------------------------------------------------- */
+int gnn_coo_to_csr(const int64_t *indices, int64_t M, int64_t nnz,
+                   int32_t *out_rowptr, int32_t *out_colidx32, gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * gnn_csr_spmm_f32 - Y[M,D] = A[M,K] . X[K,D], fp32, A in CSR.
+ *
+ * Replaces spmm_load_balance / spmm_naive: spmm.cpp:23-27,38-42 ->
+ * spmm_cuda_v2 / spmm_cuda_v1, cuda_spmm.cu:619-704 / :134-160 (forward of
+ * custom_sparse_ops.py:16-28).  Every row of Y is written (empty rows get zeros,
+ * matching the zero-initialised output of cuda_spmm.cu:626).  Rows longer than
+ * the internal chunk size are summed by a fixed-order two-level reduction, so
+ * results are bit-reproducible run to run (the reference's atomicAdd order,
+ * cuda_spmm.cu:205-209, is not).
+ *
+ * workspace: gnn_csr_spmm_workspace_bytes(M, nnz, D) bytes of device memory,
+ * contents undefined on entry, private to this call until it completes.
+ * ------------------------------------------------------------------------- */
+size_t gnn_csr_spmm_workspace_bytes(int64_t M, int64_t nnz, int64_t D);
+
+int gnn_csr_spmm_f32(const int32_t *rowptr, const int32_t *colidx, const float *vals,
+                     int64_t M, int64_t K, int64_t nnz, int64_t D,
+                     const float *X, int64_t ldx, float *Y, int64_t ldy,
+                     void *workspace, size_t workspace_bytes, gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * gnn_gather_spmm_f32 - fused input-feature gather + SpMM for the deepest layer:
+ *     Y[M,D] = A[M,K] . Xg,   Xg[j,:] = *(xrows[j])   (row j never materialised)
+ *
+ * Replaces main.py:129-134 followed by the first spmm of models.py:18 / :60.
+ * xrows[j] points at the feature row of input node j wherever the placement put
+ * it (local HBM, a peer GPU's shard mapped over NVLink, or mapped pinned host
+ * memory); build it with gnn_placement_remap.  Every A nonzero reads its X row
+ * through the table, so use this only when rows are local or nnz/K is small;
+ * otherwise stage with gnn_gather_rows_f32 first.
+ * ------------------------------------------------------------------------- */
+int gnn_gather_spmm_f32(const int32_t *rowptr, const int32_t *colidx, const float *vals,
+                        int64_t M, int64_t K, int64_t nnz, int64_t D,
+                        const float *const *xrows, float *Y, int64_t ldy,
+                        void *workspace, size_t workspace_bytes, gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * gnn_csr_transpose - CSR of A^T (entries of each output row in ascending source
+ * row) built on the device, once per adjacency.
+ *
+ * Replaces mat1.transpose(0,1).coalesce() of every backward call,
+ * custom_sparse_ops.py:34 (an index swap plus a full sort of nnz keys).
+ * The backward product dX = A^T.G is then gnn_csr_spmm_f32 on the result.
+ * Deterministic: no atomics decide the order.
+ *
+ * workspace: gnn_csr_transpose_workspace_bytes(M, K, nnz) bytes.
+ * ------------------------------------------------------------------------- */
+size_t gnn_csr_transpose_workspace_bytes(int64_t M, int64_t K, int64_t nnz);
+
+int gnn_csr_transpose(const int32_t *rowptr, const int32_t *colidx, const float *vals,
+                      int64_t M, int64_t K, int64_t nnz,
+                      int32_t *t_rowptr, int32_t *t_colidx, float *t_vals,
+                      void *workspace, size_t workspace_bytes, gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * gnn_placement_remap - per-minibatch placement remap on the device.
+ *
+ * Replaces sampler.py:150-158 (device_id_of_nodes[previous_nodes], one boolean
+ * mask and one slot list per source device, host mask + ids).  For input node j:
+ *     dev = device_id_of_nodes[input_nodes[j]]
+ *     dev == -1          -> src_dev[j] = -1, slot[j] = input_nodes[j]      (host table row)
+ *     dev == devices[i]  -> src_dev[j] =  i, slot[j] = idx_of_nodes_on_device[input_nodes[j]]
+ *     otherwise          -> src_dev[j] = -2, slot[j] = -1
+ * and, when xrows != NULL,
+ *     xrows[j] = bases[i] + slot[j]*ld_src     (bases[world] is the host table)
+ * or NULL for src_dev -2.  The tables are the per-rank views produced by
+ * create_buffer (preprocess.py:311-407), resident on the device as int64.
+ * counts (optional, int64 [world+2], zeroed by this call) receives the number of
+ * rows per source: counts[i] for GPU i, counts[world] host, counts[world+1] invalid.
+ * ------------------------------------------------------------------------- */
+int gnn_placement_remap(const int64_t *input_nodes, int64_t n0,
+                        const int64_t *device_id_of_nodes, const int64_t *idx_of_nodes_on_device,
+                        const int64_t *devices, int64_t world,
+                        const float *const *bases, int64_t ld_src,
+                        int32_t *src_dev, int64_t *slot, const float **xrows, int64_t *counts,
+                        gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * gnn_gather_rows_f32 - out[j, 0:F] = xrows[j][0:F] for j in [0,n0), bit-exact.
+ *
+ * Replaces the gather block main.py:129-134 (and its copies :185-190, :228-233):
+ * per source device a gather kernel on the *remote* GPU, a peer copy and a
+ * boolean-mask index_put, plus a CPU gather + synchronous H2D for host rows.
+ * Here one kernel on the consuming GPU pulls every row once through its pointer
+ * (local HBM, peer over NVLink, mapped pinned host).  Rows with a NULL pointer
+ * are left untouched.
+ * ------------------------------------------------------------------------- */
+int gnn_gather_rows_f32(const float *const *xrows, int64_t n0, int64_t F,
+                        float *out, int64_t ld_out, gnn_stream_t stream);
+
+/* Same gather restricted to the rows j with src_dev[j] == only_src (e.g. only peer
+ * rows), so transfers from different sources can be put on different streams. */
+int gnn_gather_rows_src_f32(const float *const *xrows, const int32_t *src_dev, int32_t only_src,
+                            int64_t n0, int64_t F, float *out, int64_t ld_out, gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * gnn_index_rows_f32 - out[i, 0:F] = X[idx[i], 0:F]  (the x[sampled_nodes] gather of
+ * models.py:19, with the int64 row-index remap of sampler.py:143 resident on device).
+ * ------------------------------------------------------------------------- */
+int gnn_index_rows_f32(const float *X, int64_t ldx, const int64_t *idx, int64_t n, int64_t F,
+                       float *out, int64_t ld_out, gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Feature-shard memory that peers can map (one process per GPU).
+ *
+ * gnn_shard_alloc   : cudaMalloc'd buffer + its 64-byte IPC handle.
+ * gnn_shard_open    : map a peer process's shard into this process (NVLink P2P).
+ * gnn_shard_close   : unmap.   gnn_shard_free : free the local buffer.
+ * gnn_host_register : pin + map an existing host buffer; returns its device alias
+ *                     (zero-copy reads over PCIe for uncached rows, main.py:134).
+ * ------------------------------------------------------------------------- */
+int gnn_shard_alloc(size_t bytes, void **dev_ptr, unsigned char ipc_handle[64]);
+int gnn_shard_open(const unsigned char ipc_handle[64], void **dev_ptr);
+int gnn_shard_close(void *dev_ptr);
+int gnn_shard_free(void *dev_ptr);
+int gnn_host_register(void *host_ptr, size_t bytes, void **dev_alias);
+int gnn_host_unregister(void *host_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNN_B200_H_ */

@@ -1,0 +1,118 @@
+"""GPU tests of the reference-facing Python API (custom_sparse_ops) - read like the tests the
+reference never shipped: create_coo_tensor -> spmm -> autograd backward, on sampler output."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from gnn_b200 import graphgen, sampler
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def cso():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import custom_sparse_ops
+    return custom_sparse_ops
+
+
+@pytest.fixture(scope="module")
+def mb():
+    shape = graphgen.SHAPES["small"]
+    g = graphgen.generate(shape, seed=0)
+    return sampler.ladies_sample(99, g.train_nodes[:128], [1024] * 3, shape.num_nodes, g.indptr, g.indices, [1, 1, 1])
+
+
+def _upload(layer, dev="cuda"):
+    return (torch.from_numpy(layer.fullrowptr).to(dev), torch.from_numpy(layer.rowptr).to(dev),
+            torch.from_numpy(layer.colidx).to(dev), torch.from_numpy(layer.normfact).to(dev), layer.nrows, layer.ncols)
+
+
+def test_create_coo_tensor_contract(cso, mb):
+    for layer in mb.layers:
+        a = cso.create_coo_tensor(*_upload(layer))
+        assert a.is_sparse and a.is_cuda and a.is_coalesced()
+        assert tuple(a.shape) == (layer.nrows, layer.ncols)
+        assert a._indices().dtype == torch.int64 and a._values().dtype == torch.float32
+        rows, cols, vals = oracle.build_adj(layer.fullrowptr, layer.rowptr, layer.colidx, layer.normfact, layer.nrows)
+        assert np.array_equal(a._indices().cpu().numpy(), np.stack([rows, cols]))
+        assert np.array_equal(a._values().cpu().numpy().view(np.uint32), vals.view(np.uint32))
+        # the raw extension entry point keeps the reference signature and result
+        b = cso.spmm_cpp.create_coo_tensor(*_upload(layer))
+        assert torch.equal(b._indices(), a._indices()) and torch.equal(b._values(), a._values())
+        # coalesce() of an already coalesced tensor is the identity, as the reference relies on
+        assert torch.equal(a.coalesce()._values(), a._values())
+        # dense view agrees with torch's own interpretation of the COO tensor
+        if layer.nrows * layer.ncols < 4_000_000:
+            dense = torch.zeros(layer.nrows, layer.ncols, device="cuda")
+            dense[a._indices()[0], a._indices()[1]] = a._values()
+            assert torch.equal(a.to_dense(), dense)
+
+
+@pytest.mark.parametrize("D", [602, 128, 33])
+def test_spmm_autograd_matches_oracle_and_torch_sparse(cso, mb, D):
+    rng = np.random.Generator(np.random.PCG64(D))
+    for layer in mb.layers:
+        a = cso.create_coo_tensor(*_upload(layer))
+        X = rng.standard_normal((layer.ncols, D)).astype(np.float32)
+        G = rng.standard_normal((layer.nrows, D)).astype(np.float32)
+        x = torch.from_numpy(X).cuda().requires_grad_(True)
+        y = cso.spmm(a, x)
+        y.backward(torch.from_numpy(G).cuda())
+        _, _, vals = oracle.build_adj(layer.fullrowptr, layer.rowptr, layer.colidx, layer.normfact, layer.nrows)
+        yref = oracle.spmm_f64acc(layer.rowptr, layer.colidx32, vals, layer.nrows, X)
+        gref = oracle.spmm_t_f64acc(layer.rowptr, layer.colidx32, vals, layer.nrows, layer.ncols, G)
+        assert oracle.rel_err(y.detach().cpu().numpy(), yref)[0] <= TOL
+        assert oracle.rel_err(x.grad.cpu().numpy(), gref)[0] <= TOL
+        # torch.sparse on the same tensor (the reference's commented alternative, custom_sparse_ops.py:25,36)
+        x2 = torch.from_numpy(X).cuda().requires_grad_(True)
+        y2 = torch.sparse.mm(a, x2)
+        y2.backward(torch.from_numpy(G).cuda())
+        assert oracle.rel_err(y.detach().cpu().numpy(), y2.detach().double().cpu().numpy())[0] <= 1e-4
+        assert oracle.rel_err(x.grad.cpu().numpy(), x2.grad.double().cpu().numpy())[0] <= 1e-4
+
+
+def test_foreign_coo_and_reference_entry_points(cso, mb):
+    layer = mb.layers[1]
+    rows, cols, vals = oracle.build_adj(layer.fullrowptr, layer.rowptr, layer.colidx, layer.normfact, layer.nrows)
+    a = torch.sparse_coo_tensor(torch.from_numpy(np.stack([rows, cols])), torch.from_numpy(vals),
+                                (layer.nrows, layer.ncols)).cuda().coalesce()
+    X = torch.randn(layer.ncols, 96, device="cuda")
+    yref = oracle.spmm_f64acc(layer.rowptr, layer.colidx32, vals, layer.nrows, X.cpu().numpy())
+    for fn in (cso.spmm_cpp.spmm_load_balance, cso.spmm_cpp.spmm_naive, cso.spmm):
+        assert oracle.rel_err(fn(a, X).cpu().numpy(), yref)[0] <= TOL
+    # the reference's backward expression works unchanged on the extension (custom_sparse_ops.py:34)
+    G = torch.randn(layer.nrows, 96, device="cuda")
+    dx = cso.spmm_cpp.spmm_load_balance(a.transpose(0, 1).coalesce(), G.contiguous())
+    gref = oracle.spmm_t_f64acc(layer.rowptr, layer.colidx32, vals, layer.nrows, layer.ncols, G.cpu().numpy())
+    assert oracle.rel_err(dx.cpu().numpy(), gref)[0] <= TOL
+
+
+def test_preconditions_raise(cso, mb):
+    layer = mb.layers[2]
+    a = cso.create_coo_tensor(*_upload(layer))
+    X = torch.randn(layer.ncols, 64, device="cuda")
+    with pytest.raises(RuntimeError):
+        cso.spmm(a, X.t().contiguous().t())                       # not contiguous (spmm.cpp:14-15)
+    with pytest.raises(RuntimeError):
+        cso.spmm(a, X.cpu())                                      # not CUDA (spmm.cpp:10-11)
+    unco = torch.sparse_coo_tensor(torch.tensor([[0, 0], [1, 1]]), torch.ones(2), (2, 2)).cuda()
+    with pytest.raises(RuntimeError):
+        cso.spmm_cpp.spmm_load_balance(unco, torch.ones(2, 2, device="cuda"))   # not coalesced (spmm.cpp:12-13)
+    with pytest.raises(RuntimeError):
+        cso.spmm(a, torch.randn(layer.ncols + 1, 8, device="cuda"))            # shape mismatch
+
+
+def test_gcn_style_two_layer_grad_flow(cso, mb):
+    """models.py:60-64 shape of use: spmm -> linear -> spmm, gradients reach the first weight."""
+    l0, l1 = mb.layers[0], mb.layers[1]
+    a0, a1 = cso.create_coo_tensor(*_upload(l0)), cso.create_coo_tensor(*_upload(l1))
+    lin = torch.nn.Linear(100, 32).cuda()
+    x = torch.randn(l0.ncols, 100, device="cuda")
+    h = torch.nn.functional.elu(lin(cso.spmm(a0, x)))
+    out = cso.spmm(a1, h)
+    out.square().mean().backward()
+    assert lin.weight.grad is not None and torch.isfinite(lin.weight.grad).all() and lin.weight.grad.abs().sum() > 0

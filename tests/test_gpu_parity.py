@@ -1,0 +1,297 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star): indices / remaps / gathers bit-exact; fp32 SpMM
+outputs and gradients within 1e-5 relative of the fp64-accumulated product
+(worst row, L2).  Differences below that are summation order: the kernel adds a
+row's terms lane-strided and chunk-wise in a fixed order, the oracle sequentially.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from gnn_b200 import graphgen, sampler
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+WIDTHS = [1, 3, 16, 32, 64, 100, 128, 256, 512, 602, 1024, 1433]
+
+
+@pytest.fixture(scope="module")
+def cu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tests import cabi_util
+    return cabi_util
+
+
+def _golden_layers(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    out = []
+    for si in range(len(z["seeds"])):
+        for li in range(int(z[f"s{si}_nlayers"])):
+            lp = f"s{si}_l{li}_"
+            if lp + "none" in z.files:
+                continue
+            out.append({k: z[lp + k] for k in ["fullrowptr", "rowptr", "colidx", "normfact", "values", "x", "g",
+                                               "y_torchsparse", "dx_torchsparse"]}
+                       | {"nrows": int(z[lp + "nrows"]), "ncols": int(z[lp + "ncols"])})
+    return out
+
+
+@pytest.fixture(scope="module")
+def small_mb():
+    shape = graphgen.SHAPES["small"]
+    g = graphgen.generate(shape, seed=0)
+    mb = sampler.ladies_sample(4321, g.train_nodes[:256], [2048] * 3, shape.num_nodes, g.indptr, g.indices, [1, 1, 1])
+    return shape, g, mb
+
+
+def _layer_csr(layer):
+    rows, cols, vals = oracle.build_adj(layer.fullrowptr, layer.rowptr, layer.colidx32, layer.normfact, layer.nrows)
+    return layer.rowptr, layer.colidx32, vals
+
+
+# --------------------------------------------------------------------------- build_adj
+@pytest.mark.parametrize("name", ["cora_gcn", "tiny_sage3", "tiny_order0"])
+def test_build_adj_bit_exact(cu, golden_dir, name):
+    for L in _golden_layers(golden_dir, name):
+        idx, vals, col32 = cu.build_adj(cu.dev(L["fullrowptr"]), cu.dev(L["rowptr"]), cu.dev(L["colidx"]), cu.dev(L["normfact"]),
+                                        L["nrows"], L["ncols"])
+        rows, cols, ovals = oracle.build_adj(L["fullrowptr"], L["rowptr"], L["colidx"], L["normfact"], L["nrows"])
+        assert np.array_equal(idx[0].cpu().numpy(), rows)
+        assert np.array_equal(idx[1].cpu().numpy(), cols)
+        assert np.array_equal(col32.cpu().numpy(), cols.astype(np.int32))
+        got = vals.cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), ovals.view(np.uint32)), "values not bit-exact vs oracle"
+        assert np.array_equal(got.view(np.uint32), L["values"].view(np.uint32)), "values not bit-exact vs golden"
+
+
+def test_build_adj_int32_and_empty(cu, small_mb):
+    _, _, mb = small_mb
+    layer = mb.layers[0]
+    idx, vals, col32 = cu.build_adj(cu.dev(layer.fullrowptr), cu.dev(layer.rowptr), cu.dev(layer.colidx32), cu.dev(layer.normfact),
+                                    layer.nrows, layer.ncols)
+    rows, cols, ovals = oracle.build_adj(layer.fullrowptr, layer.rowptr, layer.colidx32, layer.normfact, layer.nrows)
+    assert np.array_equal(idx.cpu().numpy(), np.stack([rows, cols]))
+    assert np.array_equal(vals.cpu().numpy().view(np.uint32), ovals.view(np.uint32))
+    # int16 and int32 column ids give the same adjacency
+    idx16, vals16, _ = cu.build_adj(cu.dev(layer.fullrowptr), cu.dev(layer.rowptr), cu.dev(layer.colidx), cu.dev(layer.normfact),
+                                    layer.nrows, layer.ncols)
+    assert torch.equal(idx16, idx) and torch.equal(vals16, vals)
+    # nnz == 0
+    z = torch.zeros(5, dtype=torch.int32, device="cuda")
+    i0, v0, c0 = cu.build_adj(z, z, torch.zeros(0, dtype=torch.int16, device="cuda"), torch.ones(3, device="cuda"), 4, 3)
+    assert i0.shape == (2, 0) and v0.numel() == 0
+
+
+# --------------------------------------------------------------------------- forward SpMM
+@pytest.mark.parametrize("name", ["cora_gcn", "tiny_sage3"])
+def test_spmm_golden(cu, golden_dir, name):
+    for L in _golden_layers(golden_dir, name):
+        rowptr, col32, vals = L["rowptr"], L["colidx"].astype(np.int32), L["values"]
+        Y = cu.csr_spmm(cu.dev(rowptr), cu.dev(col32), cu.dev(vals), L["nrows"], L["ncols"], cu.dev(L["x"])).cpu().numpy()
+        ref = oracle.spmm_f64acc(rowptr, col32, vals, L["nrows"], L["x"])
+        err, _ = oracle.rel_err(Y, ref)
+        assert err <= TOL, err
+        # the reference's own CPU alternative (torch.sparse, custom_sparse_ops.py:25) is a tolerance-level oracle
+        err_ts, _ = oracle.rel_err(Y, L["y_torchsparse"])
+        assert err_ts <= 1e-4, err_ts
+
+
+@pytest.mark.parametrize("D", WIDTHS)
+def test_spmm_width_sweep(cu, small_mb, D):
+    _, _, mb = small_mb
+    rng = np.random.Generator(np.random.PCG64(D))
+    for li, layer in enumerate(mb.layers):
+        rowptr, col32, vals = _layer_csr(layer)
+        X = rng.standard_normal((layer.ncols, D)).astype(np.float32)
+        d_rowptr, d_col, d_vals, d_X = cu.dev(rowptr), cu.dev(col32), cu.dev(vals), cu.dev(X)
+        Y = cu.csr_spmm(d_rowptr, d_col, d_vals, layer.nrows, layer.ncols, d_X)
+        ref = oracle.spmm_f64acc(rowptr, col32, vals, layer.nrows, X)
+        err, maxerr = oracle.rel_err(Y.cpu().numpy(), ref)
+        assert err <= TOL, (li, D, err, maxerr)
+        Y2 = cu.csr_spmm(d_rowptr, d_col, d_vals, layer.nrows, layer.ncols, d_X)
+        assert torch.equal(Y, Y2), "not bit-reproducible"
+
+
+def _random_csr(rng, M, K, row_lens):
+    rowptr = np.zeros(M + 1, np.int32)
+    rowptr[1:] = np.cumsum(row_lens)
+    cols = np.concatenate([np.sort(rng.choice(K, n, replace=False)) for n in row_lens] + [np.empty(0, np.int64)]).astype(np.int32)
+    vals = rng.standard_normal(cols.size).astype(np.float32)
+    return rowptr, cols, vals
+
+
+@pytest.mark.parametrize("D,pad", [(8, 0), (64, 0), (130, 2), (602, 2), (257, 7), (1024, 0)])
+def test_spmm_ragged_empty_long_rows(cu, D, pad):
+    rng = np.random.Generator(np.random.PCG64(7 + D))
+    M, K = 300, 9000
+    lens = rng.integers(0, 40, M)
+    lens[[0, 1, 2]] = 0              # leading empty rows
+    lens[[50, 51]] = 0               # empty rows in the middle
+    lens[-3:] = 0                    # trailing empty rows
+    lens[7] = 8000                   # one row spanning many chunks
+    lens[120] = 3000
+    lens[121] = 2049
+    rowptr, cols, vals = _random_csr(rng, M, K, lens)
+    ldx = D + pad
+    Xfull = rng.standard_normal((K, ldx)).astype(np.float32)
+    X = np.ascontiguousarray(Xfull[:, :D])
+    dX = cu.dev(Xfull)[:, :D]
+    Y = cu.csr_spmm(cu.dev(rowptr), cu.dev(cols), cu.dev(vals), M, K, dX, ldx=ldx, ldy=D + pad)
+    ref = oracle.spmm_f64acc(rowptr, cols, vals, M, X)
+    Yh = Y.cpu().numpy()
+    assert not np.isnan(Yh).any(), "some output row was never written"
+    assert np.all(Yh[lens == 0] == 0.0), "empty rows must be zero (reference cuda_spmm.cu:626)"
+    err, maxerr = oracle.rel_err(Yh, ref)
+    assert err <= TOL, (err, maxerr)
+
+
+def test_spmm_all_empty_and_degenerate(cu):
+    rowptr = torch.zeros(11, dtype=torch.int32, device="cuda")
+    e_i = torch.zeros(0, dtype=torch.int32, device="cuda")
+    e_f = torch.zeros(0, dtype=torch.float32, device="cuda")
+    X = torch.ones(5, 12, device="cuda")
+    Y = cu.csr_spmm(rowptr, e_i, e_f, 10, 5, X)
+    assert Y.shape == (10, 12) and torch.all(Y == 0)
+    # single entry, single column
+    Y = cu.csr_spmm(cu.dev(np.array([0, 1], np.int32)), cu.dev(np.array([2], np.int32)), cu.dev(np.array([3.0], np.float32)), 1, 5,
+                    torch.arange(5, dtype=torch.float32, device="cuda").reshape(5, 1).contiguous())
+    assert Y.item() == 6.0
+
+
+def test_spmm_nan_inf_not_leaked_from_other_rows(cu):
+    """A 0-valued lane must never multiply a foreign row: X row 0 is inf/nan but unused."""
+    rng = np.random.Generator(np.random.PCG64(3))
+    M, K, D = 40, 64, 96
+    lens = rng.integers(1, 37, M)
+    rowptr = np.zeros(M + 1, np.int32)
+    rowptr[1:] = np.cumsum(lens)
+    cols = np.concatenate([np.sort(rng.choice(np.arange(1, K), n, replace=False)) for n in lens]).astype(np.int32)
+    vals = rng.standard_normal(cols.size).astype(np.float32)
+    X = rng.standard_normal((K, D)).astype(np.float32)
+    X[0] = np.inf
+    X[0, ::2] = np.nan
+    Y = cu.csr_spmm(cu.dev(rowptr), cu.dev(cols), cu.dev(vals), M, K, cu.dev(X)).cpu().numpy()
+    assert np.isfinite(Y).all()
+
+
+# --------------------------------------------------------------------------- transpose + backward
+def test_transpose_bit_exact_and_backward(cu, small_mb):
+    _, _, mb = small_mb
+    rng = np.random.Generator(np.random.PCG64(11))
+    for layer in mb.layers:
+        rowptr, col32, vals = _layer_csr(layer)
+        M, K = layer.nrows, layer.ncols
+        t_rowptr, t_col, t_vals = cu.csr_transpose(cu.dev(rowptr), cu.dev(col32), cu.dev(vals), M, K)
+        o_rowptr, o_col, perm = oracle.csr_transpose(rowptr, col32, M, K)
+        assert np.array_equal(t_rowptr.cpu().numpy(), o_rowptr)
+        assert np.array_equal(t_col.cpu().numpy(), o_col)
+        assert np.array_equal(t_vals.cpu().numpy().view(np.uint32), vals[perm].view(np.uint32))
+        for D in (64, 602):
+            G = rng.standard_normal((M, D)).astype(np.float32)
+            dXg = cu.csr_spmm(t_rowptr, t_col, t_vals, K, M, cu.dev(G)).cpu().numpy()
+            ref = oracle.spmm_t_f64acc(rowptr, col32, vals, M, K, G)
+            err, _ = oracle.rel_err(dXg, ref)
+            assert err <= TOL, err
+
+
+def test_transpose_edge_cases(cu):
+    rng = np.random.Generator(np.random.PCG64(5))
+    for M, K in [(1, 1), (33, 70), (64, 31), (100, 3)]:
+        lens = rng.integers(0, min(K, 20) + 1, M)
+        rowptr, cols, vals = _random_csr(rng, M, K, lens)
+        t_rowptr, t_col, t_vals = cu.csr_transpose(cu.dev(rowptr), cu.dev(cols), cu.dev(vals), M, K)
+        o_rowptr, o_col, perm = oracle.csr_transpose(rowptr, cols, M, K)
+        assert np.array_equal(t_rowptr.cpu().numpy(), o_rowptr)
+        assert np.array_equal(t_col.cpu().numpy(), o_col)
+        assert np.array_equal(t_vals.cpu().numpy(), vals[perm])
+
+
+@pytest.mark.parametrize("name", ["cora_gcn", "tiny_sage3"])
+def test_backward_golden(cu, golden_dir, name):
+    for L in _golden_layers(golden_dir, name):
+        rowptr, col32, vals = L["rowptr"], L["colidx"].astype(np.int32), L["values"]
+        M, K = L["nrows"], L["ncols"]
+        t = cu.csr_transpose(cu.dev(rowptr), cu.dev(col32), cu.dev(vals), M, K)
+        dXg = cu.csr_spmm(*t, K, M, cu.dev(L["g"])).cpu().numpy()
+        ref = oracle.spmm_t_f64acc(rowptr, col32, vals, M, K, L["g"])
+        err, _ = oracle.rel_err(dXg, ref)
+        assert err <= TOL, err
+        err_ts, _ = oracle.rel_err(dXg, L["dx_torchsparse"])
+        assert err_ts <= 1e-4, err_ts
+
+
+def test_coo_to_csr(cu, small_mb):
+    _, _, mb = small_mb
+    layer = mb.layers[1]
+    rows, cols, _ = oracle.build_adj(layer.fullrowptr, layer.rowptr, layer.colidx32, layer.normfact, layer.nrows)
+    rowptr, col32 = cu.coo_to_csr(cu.dev(np.stack([rows, cols])), layer.nrows)
+    assert np.array_equal(rowptr.cpu().numpy(), layer.rowptr)
+    assert np.array_equal(rowptr.cpu().numpy(), oracle.coo_rows_to_rowptr(rows, layer.nrows))
+    assert np.array_equal(col32.cpu().numpy(), layer.colidx32)
+
+
+# --------------------------------------------------------------------------- remap + gather
+@pytest.mark.parametrize("name", ["cora_gcn", "tiny_sage3", "tiny_order0"])
+def test_placement_remap_and_gather_bit_exact(cu, golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    shape = graphgen.SHAPES[str(z["shape"])]
+    g = graphgen.generate(shape, seed=0)
+    feats = graphgen.features(shape, seed=1)
+    world = int(z["world"])
+    F = shape.feat_dim
+    ld = (F + 3) // 4 * 4                 # shards are padded to 16-byte rows
+    def padded(a):
+        out = np.zeros((a.shape[0], ld), np.float32)
+        out[:, :F] = a
+        return out
+    bufs = [cu.dev(padded(feats[z["gpu_buffer_group"][i]])) for i in range(world)]
+    host = cu.dev(padded(feats))          # stands in for the mapped host table
+    bases = torch.tensor([b.data_ptr() for b in bufs] + [host.data_ptr()], dtype=torch.int64, device="cuda")
+    devices = torch.arange(world, dtype=torch.int64, device="cuda")
+    orders = [int(o) for o in z["orders"]]
+    for si, seed in enumerate(z["seeds"]):
+        pre = f"s{si}_"
+        rank = int(z[pre + "rank"])
+        mb = sampler.ladies_sample(int(seed), z[pre + "batch_nodes"], [int(z["samp_num"])] * 5, shape.num_nodes, g.indptr,
+                                   g.indices, orders)
+        did, idx = z["device_id_of_nodes_group"][rank], z["idx_of_nodes_on_device_group"][rank]
+        src, slot, xrows, counts = cu.placement_remap(cu.dev(mb.input_nodes), cu.dev(did, torch.int64), cu.dev(idx, torch.int64),
+                                                      devices, bases, ld)
+        o_src, o_slot = oracle.placement_remap(mb.input_nodes, did, idx, list(range(world)))
+        assert np.array_equal(src.cpu().numpy(), o_src)
+        assert np.array_equal(slot.cpu().numpy(), o_slot)
+        for i in range(world):                  # the reference's masks / slot lists (sampler.py:156-158)
+            assert np.array_equal(src.cpu().numpy() == i, z[pre + f"mask_dev{i}"])
+            assert np.array_equal(slot.cpu().numpy()[o_src == i], z[pre + f"idx_dev{i}"])
+        assert np.array_equal(slot.cpu().numpy()[o_src == -1], z[pre + "idx_cpu"])
+        c = counts.cpu().numpy()
+        assert c[:world].tolist() == [int((o_src == i).sum()) for i in range(world)] and c[world] == int((o_src == -1).sum())
+        out = cu.gather_rows(xrows, F).cpu().numpy()
+        ref = oracle.gather_rows([feats[z["gpu_buffer_group"][i]] for i in range(world)], feats, o_src, o_slot)
+        assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+        sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(out).tobytes()).digest(), dtype=np.uint8)
+        assert np.array_equal(sha, z[pre + "input_feat_sha"]), "gathered rows differ from the reference gather (main.py:129-134)"
+        # fused gather + SpMM on the deepest layer
+        layer = mb.layers[0]
+        rowptr, col32, vals = _layer_csr(layer)
+        Y = cu.gather_spmm(cu.dev(rowptr), cu.dev(col32), cu.dev(vals), layer.nrows, layer.ncols, F, xrows).cpu().numpy()
+        yref = oracle.gather_spmm_f64acc(rowptr, col32, vals, layer.nrows, [feats[z["gpu_buffer_group"][i]] for i in range(world)],
+                                         feats, o_src, o_slot)
+        err, _ = oracle.rel_err(Y, yref)
+        assert err <= TOL, err
+
+
+def test_index_rows(cu):
+    rng = np.random.Generator(np.random.PCG64(1))
+    for F in (5, 64, 602, 1024):
+        X = rng.standard_normal((500, F)).astype(np.float32)
+        idx = rng.integers(0, 500, 333)
+        out = cu.index_rows(cu.dev(X), cu.dev(idx)).cpu().numpy()
+        assert np.array_equal(out, X[idx])

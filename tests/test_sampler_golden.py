@@ -1,0 +1,94 @@
+"""Host sampler mirror + oracle remaps vs arrays captured from the unmodified reference
+(tests/golden/make_golden.py: reference sampler.py:90-160, preprocess.py:311-407)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from gnn_b200 import graphgen, sampler
+
+CASES = ["cora_gcn", "tiny_sage3", "tiny_order0"]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_ladies_sample_matches_reference(golden_dir, name):
+    z = _load(golden_dir, name)
+    shape = graphgen.SHAPES[str(z["shape"])]
+    g = graphgen.generate(shape, seed=0)
+    orders = [int(o) for o in z["orders"]]
+    world = int(z["world"])
+    for si, seed in enumerate(z["seeds"]):
+        pre = f"s{si}_"
+        rank = int(z[pre + "rank"])
+        mb = sampler.ladies_sample(int(seed), z[pre + "batch_nodes"], [int(z["samp_num"])] * 5, shape.num_nodes,
+                                   g.indptr, g.indices, orders)
+        assert len(mb.layers) == int(z[pre + "nlayers"])
+        assert mb.input_nodes.size == int(z[pre + "n0"])
+        for li, layer in enumerate(mb.layers):
+            lp = pre + f"l{li}_"
+            if layer is None:
+                assert lp + "none" in z.files
+                continue
+            for k in ["fullrowptr", "rowptr", "colidx", "normfact"]:
+                ref = z[lp + k]
+                got = getattr(layer, k)
+                assert got.dtype == ref.dtype, (k, got.dtype, ref.dtype)
+                assert np.array_equal(got, ref), k
+            assert layer.nrows == int(z[lp + "nrows"]) and layer.ncols == int(z[lp + "ncols"])
+            assert np.array_equal(mb.sampled_nodes[li], z[lp + "sampled_nodes"])
+        # placement remap, reference sampler.py:150-158
+        did = z["device_id_of_nodes_group"][rank]
+        idx = z["idx_of_nodes_on_device_group"][rank]
+        devices = list(range(world))
+        pr = sampler.placement_remap(mb.input_nodes, did, idx, devices)
+        assert np.array_equal(pr.mask_on_cpu, z[pre + "mask_cpu"])
+        assert np.array_equal(pr.idx_on_cpu, z[pre + "idx_cpu"])
+        for i in range(world):
+            assert np.array_equal(pr.mask_on_devices[i], z[pre + f"mask_dev{i}"])
+            assert np.array_equal(pr.idx_on_devices[i], z[pre + f"idx_dev{i}"])
+        # the compact (src_dev, slot) form is the same information
+        o_src, o_slot = oracle.placement_remap(mb.input_nodes, did, idx, devices)
+        assert np.array_equal(o_src, pr.src_dev) and np.array_equal(o_slot, pr.slot)
+        for i in range(world):
+            assert np.array_equal(o_src == i, z[pre + f"mask_dev{i}"])
+            assert np.array_equal(o_slot[o_src == i], z[pre + f"idx_dev{i}"])
+        assert np.array_equal(o_slot[o_src == -1], z[pre + "idx_cpu"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_gather_matches_reference(golden_dir, name):
+    z = _load(golden_dir, name)
+    shape = graphgen.SHAPES[str(z["shape"])]
+    feats = graphgen.features(shape, seed=1)
+    world = int(z["world"])
+    bufs = [feats[z["gpu_buffer_group"][i]] for i in range(world)]
+    import hashlib
+    for si in range(len(z["seeds"])):
+        pre = f"s{si}_"
+        n0 = int(z[pre + "n0"])
+        src = np.full(n0, -1, np.int32)
+        slot = np.zeros(n0, np.int64)
+        slot[z[pre + "mask_cpu"]] = z[pre + "idx_cpu"]
+        for i in range(world):
+            src[z[pre + f"mask_dev{i}"]] = i
+            slot[z[pre + f"mask_dev{i}"]] = z[pre + f"idx_dev{i}"]
+        out = oracle.gather_rows(bufs, feats, src, slot)
+        sha = np.frombuffer(hashlib.sha256(out.tobytes()).digest(), dtype=np.uint8)
+        assert np.array_equal(sha, z[pre + "input_feat_sha"])
+        if pre + "input_feat" in z.files:
+            assert np.array_equal(out, z[pre + "input_feat"])
+
+
+def test_oracle_sampled_nodes_direct():
+    rng = np.random.Generator(np.random.PCG64(5))
+    for _ in range(20):
+        prev = rng.choice(5000, rng.integers(1, 300), replace=False)
+        extra = rng.choice(5000, rng.integers(0, 800), replace=False)
+        after = np.unique(np.concatenate([extra, prev]))
+        assert np.array_equal(oracle.sampled_nodes(after, prev), np.where(np.isin(after, prev))[0])
+        assert np.array_equal(sampler.sampled_nodes_remap(after, prev), np.where(np.isin(after, prev))[0])
