@@ -60,7 +60,10 @@ def build_extension(verbose: bool = False, force: bool = False) -> str:
     hdr = os.path.join(INC, "gnn_b200.h")
     kern = build_kernels(verbose, force)
     if force or _newer(out, [src, hdr]):
-        cxx = os.environ.get("CXX", shutil.which("g++") or "g++")
+        # The image's $CXX (/opt/gcc/bin/g++) is a wrapper whose -B tree only has a static libstdc++;
+        # a second copy of libstdc++ inside the extension crashes on the first formatted TORCH_CHECK
+        # (two sets of locale facets in one process).  Link against the shared libstdc++ torch uses.
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else os.environ.get("CXX", shutil.which("g++") or "g++")
         incs = []
         for p in cpp_extension.include_paths(device_type="cuda") + [sysconfig.get_paths()["include"], INC]:
             incs += ["-isystem" if "site-packages" in p or "python" in p or "cuda" in p else "-I", p]

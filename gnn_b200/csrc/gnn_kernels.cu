@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 
 #include "gnn_b200.h"
 
@@ -95,16 +96,21 @@ struct XSrc {
   }
 };
 
-template <int VEC, int NV, int LPR, bool GATHER>
+// nonzeros kept in flight per warp step (U) and CTAs per SM asked of ptxas (MINB), by vectors per lane
+// (tuned on B200 over the Reddit-shaped blocks, profiles/tune_r1.txt)
+constexpr int default_u(int nv) { return nv >= 4 ? 2 : (nv >= 2 ? 4 : 8); }
+constexpr int default_minb(int nv) { return (nv == 3 || nv == 4) ? 3 : (nv >= 6 ? 2 : 4); }
+
+// Dload = floats readable per X row (D, or D rounded up to 4 when rows are padded to 16 bytes)
+template <int VEC, int NV, int LPR, bool GATHER, int U>
 __device__ __forceinline__ void accumulate_segment(const int *__restrict__ colidx, const float *__restrict__ vals,
-                                                   const XSrc<GATHER> &xs, int s, int e, int lane, int col0, int D,
+                                                   const XSrc<GATHER> &xs, int s, int e, int lane, int col0, int Dload,
                                                    float (&acc)[NV][VEC]) {
   constexpr int G = 32 / LPR;                       // row groups in the warp
-  constexpr int U = (NV >= 5) ? 1 : (NV >= 3 ? 2 : (NV == 2 ? 4 : 8));
   const int g = lane / LPR;
   bool colok[NV];
 #pragma unroll
-  for (int n = 0; n < NV; ++n) colok[n] = col0 + n * LPR * VEC + VEC <= D + (GATHER ? 3 : 0);
+  for (int n = 0; n < NV; ++n) colok[n] = col0 + n * LPR * VEC + VEC <= Dload;
 
   for (int base = s; base < e; base += 32) {
     const int i = base + lane;
@@ -215,10 +221,11 @@ struct SpmmParams {
   float *partials;   // [2*nchunks][Dp]
   int *counters;     // [M*nslabs], zero on entry
   int Dp;
+  int Dload;         // floats readable per X row (>= D)
 };
 
-template <int VEC, int NV, int LPR, bool GATHER>
-__global__ void __launch_bounds__(kThreads)
+template <int VEC, int NV, int LPR, bool GATHER, int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 spmm_rowsplit_kernel(const SpmmParams p, const XSrc<GATHER> xs) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -252,7 +259,7 @@ spmm_rowsplit_kernel(const SpmmParams p, const XSrc<GATHER> xs) {
     float acc[NV][VEC];
 #pragma unroll
     for (int n = 0; n < NV; ++n) vzero<VEC>(acc[n]);
-    accumulate_segment<VEC, NV, LPR, GATHER>(p.colidx, p.vals, xs, s, seg_end, lane, col0, p.D, acc);
+    accumulate_segment<VEC, NV, LPR, GATHER, U>(p.colidx, p.vals, xs, s, seg_end, lane, col0, p.Dload, acc);
 
     const int c_first = row_start / p.C;
     const int c_last = (row_end - 1) / p.C;
@@ -299,16 +306,22 @@ spmm_rowsplit_kernel(const SpmmParams p, const XSrc<GATHER> xs) {
   }
 }
 
-// chunk size: a function of (nnz, D) only so that the workspace query and the launch agree
+// chunk size: a function of (nnz, D) only so that the workspace query and the launch agree.
+// Large blocks use 1024 nonzeros per warp item; small ones shrink the chunk so that a few thousand
+// warp items exist (the top LADIES layer is 30 K nonzeros: latency, not bandwidth, decides it).
 inline int spmm_chunk(int64_t nnz, int64_t D) {
-  const int64_t slabs_est = cdiv(D, 256);
-  int64_t want = nnz * slabs_est / 16384;
+#ifdef GNN_TUNE
+  if (getenv("GNN_TUNE_C")) return atoi(getenv("GNN_TUNE_C"));
+#endif
+  const int64_t want = nnz * cdiv(D, 128) / 4096;
   int c = 64;
-  while (c < 2048 && c * 2 <= want) c *= 2;
+  while (c < 1024 && c * 2 <= want) c *= 2;
   return c;
 }
 
 struct SpmmPlan { int vec, nv, lpr, nslabs, C, nchunks, Dp; };
+
+constexpr int64_t kTargetItems = 4096;   // warp items wanted before wider slabs are preferred
 
 inline SpmmPlan make_plan(int64_t nnz, int64_t D, int vec) {
   SpmmPlan pl;
@@ -325,34 +338,81 @@ inline SpmmPlan make_plan(int64_t nnz, int64_t D, int vec) {
   }
   pl.lpr = 32;
   const int64_t n = cdiv(nvec, 32);                // vector columns per lane
-  static const int cand[] = {1, 2, 3, 4, 5, 6, 8};
+  // vectors per lane: least padded width, then fewest slabs - among the choices that still give
+  // enough warp items; the narrowest slab when nothing does
+  static const int cand[] = {5, 4, 3, 2, 1};
   double best = 1e30;
   pl.nv = 1;
   for (int nv : cand) {
     const int64_t slabs = cdiv(n, nv);
+    if (nv > 1 && (int64_t)pl.nchunks * slabs < kTargetItems) continue;
     const double cost = (double)(nv * slabs) + 0.5 * (double)slabs;
-    if (cost < best - 1e-9 || (cost < best + 1e-9 && nv > pl.nv)) { best = cost; pl.nv = nv; }
+    if (cost < best - 1e-9) { best = cost; pl.nv = nv; }
   }
+#ifdef GNN_TUNE
+  if (getenv("GNN_TUNE_NV")) pl.nv = atoi(getenv("GNN_TUNE_NV"));
+#endif
   pl.nslabs = (int)cdiv(n, pl.nv);
   return pl;
 }
 
-// counters: one int per (row, slab); vec == 1 gives the largest slab count of the three layouts
+// counters: one int per (row, slab); the narrowest layout (scalar loads, one vector per lane) has ceil(D/32) slabs
 inline size_t spmm_counter_bytes(int64_t M, int64_t nnz, int64_t D) {
-  return ((size_t)M * (size_t)make_plan(nnz, D, 1).nslabs * sizeof(int) + 255) / 256 * 256;
+  (void)nnz;
+  return ((size_t)M * (size_t)cdiv(D, 32) * sizeof(int) + 255) / 256 * 256;
 }
 
-template <int VEC, int NV, int LPR, bool GATHER>
+template <int VEC, int NV, int LPR, bool GATHER, int U = default_u(NV), int MINB = default_minb(NV)>
 int launch_spmm_t(const SpmmParams &p, const XSrc<GATHER> &xs, cudaStream_t st) {
   const int64_t items = (int64_t)p.nchunks * p.nslabs;
   const unsigned grid = (unsigned)cdiv(items, kWarpsPerCta);
-  spmm_rowsplit_kernel<VEC, NV, LPR, GATHER><<<grid, kThreads, 0, st>>>(p, xs);
+  spmm_rowsplit_kernel<VEC, NV, LPR, GATHER, U, MINB><<<grid, kThreads, 0, st>>>(p, xs);
   GNN_LAUNCH_CHECK();
   return 0;
 }
 
+#ifdef GNN_TUNE
+// experiment build only (scratch/tune.py): pick (NV, U, MINB) from the environment
+inline int env_int(const char *name, int dflt) { const char *v = getenv(name); return v ? atoi(v) : dflt; }
+template <int NV, int U>
+int launch_tune_minb(int minb, const SpmmParams &p, const XSrc<false> &xs, cudaStream_t st) {
+  switch (minb) {
+    case 2: return launch_spmm_t<4, NV, 32, false, U, 2>(p, xs, st);
+    case 3: return launch_spmm_t<4, NV, 32, false, U, 3>(p, xs, st);
+    case 4: return launch_spmm_t<4, NV, 32, false, U, 4>(p, xs, st);
+    default: return launch_spmm_t<4, NV, 32, false, U, 6>(p, xs, st);
+  }
+}
+template <int NV>
+int launch_tune_u(int u, int minb, const SpmmParams &p, const XSrc<false> &xs, cudaStream_t st) {
+  switch (u) {
+    case 1: return launch_tune_minb<NV, 1>(minb, p, xs, st);
+    case 2: return launch_tune_minb<NV, 2>(minb, p, xs, st);
+    case 4: return launch_tune_minb<NV, 4>(minb, p, xs, st);
+    default: return launch_tune_minb<NV, 8>(minb, p, xs, st);
+  }
+}
+inline int launch_tune(const SpmmPlan &pl, const SpmmParams &p, const XSrc<false> &xs, cudaStream_t st) {
+  const int u = env_int("GNN_TUNE_U", 1), minb = env_int("GNN_TUNE_MINB", 2);
+  switch (pl.nv) {
+    case 1: return launch_tune_u<1>(u, minb, p, xs, st);
+    case 2: return launch_tune_u<2>(u, minb, p, xs, st);
+    case 3: return launch_tune_u<3>(u, minb, p, xs, st);
+    case 4: return launch_tune_u<4>(u, minb, p, xs, st);
+    case 5: return launch_tune_u<5>(u, minb, p, xs, st);
+    case 6: return launch_tune_u<6>(u, minb, p, xs, st);
+    default: return launch_tune_u<8>(u, minb, p, xs, st);
+  }
+}
+#endif
+
 template <int VEC, bool GATHER>
 int launch_spmm_nv(const SpmmPlan &pl, const SpmmParams &p, const XSrc<GATHER> &xs, cudaStream_t st) {
+#ifdef GNN_TUNE
+  if constexpr (VEC == 4 && !GATHER) {
+    if (pl.lpr == 32 && getenv("GNN_TUNE_U")) return launch_tune(pl, p, xs, st);
+  }
+#endif
   if (pl.lpr != 32) {
     if constexpr (VEC == 4) {
       switch (pl.lpr) {
@@ -369,9 +429,7 @@ int launch_spmm_nv(const SpmmPlan &pl, const SpmmParams &p, const XSrc<GATHER> &
     case 2: return launch_spmm_t<VEC, 2, 32, GATHER>(p, xs, st);
     case 3: return launch_spmm_t<VEC, 3, 32, GATHER>(p, xs, st);
     case 4: return launch_spmm_t<VEC, 4, 32, GATHER>(p, xs, st);
-    case 5: return launch_spmm_t<VEC, 5, 32, GATHER>(p, xs, st);
-    case 6: return launch_spmm_t<VEC, 6, 32, GATHER>(p, xs, st);
-    default: return launch_spmm_t<VEC, 8, 32, GATHER>(p, xs, st);
+    default: return launch_spmm_t<VEC, 5, 32, GATHER>(p, xs, st);
   }
 }
 
@@ -397,12 +455,16 @@ int spmm_entry(const int32_t *rowptr, const int32_t *colidx, const float *vals, 
   if (!rowptr || !colidx || !vals) return GNN_E_BADARG;
   if (GATHER ? (xrows == nullptr) : (X == nullptr || ldx < D)) return GNN_E_BADARG;
   int vec = 1;
+  int64_t Dload = D;
+  const int64_t D4 = cdiv(D, 4) * 4;
   if (GATHER) {
     vec = 4;   // contract: every row pointer is 16-byte aligned and readable up to ceil(D/4)*4 floats
+    Dload = D4;
   } else {
     const uintptr_t a = reinterpret_cast<uintptr_t>(X) | (uintptr_t)(ldx * 4);
-    if ((a & 15) == 0 && D % 4 == 0) vec = 4;
-    else if ((a & 7) == 0 && D % 2 == 0) vec = 2;
+    // rows padded to 16 bytes (ldx >= ceil4(D), e.g. the gathered input buffer) may be read past D
+    if ((a & 15) == 0 && (D % 4 == 0 || ldx >= D4)) { vec = 4; Dload = D4; }
+    else if ((a & 7) == 0 && (D % 2 == 0 || ldx >= D + 1)) { vec = 2; Dload = cdiv(D, 2) * 2; }
   }
   const SpmmPlan pl = make_plan(nnz, D, vec);
   const size_t need = gnn_csr_spmm_workspace_bytes(M, nnz, D);
@@ -412,7 +474,7 @@ int spmm_entry(const int32_t *rowptr, const int32_t *colidx, const float *vals, 
   p.rowptr = rowptr; p.colidx = colidx; p.vals = vals;
   p.M = (int)M; p.nnz = (int)nnz; p.D = (int)D;
   p.C = pl.C; p.nchunks = pl.nchunks; p.nslabs = pl.nslabs; p.Dp = pl.Dp;
-  p.Y = Y; p.ldy = ldy;
+  p.Y = Y; p.ldy = ldy; p.Dload = (int)Dload;
   p.counters = reinterpret_cast<int *>(workspace);
   const size_t counter_bytes = spmm_counter_bytes(M, nnz, D);
   p.partials = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + counter_bytes);
@@ -465,10 +527,15 @@ __global__ void coo_to_csr_kernel(const int64_t *__restrict__ idx, int64_t M, in
 
 // ---------------------------------------------------------------------------
 // CSR transpose through a column-major bitmap (deterministic: bit OR is order-free)
+//
+// cell[c][w] = { bits of rows 32w..32w+31 that have a nonzero in column c,
+//                number of nonzeros of column c in rows < 32w }
+// so the entry (r, c) lands at t_rowptr[c] + cell.prefix + popc(cell.bits below r):
+// the transposed rows come out in ascending source row without any sort.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 bitmap_set_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx, int M, int words_per_col,
-                  unsigned *__restrict__ bitmap) {
+                  uint2 *__restrict__ cells) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
@@ -476,21 +543,50 @@ bitmap_set_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx
     const unsigned bit = 1u << (r & 31);
     const int word = r >> 5;
     for (int i = b + lane; i < e; i += 32)
-      atomicOr(bitmap + (int64_t)__ldg(colidx + i) * words_per_col + word, bit);
+      atomicOr(&cells[(int64_t)__ldg(colidx + i) * words_per_col + word].x, bit);
   }
 }
 
 __global__ void __launch_bounds__(256)
-bitmap_count_kernel(const unsigned *__restrict__ bitmap, int K, int words_per_col, int *__restrict__ counts) {
+bitmap_prefix_kernel(uint2 *__restrict__ cells, int K, int words_per_col, int *__restrict__ counts) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < K; c += gridDim.x * wpb) {
-    const unsigned *col = bitmap + (int64_t)c * words_per_col;
-    int n = 0;
-    for (int w = lane; w < words_per_col; w += 32) n += __popc(col[w]);
+    uint2 *col = cells + (int64_t)c * words_per_col;
+    int running = 0;
+    for (int w0 = 0; w0 < words_per_col; w0 += 32) {
+      const int w = w0 + lane;
+      const int cnt = w < words_per_col ? __popc(col[w].x) : 0;
+      int incl = cnt;
 #pragma unroll
-    for (int off = 16; off; off >>= 1) n += __shfl_xor_sync(kFull, n, off);
-    if (lane == 0) counts[c] = n;
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(kFull, incl, off);
+        if (lane >= off) incl += y;
+      }
+      if (w < words_per_col) col[w].y = (unsigned)(running + incl - cnt);
+      running += __shfl_sync(kFull, incl, 31);
+    }
+    if (lane == 0) counts[c] = running;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+transpose_fill_kernel(const uint2 *__restrict__ cells, int M, int words_per_col, const int *__restrict__ rowptr,
+                      const int *__restrict__ colidx, const float *__restrict__ vals, const int *__restrict__ t_rowptr,
+                      int *__restrict__ t_colidx, float *__restrict__ t_vals) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
+    const int b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+    const unsigned below = (1u << (r & 31)) - 1u;
+    const int word = r >> 5;
+    for (int i = b + lane; i < e; i += 32) {
+      const int c = __ldg(colidx + i);
+      const uint2 cell = __ldg(cells + (int64_t)c * words_per_col + word);
+      const int pos = __ldg(t_rowptr + c) + (int)cell.y + __popc(cell.x & below);
+      t_colidx[pos] = r;
+      t_vals[pos] = __ldg(vals + i);
+    }
   }
 }
 
@@ -531,44 +627,6 @@ exclusive_scan_kernel(const int *__restrict__ counts, int n, int *__restrict__ o
     __syncthreads();
   }
   if (threadIdx.x == 0) out[n] = carry_s;
-}
-
-__global__ void __launch_bounds__(256)
-bitmap_enumerate_kernel(const unsigned *__restrict__ bitmap, int K, int words_per_col, const int *__restrict__ rowptr,
-                        const int *__restrict__ colidx, const float *__restrict__ vals, const int *__restrict__ t_rowptr,
-                        int *__restrict__ t_colidx, float *__restrict__ t_vals) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < K; c += gridDim.x * wpb) {
-    const unsigned *col = bitmap + (int64_t)c * words_per_col;
-    int base = __ldg(t_rowptr + c);
-    for (int w0 = 0; w0 < words_per_col; w0 += 32) {
-      const int w = w0 + lane;
-      unsigned word = w < words_per_col ? col[w] : 0u;
-      const int cnt = __popc(word);
-      int incl = cnt;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int y = __shfl_up_sync(kFull, incl, off);
-        if (lane >= off) incl += y;
-      }
-      int pos = base + incl - cnt;
-      while (word) {
-        const int r = w * 32 + (__ffs(word) - 1);
-        word &= word - 1;
-        // position of column c inside row r of the CSR (columns ascending within a row)
-        int lo = __ldg(rowptr + r), hi = __ldg(rowptr + r + 1) - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (__ldg(colidx + mid) < c) lo = mid + 1; else hi = mid;
-        }
-        t_colidx[pos] = r;
-        t_vals[pos] = __ldg(vals + lo);
-        ++pos;
-      }
-      base += __shfl_sync(kFull, incl, 31);
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -720,7 +778,7 @@ size_t gnn_csr_transpose_workspace_bytes(int64_t M, int64_t K, int64_t nnz) {
   (void)nnz;
   if (M <= 0 || K <= 0) return 256;
   const size_t words_per_col = (size_t)cdiv(M, 32);
-  return (size_t)K * words_per_col * 4 + ((size_t)K * 4 + 255) / 256 * 256 + 256;
+  return (size_t)K * words_per_col * sizeof(uint2) + ((size_t)K * 4 + 255) / 256 * 256 + 256;
 }
 
 int gnn_csr_transpose(const int32_t *rowptr, const int32_t *colidx, const float *vals, int64_t M, int64_t K, int64_t nnz,
@@ -737,16 +795,16 @@ int gnn_csr_transpose(const int32_t *rowptr, const int32_t *colidx, const float 
   if (!workspace || workspace_bytes < need) return GNN_E_WORKSPACE;
   const int words_per_col = (int)cdiv(M, 32);
   int *counts = reinterpret_cast<int *>(workspace);
-  unsigned *bitmap = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(workspace) + ((size_t)K * 4 + 255) / 256 * 256);
-  GNN_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)K * words_per_col * 4, st));
-  bitmap_set_kernel<<<warp_grid(M, 8), 256, 0, st>>>(rowptr, colidx, (int)M, words_per_col, bitmap);
+  uint2 *cells = reinterpret_cast<uint2 *>(reinterpret_cast<char *>(workspace) + ((size_t)K * 4 + 255) / 256 * 256);
+  GNN_CUDA(cudaMemsetAsync(cells, 0, (size_t)K * words_per_col * sizeof(uint2), st));
+  bitmap_set_kernel<<<warp_grid(M, 8), 256, 0, st>>>(rowptr, colidx, (int)M, words_per_col, cells);
   GNN_LAUNCH_CHECK();
-  bitmap_count_kernel<<<warp_grid(K, 8), 256, 0, st>>>(bitmap, (int)K, words_per_col, counts);
+  bitmap_prefix_kernel<<<warp_grid(K, 8), 256, 0, st>>>(cells, (int)K, words_per_col, counts);
   GNN_LAUNCH_CHECK();
   exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, (int)K, t_rowptr);
   GNN_LAUNCH_CHECK();
-  bitmap_enumerate_kernel<<<warp_grid(K, 8), 256, 0, st>>>(bitmap, (int)K, words_per_col, rowptr, colidx, vals, t_rowptr,
-                                                          t_colidx, t_vals);
+  transpose_fill_kernel<<<warp_grid(M, 8), 256, 0, st>>>(cells, (int)M, words_per_col, rowptr, colidx, vals, t_rowptr, t_colidx,
+                                                        t_vals);
   GNN_LAUNCH_CHECK();
   return 0;
 }

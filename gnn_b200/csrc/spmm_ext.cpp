@@ -47,7 +47,10 @@ inline torch::Tensor workspace(size_t bytes, const torch::Device &dev) {
 // ---- CSR fast path -------------------------------------------------------
 torch::Tensor csr_spmm(const torch::Tensor &rowptr, const torch::Tensor &colidx, const torch::Tensor &vals, int64_t M,
                        int64_t K, const torch::Tensor &dense) {
-  CHECK_DENSE(rowptr); CHECK_DENSE(colidx); CHECK_DENSE(vals); CHECK_DENSE(dense);
+  CHECK_DENSE(rowptr); CHECK_DENSE(colidx); CHECK_DENSE(vals); CHECK_CUDA(dense);
+  // rows may be padded (stride(0) >= D) as long as each row is contiguous: the gathered buffer is 16-byte-row aligned
+  TORCH_CHECK(dense.dim() == 2 && (dense.stride(1) == 1 || dense.size(1) <= 1) && dense.stride(0) >= dense.size(1),
+              "denseMat must be contiguous");
   TORCH_CHECK(rowptr.scalar_type() == torch::kInt && colidx.scalar_type() == torch::kInt, "CSR indices must be int32");
   TORCH_CHECK(vals.scalar_type() == torch::kFloat && dense.scalar_type() == torch::kFloat, "values/dense must be float32");
   TORCH_CHECK(dense.dim() == 2 && dense.size(0) == K, "dense operand must be [", K, ", D], got ", dense.sizes());
@@ -60,7 +63,8 @@ torch::Tensor csr_spmm(const torch::Tensor &rowptr, const torch::Tensor &colidx,
   const size_t wsb = gnn_csr_spmm_workspace_bytes(M, nnz, D);
   auto ws = workspace(wsb, dense.device());
   check_rc(gnn_csr_spmm_f32(rowptr.data_ptr<int32_t>(), colidx.data_ptr<int32_t>(), vals.data_ptr<float>(), M, K, nnz, D,
-                            dense.data_ptr<float>(), D, out.data_ptr<float>(), D, ws.data_ptr(), wsb, cur_stream()),
+                            dense.data_ptr<float>(), dense.size(0) > 1 ? dense.stride(0) : D, out.data_ptr<float>(), D,
+                            ws.data_ptr(), wsb, cur_stream()),
            "gnn_csr_spmm_f32");
   return out;
 }

@@ -84,7 +84,9 @@ def adjacency_of(mat1: torch.Tensor) -> Adjacency:
 def _check_dense(t: torch.Tensor, name: str):
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor")
-    if not t.is_contiguous():
+    # the reference requires is_contiguous() (spmm.cpp:14-15); row-padded buffers (unit inner stride) are also
+    # accepted because the gathered input-feature buffer keeps 16-byte-aligned rows
+    if t.dim() != 2 or not (t.is_contiguous() or (t.stride(1) == 1 and t.stride(0) >= t.shape[1])):
         raise RuntimeError(f"{name} must be contiguous")
     if t.dtype != torch.float32:
         raise RuntimeError(f"{name} must be float32")

@@ -1,0 +1,129 @@
+"""Placement-partitioned feature buffers and the per-minibatch input gather.
+
+Host-side mirror of the reference's gather block (main.py:129-134, copies at
+:185-190 and :228-233) and of the buffers ``create_buffer`` uploads
+(preprocess.py:397-399):
+
+    input_feat_data[mask_i]   = gpu_buffers[i][slots_i].to(device)     for every GPU i
+    input_feat_data[mask_cpu] = feat_data[ids_cpu].to(device)
+
+Here the per-GPU buffers are *shards* allocated through the C ABI so that every
+rank (one process per GPU) can map its peers' shards over NVLink (CUDA IPC), the
+host table is pinned and mapped for zero-copy reads, the placement tables live
+on the device, and one remap kernel + one gather kernel on the consuming GPU
+replace the mask/scatter sequence.  Row j of the result belongs to
+``input_nodes[j]`` exactly as in the reference.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native
+
+
+def padded_ld(feat_dim: int) -> int:
+    """Rows of shards / gathered buffers are padded to 16 bytes so every row is float4-aligned."""
+    return (int(feat_dim) + 3) // 4 * 4
+
+
+class FeatureStore:
+    def __init__(self, feat_data: torch.Tensor, gpu_buffer_nodes: Sequence[np.ndarray], device_id_of_nodes: np.ndarray,
+                 idx_of_nodes_on_device: np.ndarray, devices: Sequence[int], rank: int, device: torch.device,
+                 group=None, map_host: bool = True):
+        """feat_data: CPU float32 [N, F] (the reference's ``feat_data``); gpu_buffer_nodes[i]: node id of every
+        slot of GPU i's buffer (``gpu_buffer_group``); device_id_of_nodes / idx_of_nodes_on_device: THIS rank's
+        view of the placement tables; devices: device ids as they appear in the tables; ``group``: a
+        torch.distributed process group when there is one process per GPU (None = single process)."""
+        self.ext = _native.extension()
+        self.rank, self.world = int(rank), len(devices)
+        self.device = torch.device(device)
+        self.feat_dim = int(feat_data.shape[1])
+        self.ld = padded_ld(self.feat_dim)
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+
+        # ---- host table: padded, pinned, mapped (zero-copy reads of uncached rows, main.py:134)
+        self.host = None
+        host_alias = 0
+        if map_host:
+            if feat_data.shape[1] == self.ld and feat_data.is_contiguous():
+                self.host = feat_data
+            else:
+                self.host = torch.zeros((feat_data.shape[0], self.ld), dtype=torch.float32)
+                self.host[:, :self.feat_dim] = feat_data
+            host_alias = self.ext.host_register(self.host)
+
+        # ---- shards
+        self.shards: List[Optional[torch.Tensor]] = [None] * self.world
+        self._handles = None
+        multi_process = group is not None and self.world > 1
+        if multi_process:
+            import torch.distributed as dist
+            nodes = np.asarray(gpu_buffer_nodes[self.rank])
+            shard, handle = self.ext.shard_alloc(len(nodes), self.ld, dev_index)
+            self._fill(shard, feat_data, nodes)
+            self.shards[self.rank] = shard
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (bytes(handle), int(len(nodes))), group=group)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)
+            for i, (h, rows) in enumerate(handles):
+                if i != self.rank:
+                    self.shards[i] = self.ext.shard_open(h, rows, self.ld, dev_index)
+        else:
+            # single process: every buffer lives on this device (world == 1, or a test emulating more ranks)
+            for i in range(self.world):
+                nodes = np.asarray(gpu_buffer_nodes[i])
+                shard, _ = self.ext.shard_alloc(max(len(nodes), 1), self.ld, dev_index)
+                self._fill(shard, feat_data, nodes)
+                self.shards[i] = shard
+
+        ptrs = [int(s.data_ptr()) for s in self.shards] + [int(host_alias)]
+        self.bases = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        self.devices = torch.tensor([int(d) for d in devices], dtype=torch.int64, device=self.device)
+        self.device_id_of_nodes = torch.from_numpy(np.ascontiguousarray(device_id_of_nodes, dtype=np.int64)).to(self.device)
+        self.idx_of_nodes_on_device = torch.from_numpy(np.ascontiguousarray(idx_of_nodes_on_device, dtype=np.int64)).to(self.device)
+
+    def _fill(self, shard: torch.Tensor, feat_data: torch.Tensor, nodes: np.ndarray):
+        if len(nodes) == 0:
+            return
+        shard.zero_()
+        rows = feat_data[torch.from_numpy(np.ascontiguousarray(nodes, dtype=np.int64))]
+        shard[:len(nodes), :self.feat_dim].copy_(rows.to(self.device, non_blocking=False))
+
+    # ------------------------------------------------------------------
+    def remap(self, input_nodes: torch.Tensor):
+        """Device placement remap (reference sampler.py:150-158): -> (src_dev i32, slot i64, xrows i64, counts i64)."""
+        return self.ext.placement_remap(input_nodes, self.device_id_of_nodes, self.idx_of_nodes_on_device, self.devices,
+                                        self.bases, self.ld)
+
+    def gather(self, input_nodes: torch.Tensor) -> torch.Tensor:
+        """input_feat_data of main.py:129-134 as a [n0, F] view of a 16-byte-row-aligned buffer."""
+        _, _, xrows, _ = self.remap(input_nodes)
+        return self.ext.gather_rows(xrows, self.feat_dim, self.ld)
+
+    def gather_from_reference_tuple(self, masks_on_devices, mask_on_cpu, idx_on_devices, idx_on_cpu, num_input_nodes):
+        """Same gather driven by the reference sampler's own outputs (sampler.py:160 tuple), for main.py drop-in use:
+        the masks / slot lists are folded into a pointer table on the host, then one gather kernel runs."""
+        slot = np.zeros(num_input_nodes, dtype=np.int64)
+        src = np.full(num_input_nodes, self.world, dtype=np.int64)      # index into bases; world = host
+        for i in range(self.world):
+            m = np.asarray(masks_on_devices[i])
+            slot[m] = np.asarray(idx_on_devices[i])
+            src[m] = i
+        mc = np.asarray(mask_on_cpu)
+        slot[mc] = np.asarray(idx_on_cpu)
+        bases = self.bases.cpu().numpy()
+        xrows = torch.from_numpy(bases[src] + slot * (self.ld * 4)).to(self.device)
+        return self.ext.gather_rows(xrows, self.feat_dim, self.ld)
+
+    def close(self):
+        if self.host is not None:
+            try:
+                self.ext.host_unregister(self.host)
+            except RuntimeError:
+                pass
+            self.host = None
+        self.shards = []

@@ -1,0 +1,149 @@
+"""Training-step harness for the secondary BASELINE metric (training minibatches/s at 1/2/4/8 B200).
+
+NOT part of the product path: the reference's models.py / main.py are dense torch code that must
+keep working unchanged on top of ``custom_sparse_ops``.  The GPU
+box does not have /root/reference, so the few dense pieces a training step needs are restated
+here with the same math, only to drive the hot path in its real calling pattern:
+
+  * GraphSAGE layer: ``spmm(adj, x)`` then ``cat[linearB(x[sampled_nodes]), linearW(feat)]``, ELU,
+    per-row standardisation with learnable scale/offset   (reference models.py:6-25, 27-44)
+  * head: L2-normalise, dropout, linear                     (models.py:86-97)
+  * loss: BCE-with-logits weighted 1/batch, summed          (utils.py:129-140, sigmoid_loss default)
+  * step: gather -> forward -> loss -> backward -> clip_grad_norm_(5) -> gradient exchange -> Adam
+    (main.py:129-170); the exchange is ONE NCCL allreduce(SUM) of the flattened gradient - the
+    reference sums, it does not average (main.py:159) - replacing threads + barrier + peer copies.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class SageLayer(nn.Module):
+    def __init__(self, n_in, n_out, order, spmm):
+        super().__init__()
+        self.linearW = nn.Linear(n_in, n_out)
+        self.linearB = nn.Linear(n_in, n_out)
+        self.offset = nn.Parameter(torch.zeros((1 + order) * n_out))
+        self.scale = nn.Parameter(torch.ones((1 + order) * n_out))
+        self.order = order
+        self.spmm = spmm
+
+    def forward(self, x, adj, sampled_nodes):
+        if self.order > 0:
+            feat = self.spmm(adj, x)
+            feat = torch.cat([self.linearB(x[sampled_nodes]), self.linearW(feat)], 1)
+        else:
+            feat = self.linearW(x)
+        out = F.elu(feat)
+        mean = out.mean(dim=1, keepdim=True)
+        var = out.var(dim=1, unbiased=False, keepdim=True) + 1e-9
+        return (out - mean) * self.scale * torch.rsqrt(var) + self.offset
+
+
+class SageNet(nn.Module):
+    def __init__(self, nfeat, nhid, orders, num_classes, spmm, dropout=0.1):
+        super().__init__()
+        self.layers = nn.ModuleList([SageLayer(nfeat, nhid, orders[0], spmm)])
+        for i in range(len(orders) - 1):
+            self.layers.append(SageLayer((1 + orders[i]) * nhid, nhid, orders[i + 1], spmm))
+        self.dropout = nn.Dropout(dropout)
+        self.head = nn.Linear((1 + orders[-1]) * nhid, num_classes)
+
+    def forward(self, feat, adjs, sampled_nodes):
+        x = feat
+        for layer, adj, sn in zip(self.layers, adjs, sampled_nodes):
+            x = self.dropout(layer(x, adj, sn))
+        x = F.normalize(x, p=2, dim=1)
+        return self.head(self.dropout(x))
+
+
+def bce_loss(preds, labels):
+    w = torch.full((preds.shape[0], 1), 1.0 / preds.shape[0], device=preds.device)
+    return F.binary_cross_entropy_with_logits(preds, labels, weight=w, reduction="sum")
+
+
+def exchange_gradients(params, world):
+    """One allreduce(SUM) of the flattened gradient (reference main.py:149-168 / utils.py:152-160)."""
+    if world <= 1:
+        return 0
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    flat = torch.cat([gr.reshape(-1) for gr in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    off = 0
+    for gr in grads:
+        n = gr.numel()
+        gr.copy_(flat[off:off + n].view_as(gr))
+        off += n
+    return flat.numel() * 4
+
+
+def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, world, log):
+    """Full training steps over the rotated pre-sampled minibatches (sampling excluded, as stated in the line)."""
+    import torch.distributed as dist
+    from . import graphgen
+    torch.manual_seed(1234)                      # same initial replica on every rank (reference main.py:91-97 builds one per thread)
+    model = SageNet(shape.feat_dim, nhid, orders, shape.num_classes, cso.spmm).to(device)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=0.01)
+    labels_all = graphgen.labels(shape, seed=3)
+    prepared = []
+    for mb in mbs:
+        adjs = [cso.create_coo_tensor(torch.from_numpy(l.fullrowptr).to(device), torch.from_numpy(l.rowptr).to(device),
+                                      torch.from_numpy(l.colidx).to(device), torch.from_numpy(l.normfact).to(device),
+                                      l.nrows, l.ncols) for l in mb.layers]
+        sn = [torch.from_numpy(np.ascontiguousarray(s, dtype=np.int64)).to(device) for s in mb.sampled_nodes]
+        y = F.one_hot(torch.from_numpy(labels_all[mb.batch_nodes]), shape.num_classes).float().to(device)
+        prepared.append((adjs, sn, y, torch.from_numpy(mb.input_nodes).to(device)))
+
+    model.train()
+    comm_bytes = 0
+
+    def step(i):
+        nonlocal comm_bytes
+        adjs, sn, y, nodes = prepared[i % len(prepared)]
+        for a in adjs:
+            cso.adjacency_of(a)._t = None        # a fresh adjacency every minibatch: backward rebuilds its A^T index
+        opt.zero_grad(set_to_none=False)
+        x0 = store.gather(nodes)
+        out = model(x0, adjs, sn)
+        loss = bce_loss(out, y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 5)
+        comm_bytes = exchange_gradients(params, world)
+        opt.step()
+        return loss
+
+    steps = max(2, min(args.steps, 20))
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for s in range(steps):
+        loss = step(s)
+    ev1.record()
+    last = float(loss.item())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms, wall * 1e3], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall = float(t[0].item()), float(t[1].item()) / 1e3
+    nparams = sum(p.numel() for p in params)
+    return {"minibatches_per_s": round(world * steps / max(ms * 1e-3, wall), 2), "unit": "minibatches/s", "steps": steps,
+            "ms_per_step_device": round(ms / steps, 3), "ms_per_step_wall": round(wall / steps * 1e3, 3),
+            "allreduce_bytes_per_step": int(comm_bytes), "parameters": int(nparams), "final_loss": round(last, 4),
+            "note": "gather + GraphSAGE fwd + BCE loss + bwd + clip + NCCL allreduce(sum) + Adam on pre-sampled minibatches "
+                    "(host LADIES sampling and adjacency upload excluded)"}
