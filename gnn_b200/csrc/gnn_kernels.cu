@@ -88,8 +88,9 @@ __device__ __forceinline__ void ldg_vec(const float *p, float (&x)[VEC]) {
 template <bool GATHER>
 struct XSrc {
   const float *X;
-  int64_t ldx;
+  int ldx;                       // elements; < 2^31 (checked on the host)
   const float *const *xrows;
+  // start of X row c (one IMAD.WIDE for the dense case)
   __device__ __forceinline__ const float *row(int c) const {
     if constexpr (GATHER) return reinterpret_cast<const float *>(__ldg(reinterpret_cast<const unsigned long long *>(xrows) + c));
     else return X + (int64_t)c * ldx;
@@ -321,7 +322,7 @@ inline int spmm_chunk(int64_t nnz, int64_t D) {
 
 struct SpmmPlan { int vec, nv, lpr, nslabs, C, nchunks, Dp; };
 
-constexpr int64_t kTargetItems = 4096;   // warp items wanted before wider slabs are preferred
+constexpr int64_t kTargetItems = 2048;   // warp items wanted before wider slabs are preferred
 
 inline SpmmPlan make_plan(int64_t nnz, int64_t D, int vec) {
   SpmmPlan pl;
@@ -446,7 +447,7 @@ int spmm_entry(const int32_t *rowptr, const int32_t *colidx, const float *vals, 
   if (M < 0 || K < 0 || nnz < 0 || D < 0) return GNN_E_BADARG;
   if (M == 0 || D == 0) return 0;
   if (!Y || ldy < D) return GNN_E_BADARG;
-  if (M >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 2048 || K >= (1ll << 31) || D >= (1ll << 24)) return GNN_E_RANGE;
+  if (M >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 2048 || K >= (1ll << 31) || D >= (1ll << 24) || ldx >= (1ll << 31)) return GNN_E_RANGE;
   if (nnz == 0) {
     zero_rows_kernel<<<(unsigned)std::min<int64_t>(cdiv(M * D, 256), 148 * 16), 256, 0, st>>>(Y, ldy, M, D);
     GNN_LAUNCH_CHECK();
@@ -479,7 +480,7 @@ int spmm_entry(const int32_t *rowptr, const int32_t *colidx, const float *vals, 
   const size_t counter_bytes = spmm_counter_bytes(M, nnz, D);
   p.partials = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + counter_bytes);
   GNN_CUDA(cudaMemsetAsync(p.counters, 0, (size_t)M * pl.nslabs * sizeof(int), st));
-  XSrc<GATHER> xs{X, ldx, xrows};
+  XSrc<GATHER> xs{X, (int)ldx, xrows};
   switch (vec) {
     case 4: return launch_spmm_nv<4, GATHER>(pl, p, xs, st);
     case 2: if constexpr (!GATHER) return launch_spmm_nv<2, false>(pl, p, xs, st); else return GNN_E_BADARG;
