@@ -202,6 +202,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) go to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     def log(msg):
         if args.verbose or os.environ.get("BENCH_VERBOSE"):
@@ -404,7 +409,7 @@ def main():
         }
         if ref_gpu is not None:
             line["reference_cuda_kernels_same_gpu"] = ref_gpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -581,8 +586,17 @@ def run_reference(args, log):
                        "blocks": block_stats(mbs[0], widths)},
             "cpu_baseline": cpu, "gpu_launches": 0,
             "e2e": {"value": round(cpu["value"], 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 if __name__ == "__main__":

@@ -591,43 +591,42 @@ transpose_fill_kernel(const uint2 *__restrict__ cells, int M, int words_per_col,
   }
 }
 
-// exclusive scan of counts[0..n) into out[0..n], out[n] = total; single CTA of 1024 threads
+// exclusive scan of counts[0..n) into out[0..n], out[n] = total; single CTA of 1024 threads.
+// Thread t owns the contiguous slice [t*per, (t+1)*per): one serial pass for the slice sums, one block
+// scan of the 1024 sums, one serial pass to write - two barriers in total whatever n is.
 __global__ void __launch_bounds__(1024)
 exclusive_scan_kernel(const int *__restrict__ counts, int n, int *__restrict__ out) {
   __shared__ int warp_sums[32];
-  __shared__ int carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += counts[i];
+  int x = sum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int y = __shfl_up_sync(kFull, x, off);
+    if (lane >= off) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
   __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int v = i < n ? counts[i] : 0;
-    int x = v;
+  if (warp == 0) {
+    int w = warp_sums[lane];
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      const int y = __shfl_up_sync(kFull, x, off);
-      if (lane >= off) x += y;
+      const int y = __shfl_up_sync(kFull, w, off);
+      if (lane >= off) w += y;
     }
-    if (lane == 31) warp_sums[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      int w = warp_sums[lane];
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int y = __shfl_up_sync(kFull, w, off);
-        if (lane >= off) w += y;
-      }
-      warp_sums[lane] = w;
-    }
-    __syncthreads();
-    const int carry = carry_s;
-    const int incl = x + (warp ? warp_sums[warp - 1] : 0) + carry;
-    if (i < n) out[i] = incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = incl;
-    __syncthreads();
+    warp_sums[lane] = w;
   }
-  if (threadIdx.x == 0) out[n] = carry_s;
+  __syncthreads();
+  int run = x - sum + (warp ? warp_sums[warp - 1] : 0);      // exclusive prefix of this thread's slice
+  for (int i = lo; i < hi; ++i) {
+    const int v = counts[i];
+    out[i] = run;
+    run += v;
+  }
+  if (threadIdx.x == 1023) out[n] = warp_sums[31];
 }
 
 // ---------------------------------------------------------------------------
