@@ -534,17 +534,65 @@ __global__ void coo_to_csr_kernel(const int64_t *__restrict__ idx, int64_t M, in
 // so the entry (r, c) lands at t_rowptr[c] + cell.prefix + popc(cell.bits below r):
 // the transposed rows come out in ascending source row without any sort.
 // ---------------------------------------------------------------------------
+// Both passes over the nonzeros (set bits / fill) are nnz-balanced: a warp takes 256 consecutive nonzeros,
+// finds the rows its chunk touches with one uniform binary search, keeps 8 independent loads per lane in
+// flight, and resolves each nonzero's row by a search restricted to the chunk's few rows.
+constexpr int kTrChunk = 256;
+
+__device__ __forceinline__ int row_of_nnz(const int *__restrict__ rowptr, int lo, int hi, int i) {
+  // largest r in [lo, hi] with rowptr[r] <= i  (skips empty rows that share the same start)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(rowptr + mid) <= i) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+template <bool FILL>
 __global__ void __launch_bounds__(256)
-bitmap_set_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx, int M, int words_per_col,
-                  uint2 *__restrict__ cells) {
+transpose_pass_kernel(uint2 *__restrict__ cells, int M, int nnz, int words_per_col, const int *__restrict__ rowptr,
+                      const int *__restrict__ colidx, const float *__restrict__ vals, const int *__restrict__ t_rowptr,
+                      int *__restrict__ t_colidx, float *__restrict__ t_vals) {
   const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
-    const int b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
-    const unsigned bit = 1u << (r & 31);
-    const int word = r >> 5;
-    for (int i = b + lane; i < e; i += 32)
-      atomicOr(&cells[(int64_t)__ldg(colidx + i) * words_per_col + word].x, bit);
+  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t s64 = item * kTrChunk;
+  if (s64 >= nnz) return;
+  const int s = (int)s64, e = min(s + kTrChunk, nnz);
+  const int r_lo = row_of_nnz(rowptr, 0, M - 1, s);
+  const int r_hi = row_of_nnz(rowptr, r_lo, M - 1, e - 1);
+  constexpr int J = kTrChunk / 32;
+  int c[J], r[J];
+  float v[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int i = s + lane + 32 * j;
+    c[j] = i < e ? __ldg(colidx + i) : -1;
+    if (FILL) v[j] = i < e ? __ldg(vals + i) : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) r[j] = c[j] >= 0 ? row_of_nnz(rowptr, r_lo, r_hi, s + lane + 32 * j) : 0;
+  if (!FILL) {
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+      if (c[j] >= 0) atomicOr(&cells[(int64_t)c[j] * words_per_col + (r[j] >> 5)].x, 1u << (r[j] & 31));
+  } else {
+    uint2 cell[J];
+    int base[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      if (c[j] >= 0) {
+        cell[j] = __ldg(cells + (int64_t)c[j] * words_per_col + (r[j] >> 5));
+        base[j] = __ldg(t_rowptr + c[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      if (c[j] >= 0) {
+        const int pos = base[j] + (int)cell[j].y + __popc(cell[j].x & ((1u << (r[j] & 31)) - 1u));
+        t_colidx[pos] = r[j];
+        t_vals[pos] = v[j];
+      }
+    }
   }
 }
 
@@ -571,62 +619,51 @@ bitmap_prefix_kernel(uint2 *__restrict__ cells, int K, int words_per_col, int *_
   }
 }
 
-__global__ void __launch_bounds__(256)
-transpose_fill_kernel(const uint2 *__restrict__ cells, int M, int words_per_col, const int *__restrict__ rowptr,
-                      const int *__restrict__ colidx, const float *__restrict__ vals, const int *__restrict__ t_rowptr,
-                      int *__restrict__ t_colidx, float *__restrict__ t_vals) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
-    const int b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
-    const unsigned below = (1u << (r & 31)) - 1u;
-    const int word = r >> 5;
-    for (int i = b + lane; i < e; i += 32) {
-      const int c = __ldg(colidx + i);
-      const uint2 cell = __ldg(cells + (int64_t)c * words_per_col + word);
-      const int pos = __ldg(t_rowptr + c) + (int)cell.y + __popc(cell.x & below);
-      t_colidx[pos] = r;
-      t_vals[pos] = __ldg(vals + i);
-    }
-  }
-}
-
-// exclusive scan of counts[0..n) into out[0..n], out[n] = total; single CTA of 1024 threads.
-// Thread t owns the contiguous slice [t*per, (t+1)*per): one serial pass for the slice sums, one block
-// scan of the 1024 sums, one serial pass to write - two barriers in total whatever n is.
+// exclusive scan of counts[0..n) into out[0..n], out[n] = total; single CTA of 1024 threads, tiles of 4096
+// elements (4 consecutive per thread, coalesced), two barriers per tile.
 __global__ void __launch_bounds__(1024)
 exclusive_scan_kernel(const int *__restrict__ counts, int n, int *__restrict__ out) {
   __shared__ int warp_sums[32];
+  __shared__ int carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int per = (n + 1023) / 1024;
-  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
-  int sum = 0;
-  for (int i = lo; i < hi; ++i) sum += counts[i];
-  int x = sum;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const int y = __shfl_up_sync(kFull, x, off);
-    if (lane >= off) x += y;
-  }
-  if (lane == 31) warp_sums[warp] = x;
+  if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  if (warp == 0) {
-    int w = warp_sums[lane];
+  for (int base = 0; base < n; base += 4096) {
+    const int i0 = base + 4 * (int)threadIdx.x;
+    int v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = i0 + q < n ? counts[i0 + q] : 0;
+    const int sum = v[0] + v[1] + v[2] + v[3];
+    int x = sum;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      const int y = __shfl_up_sync(kFull, w, off);
-      if (lane >= off) w += y;
+      const int y = __shfl_up_sync(kFull, x, off);
+      if (lane >= off) x += y;
     }
-    warp_sums[lane] = w;
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    const int carry = carry_s;
+    if (warp == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(kFull, w, off);
+        if (lane >= off) w += y;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    int run = carry + x - sum + (warp ? warp_sums[warp - 1] : 0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (i0 + q < n) out[i0 + q] = run;
+      run += v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = run;
+    __syncthreads();
   }
-  __syncthreads();
-  int run = x - sum + (warp ? warp_sums[warp - 1] : 0);      // exclusive prefix of this thread's slice
-  for (int i = lo; i < hi; ++i) {
-    const int v = counts[i];
-    out[i] = run;
-    run += v;
-  }
-  if (threadIdx.x == 1023) out[n] = warp_sums[31];
+  if (threadIdx.x == 0) out[n] = carry_s;
 }
 
 // ---------------------------------------------------------------------------
@@ -797,14 +834,16 @@ int gnn_csr_transpose(const int32_t *rowptr, const int32_t *colidx, const float 
   int *counts = reinterpret_cast<int *>(workspace);
   uint2 *cells = reinterpret_cast<uint2 *>(reinterpret_cast<char *>(workspace) + ((size_t)K * 4 + 255) / 256 * 256);
   GNN_CUDA(cudaMemsetAsync(cells, 0, (size_t)K * words_per_col * sizeof(uint2), st));
-  bitmap_set_kernel<<<warp_grid(M, 8), 256, 0, st>>>(rowptr, colidx, (int)M, words_per_col, cells);
+  const unsigned pass_grid = (unsigned)cdiv(cdiv(nnz, kTrChunk), 8);
+  transpose_pass_kernel<false><<<pass_grid, 256, 0, st>>>(cells, (int)M, (int)nnz, words_per_col, rowptr, colidx, vals, t_rowptr,
+                                                         t_colidx, t_vals);
   GNN_LAUNCH_CHECK();
   bitmap_prefix_kernel<<<warp_grid(K, 8), 256, 0, st>>>(cells, (int)K, words_per_col, counts);
   GNN_LAUNCH_CHECK();
   exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, (int)K, t_rowptr);
   GNN_LAUNCH_CHECK();
-  transpose_fill_kernel<<<warp_grid(M, 8), 256, 0, st>>>(cells, (int)M, words_per_col, rowptr, colidx, vals, t_rowptr, t_colidx,
-                                                        t_vals);
+  transpose_pass_kernel<true><<<pass_grid, 256, 0, st>>>(cells, (int)M, (int)nnz, words_per_col, rowptr, colidx, vals, t_rowptr,
+                                                        t_colidx, t_vals);
   GNN_LAUNCH_CHECK();
   return 0;
 }

@@ -42,6 +42,9 @@ SHAPES = {
     "reddit": GraphShape("reddit", 232965, 57307946, 602, 41, max_degree=21657),
     # ogbn-products: 2,449,029 nodes / 61.86 M undirected edges / 100-d / 47 classes, GCN => +I
     "products": GraphShape("products", 2449029, 61859140, 100, 47, max_degree=17481, self_loops=True),
+    # ogbn-papers100M scaled by 1/16 in nodes and edges (111 M nodes / 1.6 B undirected edges do not fit the
+    # time budget of a bench run; degree statistics are kept: mean directed degree ~29), 128-d, GCN => +I
+    "papers16": GraphShape("papers16", 6941000, 100000000, 128, 172, max_degree=15000, self_loops=True),
     # small shapes used by the CPU test-suite and smoke()
     "tiny": GraphShape("tiny", 600, 3000, 37, 5, max_degree=90, self_loops=True),
     "small": GraphShape("small", 20000, 400000, 100, 16, max_degree=2500),

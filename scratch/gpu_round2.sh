@@ -6,5 +6,5 @@ python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-train > gpu
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-train > gpurun_out/ncu1.log 2>&1
 echo "ncu1 rc=$?"
 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-train > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"spmm_rowsplit|transpose_fill|bitmap" -c 13 -o gpurun_out/prof_r1_spmm python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-train > gpurun_out/ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"spmm_rowsplit|transpose_pass|bitmap" -c 13 -o gpurun_out/prof_r1_spmm python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-train > gpurun_out/ncu2.log 2>&1
 echo "ncu2 rc=$?"
