@@ -262,9 +262,13 @@ def main():
                       for li, (l, D) in enumerate(zip(mb.layers, widths))) for mb in mbs]
 
     flush_buf = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=device)   # 3x L2
+    flush_src = torch.zeros(96 * 1024 * 1024, dtype=torch.int32, device=device)   # 384 MiB, read-only
 
     def flush_l2():
+        # write 384 MiB, then read 384 MiB: the cache ends up full of CLEAN foreign lines, so the timed kernels
+        # start cold without also paying for the write-back of the flush's own dirty lines
         flush_buf.zero_()
+        flush_src.sum()
 
     op_names = [f"fwd{li}" for li in range(nl)] + [f"bwd{li}" for li in range(1, nl)]
 
@@ -400,7 +404,7 @@ def main():
                        "graph": {"nodes": g.num_nodes, "directed_nnz": g.nnz, "feat_dim": shape.feat_dim, "alpha": shape.alpha,
                                  "max_degree": int(g.degrees().max())},
                        "blocks": block_stats(mbs[0], widths), "minibatches_rotated": len(mbs),
-                       "l2": "flushed between steps (384 MiB write) and inputs rotate over >L2 working sets",
+                       "l2": "flushed between steps (384 MiB write + 384 MiB read) and inputs rotate over >L2 working sets",
                        "sharding": "each rank its own minibatches, no data-path collective in `value`",
                        "bwd_includes": "CSR-of-A^T build (gnn_csr_transpose) every step"},
             "wall_ms_per_step_incl_flush": round(wall / args.steps * 1e3, 4),

@@ -104,6 +104,18 @@ class FeatureStore:
         _, _, xrows, _ = self.remap(input_nodes)
         return self.ext.gather_rows(xrows, self.feat_dim, self.ld)
 
+    def prefetch(self, input_nodes: torch.Tensor, stream: "torch.cuda.Stream"):
+        """Issue remap + gather for a FUTURE minibatch on ``stream`` (host rows cross PCIe while the current step
+        computes).  Returns (buffer view, event); wait on the event before the first use."""
+        with torch.cuda.stream(stream):
+            src_dev, _, xrows, _ = self.remap(input_nodes)
+            buf = torch.empty((input_nodes.numel(), self.ld), dtype=torch.float32, device=self.device)
+            self.ext.gather_rows_src(xrows, src_dev, -100, self.feat_dim, buf)      # GNN_SRC_DEVICES: HBM / NVLink rows
+            self.ext.gather_rows_src(xrows, src_dev, -1, self.feat_dim, buf)        # host rows: small grid, PCIe-bound
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return buf[:, :self.feat_dim], ev
+
     def gather_from_reference_tuple(self, masks_on_devices, mask_on_cpu, idx_on_devices, idx_on_cpu, num_input_nodes):
         """Same gather driven by the reference sampler's own outputs (sampler.py:160 tuple), for main.py drop-in use:
         the masks / slot lists are folded into a pointer table on the host, then one gather kernel runs."""

@@ -103,6 +103,10 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
 
     model.train()
     comm_bytes = 0
+    # input features of minibatch i+1 are gathered on a side stream while minibatch i computes (the reference
+    # prefetches whole minibatches in sampler threads; its gather itself is synchronous, main.py:129-137)
+    side = torch.cuda.Stream(device=device)
+    pending = {}
 
     def step(i):
         nonlocal comm_bytes
@@ -110,7 +114,14 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
         for a in adjs:
             cso.adjacency_of(a)._t = None        # a fresh adjacency every minibatch: backward rebuilds its A^T index
         opt.zero_grad(set_to_none=False)
-        x0 = store.gather(nodes)
+        if i in pending:
+            x0, ev = pending.pop(i)
+            torch.cuda.current_stream().wait_event(ev)
+            x0.record_stream(torch.cuda.current_stream())
+        else:
+            x0 = store.gather(nodes)
+        side.wait_stream(torch.cuda.current_stream())
+        pending[i + 1] = store.prefetch(prepared[(i + 1) % len(prepared)][3], side)
         out = model(x0, adjs, sn)
         loss = bce_loss(out, y)
         loss.backward()
@@ -122,6 +133,9 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
     steps = max(2, min(args.steps, 20))
     for i in range(3):
         step(i)
+    pending.clear()
+    torch.cuda.synchronize()
+
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -131,6 +145,7 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
     for s in range(steps):
         loss = step(s)
     ev1.record()
+    pending.clear()
     last = float(loss.item())
     torch.cuda.synchronize()
     if world > 1:
@@ -145,5 +160,5 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
     return {"minibatches_per_s": round(world * steps / max(ms * 1e-3, wall), 2), "unit": "minibatches/s", "steps": steps,
             "ms_per_step_device": round(ms / steps, 3), "ms_per_step_wall": round(wall / steps * 1e3, 3),
             "allreduce_bytes_per_step": int(comm_bytes), "parameters": int(nparams), "final_loss": round(last, 4),
-            "note": "gather + GraphSAGE fwd + BCE loss + bwd + clip + NCCL allreduce(sum) + Adam on pre-sampled minibatches "
-                    "(host LADIES sampling and adjacency upload excluded)"}
+            "note": "gather (next minibatch prefetched on a side stream) + GraphSAGE fwd + BCE loss + bwd + clip + NCCL "
+                    "allreduce(sum) + Adam on pre-sampled minibatches (host LADIES sampling and adjacency upload excluded)"}

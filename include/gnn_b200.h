@@ -166,8 +166,10 @@ int gnn_placement_remap(const int64_t *input_nodes, int64_t n0,
 int gnn_gather_rows_f32(const float *const *xrows, int64_t n0, int64_t F,
                         float *out, int64_t ld_out, gnn_stream_t stream);
 
-/* Same gather restricted to the rows j with src_dev[j] == only_src (e.g. only peer
- * rows), so transfers from different sources can be put on different streams. */
+/* Same gather restricted to the rows j with src_dev[j] == only_src (-1 = host rows, i = GPU i's rows,
+ * GNN_SRC_DEVICES = every row held by some GPU), so transfers from different sources can be put on
+ * different streams.  Host rows are PCIe-bound and use a deliberately small grid. */
+#define GNN_SRC_DEVICES (-100)
 int gnn_gather_rows_src_f32(const float *const *xrows, const int32_t *src_dev, int32_t only_src,
                             int64_t n0, int64_t F, float *out, int64_t ld_out, gnn_stream_t stream);
 

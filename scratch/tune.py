@@ -43,7 +43,7 @@ for b in blocks:
     print(f"layer{b['li']} D={b['D']} default: {t*1e3:.1f} us", flush=True)
 res = []
 for b in blocks:
-    cs = [1024] if b['li'] < 2 else [64]
+    cs = [512, 1024] if b['li'] < 2 else [32, 64]
     for nv, u, minb, c in itertools.product([1, 2, 3, 4, 5], [1, 2, 4, 8], [2, 3, 4], cs):
         if nv * u > 16 or nv * u < 4: continue
         os.environ.update(GNN_TUNE_NV=str(nv), GNN_TUNE_U=str(u), GNN_TUNE_MINB=str(minb), GNN_TUNE_C=str(c))

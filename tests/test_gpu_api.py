@@ -116,3 +116,50 @@ def test_gcn_style_two_layer_grad_flow(cso, mb):
     out = cso.spmm(a1, h)
     out.square().mean().backward()
     assert lin.weight.grad is not None and torch.isfinite(lin.weight.grad).all() and lin.weight.grad.abs().sum() > 0
+
+
+def test_cuda_graph_capture_and_stream_semantics(cso, mb):
+    """No host sync, no legacy-stream launch, no raw cudaMalloc on the path: forward + transpose + backward can be
+    captured in a CUDA graph on a side stream and replayed (the reference issues 5 device syncs per call)."""
+    layer = mb.layers[1]
+    a = cso.create_coo_tensor(*_upload(layer))
+    adj = cso.adjacency_of(a)
+    x = torch.randn(layer.ncols, 128, device="cuda")
+    go = torch.randn(layer.nrows, 128, device="cuda")
+    y_ref, dx_ref = adj.matmul(x), adj.matmul_t(go)
+    adj._t = None
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        y = adj.matmul(x)
+        dx = adj.matmul_t(go)          # includes the A^T build
+    for _ in range(3):
+        x.normal_()
+        go.normal_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(y, adj.matmul(x)) and torch.equal(dx, adj.matmul_t(go))
+    assert y_ref.shape == y.shape and dx_ref.shape == dx.shape
+
+
+def test_feature_store_prefetch_matches_gather(cso):
+    from gnn_b200 import gather, graphgen
+    shape = graphgen.SHAPES["tiny"]
+    feats = graphgen.features(shape, seed=1)
+    n = shape.num_nodes
+    top = np.arange(0, n, 3)
+    did = np.full(n, -1, dtype=np.int64)
+    did[top] = 0
+    idx = np.arange(n, dtype=np.int64)
+    idx[top] = np.arange(top.size)
+    store = gather.FeatureStore(torch.from_numpy(feats), [top], did, idx, [0], 0, torch.device("cuda", 0))
+    nodes = torch.from_numpy(np.sort(np.random.Generator(np.random.PCG64(4)).choice(n, 200, replace=False))).cuda()
+    side = torch.cuda.Stream()
+    out, ev = store.prefetch(nodes, side)
+    torch.cuda.current_stream().wait_event(ev)
+    assert np.array_equal(out.cpu().numpy(), feats[nodes.cpu().numpy()])
+    assert torch.equal(out, store.gather(nodes))
+    masks = [(did[nodes.cpu().numpy()] == 0)]
+    ref = store.gather_from_reference_tuple(masks, ~masks[0], [idx[nodes.cpu().numpy()[masks[0]]]], nodes.cpu().numpy()[~masks[0]], 200)
+    assert torch.equal(ref, out)
+    store.close()

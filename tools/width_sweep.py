@@ -22,10 +22,17 @@ import custom_sparse_ops as cso  # noqa: E402
 from gnn_b200 import graphgen, sampler  # noqa: E402
 
 
+_FLUSH_SRC = None
+
+
 def timed(fn, flush, reps=5):
+    global _FLUSH_SRC
+    if _FLUSH_SRC is None:
+        _FLUSH_SRC = torch.zeros(96 << 20, dtype=torch.int32, device=flush.device)
     ts = []
     for r in range(reps + 2):
         flush.zero_()
+        _FLUSH_SRC.sum()          # leave the cache full of clean lines (no write-back inside the timed region)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
