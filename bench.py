@@ -541,6 +541,29 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
         torch.cuda.synchronize()
         ms = ev[0].elapsed_time(ev[1]) / 3
         out.setdefault("gather_GBps", {})[name] = round(float(rows) * store.feat_dim * 4 / (ms * 1e-3) / 1e9, 1)
+    # NVLink roof of the peer-gather path: 64 Ki random rows of the next rank's shard (158 MB at F=602), one launch
+    if world > 1:
+        peer = (rank + 1) % world
+        shard = store.shards[peer]
+        gen = torch.Generator(device=device)
+        gen.manual_seed(3 + rank)
+        nrows = 65536
+        slots = torch.randint(0, shard.shape[0], (nrows,), device=device, generator=gen)
+        ptrs = shard.data_ptr() + slots * (store.ld * 4)
+        big = torch.empty((nrows, store.ld), device=device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for rep in range(4):
+            if rep == 1:
+                ev[0].record()
+            store.ext.gather_rows_src(ptrs, torch.zeros(nrows, dtype=torch.int32, device=device), 0, store.feat_dim, big)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / 3
+        ok = bool(torch.equal(big[:, :store.feat_dim], shard[slots][:, :store.feat_dim]))
+        gbs = nrows * store.feat_dim * 4 / (ms * 1e-3) / 1e9
+        out["peer_gather_roof"] = {"GBps": round(gbs, 1), "rows": nrows, "bytes": int(nrows * store.feat_dim * 4),
+                                   "frac_of_measured_peer_copy_770": round(gbs / 770.0, 3), "frac_of_nominal_900": round(gbs / 900.0, 3),
+                                   "bit_exact": ok, "note": "one-sided reads of the next rank's shard over NVLink, one kernel"}
     return out
 
 
