@@ -297,3 +297,86 @@ def test_index_rows(cu):
         idx = rng.integers(0, 500, 333)
         out = cu.index_rows(cu.dev(X), cu.dev(idx)).cpu().numpy()
         assert np.array_equal(out, X[idx])
+
+
+# --------------------------------------------------------------------------- error paths and limits
+def test_error_codes_and_workspace_contract(cu):
+    import ctypes
+    from gnn_b200 import _native
+    lib = _native.cabi()
+    rowptr = cu.dev(np.array([0, 2, 3], np.int32))
+    col = cu.dev(np.array([0, 1, 1], np.int32))
+    vals = cu.dev(np.array([1, 2, 3], np.float32))
+    X = torch.ones(2, 8, device="cuda")
+    Y = torch.zeros(2, 8, device="cuda")
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    need = lib.gnn_csr_spmm_workspace_bytes(2, 3, 8)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    assert lib.gnn_csr_spmm_f32(P(rowptr), P(col), P(vals), 2, 2, 3, 8, P(X), 8, P(Y), 8, None, 0, st) == -2          # no workspace
+    assert lib.gnn_csr_spmm_f32(P(rowptr), P(col), P(vals), 2, 2, 3, 8, P(X), 8, P(Y), 8, P(ws), need - 1, st) == -2   # too small
+    assert lib.gnn_csr_spmm_f32(P(rowptr), P(col), P(vals), 2, 2, 3, 8, P(X), 4, P(Y), 8, P(ws), need, st) == -1       # ldx < D
+    assert lib.gnn_csr_spmm_f32(P(rowptr), P(col), P(vals), 2, 2, 3, 8, P(X), 8, P(Y), 8, P(ws), need, st) == 0
+    torch.cuda.synchronize()
+    assert Y.tolist() == [[3.0] * 8, [3.0] * 8]
+    assert lib.gnn_csr_spmm_f32(P(rowptr), P(col), P(vals), 2, 2, 3, 1 << 25, P(X), 1 << 25, P(Y), 1 << 25, P(ws), need, st) == -3   # D limit
+    assert lib.gnn_build_adj(P(rowptr), P(rowptr), P(col), 8, P(vals), 2, 2, 3, None, P(vals), None, st) == -1       # colidx width
+
+
+def test_int32_columns_beyond_int16_range(cu):
+    """K > 32767 needs int32 column ids (the reference's int16 hand-off silently wraps)."""
+    rng = np.random.Generator(np.random.PCG64(9))
+    M, K, D = 200, 70000, 40
+    lens = rng.integers(1, 60, M)
+    rowptr, cols, _ = _random_csr(rng, M, K, lens)
+    full = np.zeros(M + 1, np.int32)
+    full[1:] = np.cumsum(lens + 3)
+    nf = rng.random(K).astype(np.float32) + 0.5
+    idx, vals, col32 = cu.build_adj(cu.dev(full), cu.dev(rowptr), cu.dev(cols), cu.dev(nf), M, K)
+    rows_o, cols_o, vals_o = oracle.build_adj(full, rowptr, cols, nf, M)
+    assert np.array_equal(idx.cpu().numpy(), np.stack([rows_o, cols_o])) and cols_o.max() > 32767
+    assert np.array_equal(vals.cpu().numpy().view(np.uint32), vals_o.view(np.uint32))
+    X = rng.standard_normal((K, D)).astype(np.float32)
+    Y = cu.csr_spmm(cu.dev(rowptr), col32, vals, M, K, cu.dev(X)).cpu().numpy()
+    assert oracle.rel_err(Y, oracle.spmm_f64acc(rowptr, cols, vals_o, M, X))[0] <= TOL
+    t = cu.csr_transpose(cu.dev(rowptr), col32, vals, M, K)
+    o_rowptr, o_col, perm = oracle.csr_transpose(rowptr, cols, M, K)
+    assert np.array_equal(t[0].cpu().numpy(), o_rowptr) and np.array_equal(t[1].cpu().numpy(), o_col)
+
+
+def test_concurrent_threads_and_streams(cu, small_mb):
+    """The reference is entered concurrently from trainer and sampler threads: four Python threads,
+    each on its own stream, run create/spmm/transpose/spmm at once; results must equal the single-threaded ones."""
+    import threading
+    import custom_sparse_ops as cso
+    _, _, mb = small_mb
+    layer = mb.layers[0]
+    args = [torch.from_numpy(a).cuda() for a in (layer.fullrowptr, layer.rowptr, layer.colidx, layer.normfact)]
+    X = torch.randn(layer.ncols, 100, device="cuda")
+    G = torch.randn(layer.nrows, 100, device="cuda")
+    a0 = cso.create_coo_tensor(*args, layer.nrows, layer.ncols)
+    y0 = cso.adjacency_of(a0).matmul(X)
+    d0 = cso.adjacency_of(a0).matmul_t(G)
+    torch.cuda.synchronize()
+    results, errors = {}, []
+
+    def work(tid):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(5):
+                    a = cso.create_coo_tensor(*args, layer.nrows, layer.ncols)
+                    adj = cso.adjacency_of(a)
+                    y, d = adj.matmul(X), adj.matmul_t(G)
+                s.synchronize()
+            results[tid] = (torch.equal(y, y0), torch.equal(d, d0), torch.equal(a._values(), a0._values()))
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert all(all(v) for v in results.values()) and len(results) == 4
