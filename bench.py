@@ -384,6 +384,11 @@ def main():
     if not args.no_train:
         from gnn_b200 import harness
         train = harness.bench_train(args, cso, store, shape, g, mbs, ORDERS, NHID, device, rank, world, log)
+        try:
+            train["live_sampler"] = harness.bench_train_live(args, cso, store, shape, g, ORDERS, NHID, samp, batch, device, rank,
+                                                             world, log)
+        except Exception as exc:                       # the secondary number must not take the headline down
+            train["live_sampler"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if store is not None:
         store.close()
 

@@ -61,6 +61,11 @@ def cabi() -> ctypes.CDLL:
                 "gnn_gather_rows_f32": (ctypes.c_int, [vp, i64, i64, vp, i64, vp]),
                 "gnn_gather_rows_src_f32": (ctypes.c_int, [vp, vp, i32, i64, i64, vp, i64, vp]),
                 "gnn_index_rows_f32": (ctypes.c_int, [vp, i64, vp, i64, i64, vp, i64, vp]),
+                "gnn_row_slice_count": (ctypes.c_int, [vp, vp, i64, vp, vp, vp]),
+                "gnn_row_slice_fill": (ctypes.c_int, [vp, vp, vp, i64, vp, vp, vp, vp]),
+                "gnn_lookup_set": (ctypes.c_int, [vp, vp, i64, ctypes.c_int, vp]),
+                "gnn_column_slice_count": (ctypes.c_int, [vp, vp, i64, vp, vp, vp, vp]),
+                "gnn_column_slice_fill": (ctypes.c_int, [vp, vp, i64, vp, vp, vp, ctypes.c_int, vp]),
                 "gnn_shard_alloc": (ctypes.c_int, [sz, ctypes.POINTER(vp), ctypes.c_char_p]),
                 "gnn_shard_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(vp)]),
                 "gnn_shard_close": (ctypes.c_int, [vp]),

@@ -673,6 +673,65 @@ exclusive_scan_kernel(const int *__restrict__ counts, int n, int *__restrict__ o
 }
 
 // ---------------------------------------------------------------------------
+// LADIES layer construction on the device (the array work of reference sampler.py:113-137; the weighted draw
+// itself stays numpy on the host so the sampled node set is bit-identical to the reference)
+// ---------------------------------------------------------------------------
+__global__ void row_lengths_kernel(const int64_t *__restrict__ indptr, const int64_t *__restrict__ nodes, int M,
+                                   int *__restrict__ lens) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) {
+    const int64_t n = nodes[i];
+    lens[i] = (int)(indptr[n + 1] - indptr[n]);
+  }
+}
+
+// U = lap_matrix[nodes, :] (structure): copy every row's column ids; optionally count columns (ord=0 column norm)
+__global__ void __launch_bounds__(256)
+row_slice_kernel(const int64_t *__restrict__ indptr, const int *__restrict__ indices, const int64_t *__restrict__ nodes, int M,
+                 const int *__restrict__ fullrowptr, int *__restrict__ ucols, int *__restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
+    const int64_t src = indptr[nodes[r]];
+    const int dst = __ldg(fullrowptr + r);
+    const int len = __ldg(fullrowptr + r + 1) - dst;
+    for (int i = lane; i < len; i += 32) {
+      const int c = __ldg(indices + src + i);
+      ucols[dst + i] = c;
+      if (counts) atomicAdd(counts + c, 1);
+    }
+  }
+}
+
+__global__ void lookup_set_kernel(int *__restrict__ lookup, const int64_t *__restrict__ after_nodes, int K, int set) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < K) lookup[after_nodes[j]] = set ? j : -1;
+}
+
+// adj = U[:, after_nodes] (structure): keep the entries whose column was sampled, renumbered by lookup.
+// FILL == false: per-row kept counts; FILL == true: write the local column ids at rowptr[r]...
+template <bool FILL, typename ColT>
+__global__ void __launch_bounds__(256)
+column_slice_kernel(const int *__restrict__ ucols, const int *__restrict__ fullrowptr, int M, const int *__restrict__ lookup,
+                    int *__restrict__ row_counts, const int *__restrict__ rowptr, ColT *__restrict__ colidx) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
+    const int b = __ldg(fullrowptr + r), e = __ldg(fullrowptr + r + 1);
+    int run = FILL ? __ldg(rowptr + r) : 0;
+    for (int i0 = b; i0 < e; i0 += 32) {
+      const int i = i0 + lane;
+      const int local = i < e ? __ldg(lookup + __ldg(ucols + i)) : -1;
+      const unsigned m = __ballot_sync(kFull, local >= 0);
+      if (FILL && local >= 0) colidx[run + __popc(m & lt)] = (ColT)local;
+      run += __popc(m);
+    }
+    if (!FILL && lane == 0) row_counts[r] = run;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // placement remap + gathers
 // ---------------------------------------------------------------------------
 __global__ void placement_remap_kernel(const int64_t *__restrict__ input_nodes, int64_t n0,
@@ -707,7 +766,12 @@ gather_rows_kernel(const float *const *__restrict__ xrows, const int *__restrict
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int64_t j = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); j < n0; j += (int64_t)gridDim.x * wpb) {
-    if (FILTER && (only_src == GNN_SRC_DEVICES ? src_dev[j] < 0 : src_dev[j] != only_src)) continue;
+    if (FILTER) {
+      const int sd = src_dev[j];
+      const bool take = only_src == GNN_SRC_DEVICES ? sd >= 0
+                        : (only_src <= GNN_SRC_NOT(0) ? (sd != GNN_SRC_NOT(only_src) && sd != -2) : sd == only_src);
+      if (!take) continue;
+    }
     const float *src = INDEX ? X + idx[j] * ldx : xrows[j];
     if (!src) continue;
     float *dst = out + j * ld_out;
@@ -904,6 +968,70 @@ int gnn_index_rows_f32(const float *X, int64_t ldx, const int64_t *idx, int64_t 
   if (!X || !idx || !out || ld_out < F || ldx < F) return GNN_E_BADARG;
   gather_rows_kernel<false, true><<<warp_grid(n, 8), 256, 0, (cudaStream_t)stream>>>(nullptr, nullptr, 0, X, ldx, idx, n,
                                                                                     (int)F, out, ld_out);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnn_row_slice_count(const int64_t *indptr, const int64_t *nodes, int64_t M, int32_t *scratch_lens,
+                        int32_t *out_fullrowptr, gnn_stream_t stream) {
+  if (M < 0) return GNN_E_BADARG;
+  if (M >= (1ll << 31) - 1) return GNN_E_RANGE;
+  if (!out_fullrowptr || (M > 0 && (!indptr || !nodes || !scratch_lens))) return GNN_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 0) { GNN_CUDA(cudaMemsetAsync(out_fullrowptr, 0, sizeof(int), st)); return 0; }
+  row_lengths_kernel<<<(unsigned)cdiv(M, 256), 256, 0, st>>>(indptr, nodes, (int)M, scratch_lens);
+  GNN_LAUNCH_CHECK();
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(scratch_lens, (int)M, out_fullrowptr);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnn_row_slice_fill(const int64_t *indptr, const int32_t *indices, const int64_t *nodes, int64_t M,
+                       const int32_t *fullrowptr, int32_t *out_cols, int32_t *col_counts, gnn_stream_t stream) {
+  if (M < 0) return GNN_E_BADARG;
+  if (M == 0) return 0;
+  if (!indptr || !indices || !nodes || !fullrowptr || !out_cols) return GNN_E_BADARG;
+  row_slice_kernel<<<warp_grid(M, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, nodes, (int)M, fullrowptr, out_cols,
+                                                                      col_counts);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnn_lookup_set(int32_t *lookup, const int64_t *after_nodes, int64_t K, int set, gnn_stream_t stream) {
+  if (K < 0 || K >= (1ll << 31)) return GNN_E_BADARG;
+  if (K == 0) return 0;
+  if (!lookup || !after_nodes) return GNN_E_BADARG;
+  lookup_set_kernel<<<(unsigned)cdiv(K, 256), 256, 0, (cudaStream_t)stream>>>(lookup, after_nodes, (int)K, set);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnn_column_slice_count(const int32_t *ucols, const int32_t *fullrowptr, int64_t M, const int32_t *lookup,
+                           int32_t *scratch_counts, int32_t *out_rowptr, gnn_stream_t stream) {
+  if (M < 0) return GNN_E_BADARG;
+  if (!out_rowptr || (M > 0 && (!ucols || !fullrowptr || !lookup || !scratch_counts))) return GNN_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 0) { GNN_CUDA(cudaMemsetAsync(out_rowptr, 0, sizeof(int), st)); return 0; }
+  column_slice_kernel<false, int><<<warp_grid(M, 8), 256, 0, st>>>(ucols, fullrowptr, (int)M, lookup, scratch_counts, nullptr,
+                                                                   nullptr);
+  GNN_LAUNCH_CHECK();
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(scratch_counts, (int)M, out_rowptr);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnn_column_slice_fill(const int32_t *ucols, const int32_t *fullrowptr, int64_t M, const int32_t *lookup,
+                          const int32_t *rowptr, void *out_colidx, int colidx_bytes, gnn_stream_t stream) {
+  if (M < 0 || (colidx_bytes != 2 && colidx_bytes != 4)) return GNN_E_BADARG;
+  if (M == 0) return 0;
+  if (!ucols || !fullrowptr || !lookup || !rowptr || !out_colidx) return GNN_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (colidx_bytes == 2)
+    column_slice_kernel<true, int16_t><<<warp_grid(M, 8), 256, 0, st>>>(ucols, fullrowptr, (int)M, lookup, nullptr, rowptr,
+                                                                        (int16_t *)out_colidx);
+  else
+    column_slice_kernel<true, int><<<warp_grid(M, 8), 256, 0, st>>>(ucols, fullrowptr, (int)M, lookup, nullptr, rowptr,
+                                                                    (int *)out_colidx);
   GNN_LAUNCH_CHECK();
   return 0;
 }

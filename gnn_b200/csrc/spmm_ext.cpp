@@ -226,6 +226,70 @@ torch::Tensor index_rows(const torch::Tensor &X, const torch::Tensor &idx) {
   return out;
 }
 
+// ---- LADIES layer construction on the device (array work of sampler.py:113-137) ----------
+torch::Tensor row_slice_count(const torch::Tensor &indptr, const torch::Tensor &nodes) {
+  CHECK_DENSE(indptr); CHECK_DENSE(nodes);
+  TORCH_CHECK(indptr.scalar_type() == torch::kLong && nodes.scalar_type() == torch::kLong, "indptr / nodes must be int64");
+  c10::cuda::CUDAGuard g(nodes.device());
+  const int64_t M = nodes.numel();
+  auto iopt = nodes.options().dtype(torch::kInt);
+  auto lens = torch::empty({M}, iopt);
+  auto fullrowptr = torch::empty({M + 1}, iopt);
+  check_rc(gnn_row_slice_count(indptr.data_ptr<int64_t>(), nodes.data_ptr<int64_t>(), M, lens.data_ptr<int32_t>(),
+                               fullrowptr.data_ptr<int32_t>(), cur_stream()),
+           "gnn_row_slice_count");
+  return fullrowptr;
+}
+
+torch::Tensor row_slice_fill(const torch::Tensor &indptr, const torch::Tensor &indices, const torch::Tensor &nodes,
+                             const torch::Tensor &fullrowptr, int64_t total, c10::optional<torch::Tensor> col_counts) {
+  CHECK_DENSE(indptr); CHECK_DENSE(indices); CHECK_DENSE(nodes); CHECK_DENSE(fullrowptr);
+  TORCH_CHECK(indices.scalar_type() == torch::kInt && fullrowptr.scalar_type() == torch::kInt, "indices / fullrowptr must be int32");
+  if (col_counts.has_value()) {
+    CHECK_DENSE(col_counts.value());
+    TORCH_CHECK(col_counts.value().scalar_type() == torch::kInt, "col_counts must be int32");
+  }
+  c10::cuda::CUDAGuard g(nodes.device());
+  auto ucols = torch::empty({total}, fullrowptr.options());
+  check_rc(gnn_row_slice_fill(indptr.data_ptr<int64_t>(), indices.data_ptr<int32_t>(), nodes.data_ptr<int64_t>(), nodes.numel(),
+                              fullrowptr.data_ptr<int32_t>(), ucols.data_ptr<int32_t>(),
+                              col_counts.has_value() ? col_counts.value().data_ptr<int32_t>() : nullptr, cur_stream()),
+           "gnn_row_slice_fill");
+  return ucols;
+}
+
+void lookup_set(torch::Tensor lookup, const torch::Tensor &after_nodes, bool set) {
+  CHECK_DENSE(lookup); CHECK_DENSE(after_nodes);
+  TORCH_CHECK(lookup.scalar_type() == torch::kInt && after_nodes.scalar_type() == torch::kLong, "lookup int32, after_nodes int64");
+  c10::cuda::CUDAGuard g(lookup.device());
+  check_rc(gnn_lookup_set(lookup.data_ptr<int32_t>(), after_nodes.data_ptr<int64_t>(), after_nodes.numel(), set ? 1 : 0, cur_stream()),
+           "gnn_lookup_set");
+}
+
+torch::Tensor column_slice_count(const torch::Tensor &ucols, const torch::Tensor &fullrowptr, const torch::Tensor &lookup) {
+  CHECK_DENSE(ucols); CHECK_DENSE(fullrowptr); CHECK_DENSE(lookup);
+  c10::cuda::CUDAGuard g(ucols.device());
+  const int64_t M = fullrowptr.numel() - 1;
+  auto counts = torch::empty({M}, fullrowptr.options());
+  auto rowptr = torch::empty({M + 1}, fullrowptr.options());
+  check_rc(gnn_column_slice_count(ucols.data_ptr<int32_t>(), fullrowptr.data_ptr<int32_t>(), M, lookup.data_ptr<int32_t>(),
+                                  counts.data_ptr<int32_t>(), rowptr.data_ptr<int32_t>(), cur_stream()),
+           "gnn_column_slice_count");
+  return rowptr;
+}
+
+torch::Tensor column_slice_fill(const torch::Tensor &ucols, const torch::Tensor &fullrowptr, const torch::Tensor &lookup,
+                                const torch::Tensor &rowptr, int64_t nnz, bool int16_ids) {
+  CHECK_DENSE(ucols); CHECK_DENSE(fullrowptr); CHECK_DENSE(lookup); CHECK_DENSE(rowptr);
+  c10::cuda::CUDAGuard g(ucols.device());
+  const int64_t M = fullrowptr.numel() - 1;
+  auto colidx = torch::empty({nnz}, fullrowptr.options().dtype(int16_ids ? torch::kShort : torch::kInt));
+  check_rc(gnn_column_slice_fill(ucols.data_ptr<int32_t>(), fullrowptr.data_ptr<int32_t>(), M, lookup.data_ptr<int32_t>(),
+                                 rowptr.data_ptr<int32_t>(), colidx.data_ptr(), int16_ids ? 2 : 4, cur_stream()),
+           "gnn_column_slice_fill");
+  return colidx;
+}
+
 // ---- peer-mappable feature shards ---------------------------------------
 std::tuple<torch::Tensor, py::bytes> shard_alloc(int64_t rows, int64_t ld, int64_t device_index) {
   c10::cuda::CUDAGuard g(c10::Device(c10::kCUDA, (c10::DeviceIndex)device_index));
@@ -274,6 +338,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gather_rows", &gather_rows, "out[j] = *xrows[j]", rel());
   m.def("gather_rows_src", &gather_rows_src, "gather only the rows of one source", rel());
   m.def("index_rows", &index_rows, "out[i] = X[idx[i]]", rel());
+  m.def("row_slice_count", &row_slice_count, "fullrowptr of lap_matrix[nodes, :]", rel());
+  m.def("row_slice_fill", &row_slice_fill, "column ids of lap_matrix[nodes, :] (+ column counts)", rel());
+  m.def("lookup_set", &lookup_set, "lookup[after_nodes[j]] = j or -1", rel());
+  m.def("column_slice_count", &column_slice_count, "rowptr of U[:, after_nodes]", rel());
+  m.def("column_slice_fill", &column_slice_fill, "local column ids of U[:, after_nodes]", rel());
   m.def("shard_alloc", &shard_alloc, "peer-mappable feature shard + IPC handle", rel());
   m.def("shard_open", &shard_open, "map a peer's shard", rel());
   m.def("host_register", &host_register, "pin+map a host table, returns the device alias", rel());

@@ -116,6 +116,21 @@ class FeatureStore:
             ev.record(stream)
         return buf[:, :self.feat_dim], ev
 
+    def gather_spmm(self, adjacency, input_nodes: torch.Tensor) -> torch.Tensor:
+        """Fused gather + first-layer SpMM (main.py:129-134 + models.py:18): rows in the LOCAL shard are read by the
+        SpMM straight from the shard through the pointer table; rows held by peers or the host are first staged
+        once each (never per nonzero - a LADIES block re-reads every X row ~100x) and the table is pointed at
+        the staging rows.  ``adjacency`` is a custom_sparse_ops.Adjacency whose columns are ``input_nodes``."""
+        src_dev, _, xrows, _ = self.remap(input_nodes)
+        n0 = input_nodes.numel()
+        stage = torch.empty((n0, self.ld), dtype=torch.float32, device=self.device)
+        self.ext.gather_rows_src(xrows, src_dev, -200 - self.rank, self.feat_dim, stage)       # GNN_SRC_NOT(rank)
+        staged = stage.data_ptr() + torch.arange(n0, device=self.device, dtype=torch.int64) * (self.ld * 4)
+        table = torch.where(src_dev == self.rank, xrows, staged)
+        out = adjacency.gather_matmul(table, self.feat_dim)
+        stage.record_stream(torch.cuda.current_stream())
+        return out
+
     def gather_from_reference_tuple(self, masks_on_devices, mask_on_cpu, idx_on_devices, idx_on_cpu, num_input_nodes):
         """Same gather driven by the reference sampler's own outputs (sampler.py:160 tuple), for main.py drop-in use:
         the masks / slot lists are folded into a pointer table on the host, then one gather kernel runs."""

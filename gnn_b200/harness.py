@@ -162,3 +162,95 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
             "allreduce_bytes_per_step": int(comm_bytes), "parameters": int(nparams), "final_loss": round(last, 4),
             "note": "gather (next minibatch prefetched on a side stream) + GraphSAGE fwd + BCE loss + bwd + clip + NCCL "
                     "allreduce(sum) + Adam on pre-sampled minibatches (host LADIES sampling and adjacency upload excluded)"}
+
+
+def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log, pool_num=4):
+    """Training with the sampler IN the loop (BASELINE's second minibatches/s number): ``pool_num`` sampler threads
+    (reference main.py:77 uses a ThreadPoolExecutor of --pool_num=4 per GPU) run the device LADIES sampler
+    (gnn_b200/gpu_sampler.py: numpy draw on the host, array passes on the GPU) and the feature gather on their own
+    CUDA streams, a bounded queue feeds the training stream."""
+    import collections
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    import torch.distributed as dist
+    from . import gpu_sampler, graphgen
+    torch.manual_seed(1234)
+    model = SageNet(shape.feat_dim, nhid, orders, shape.num_classes, cso.spmm).to(device)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=0.01)
+    labels_all = graphgen.labels(shape, seed=3)
+    dg = gpu_sampler.DeviceGraph(g.indptr, g.indices, device)
+    tls = threading.local()
+    main_stream = torch.cuda.current_stream(device)
+    steps = max(4, min(args.steps, 24))
+    total = steps + 4
+    rng = np.random.Generator(np.random.PCG64(77 + rank))
+    chunk = (g.train_nodes.size + world - 1) // world
+    own = g.train_nodes[rank * chunk: min((rank + 1) * chunk, g.train_nodes.size)]
+    batches = [own[rng.permutation(own.size)[:batch]] for _ in range(total)]
+
+    def job(i):
+        torch.cuda.set_device(device)
+        if not hasattr(tls, "stream"):
+            tls.stream = torch.cuda.Stream(device=device)
+            tls.scratch = dg.scratch()
+        with torch.cuda.stream(tls.stream):
+            mb = gpu_sampler.ladies_sample_device(5000 + 1000 * rank + i, batches[i], [samp] * 5, dg, orders,
+                                                  create_coo_tensor=cso.create_coo_tensor, scratch=tls.scratch)
+            nodes = torch.from_numpy(mb.input_nodes).to(device)
+            x0 = store.gather(nodes)
+            sn = [torch.from_numpy(np.ascontiguousarray(s_, dtype=np.int64)).to(device) for s_ in mb.sampled_nodes]
+            y = F.one_hot(torch.from_numpy(labels_all[mb.batch_nodes]), shape.num_classes).float().to(device)
+        tls.stream.synchronize()
+        gpu_sampler.record_stream(mb, main_stream)
+        for t in [x0, y] + sn:
+            t.record_stream(main_stream)
+        return mb, x0, sn, y
+
+    model.train()
+    pool = ThreadPoolExecutor(max_workers=pool_num)
+    pending = collections.deque()
+    nxt = 0
+    depth = 2 * pool_num
+
+    def refill():
+        nonlocal nxt
+        while len(pending) < depth and nxt < total:
+            pending.append(pool.submit(job, nxt))
+            nxt += 1
+
+    def step():
+        refill()
+        mb, x0, sn, y = pending.popleft().result()
+        refill()
+        opt.zero_grad(set_to_none=False)
+        out = model(x0, mb.adjs, sn)
+        loss = bce_loss(out, y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 5)
+        exchange_gradients(params, world)
+        opt.step()
+        return loss
+
+    for _ in range(4):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = step()
+    last = float(loss.item())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    pool.shutdown(wait=True)
+    if world > 1:
+        t = torch.tensor([wall], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    return {"minibatches_per_s": round(world * steps / wall, 2), "unit": "minibatches/s", "steps": steps,
+            "ms_per_step_wall": round(wall / steps * 1e3, 3), "sampler_threads": pool_num, "final_loss": round(last, 4),
+            "note": "live LADIES sampling: numpy draw on the host + device array passes (bit-identical sampled sets), "
+                    "gather in the sampler threads, then the same training step; wall clock incl. sampling"}

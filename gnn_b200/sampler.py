@@ -2,10 +2,10 @@
 
 This mirrors reference sampler.py:90-160 (``ladies_sampler``).  The sampling
 itself (sampler.py:113-131) is host numpy in the reference and stays host numpy
-here - it is the *input generator* of the hot path, and it draws from numpy's
-legacy global ``RandomState`` with the same calls in the same order
-(``np.random.seed`` + ``np.random.choice(p=..., replace=False)``) so sampled
-node sets are bit-identical to the reference by construction.  What is
+here - it is the *input generator* of the hot path, and it draws from a numpy
+legacy ``RandomState`` seeded and called exactly like the reference's global
+functions (``np.random.seed`` + ``np.random.choice(p=..., replace=False)``), so
+sampled node sets are bit-identical to the reference by construction.  What is
 restated differently is the data handling around it:
 
 * row slice ``lap_matrix[previous_nodes, :]`` (sampler.py:113) and column slice
@@ -96,7 +96,9 @@ def ladies_sample(seed: int, batch_nodes, samp_num_list: Sequence[int], num_node
                   indptr: np.ndarray, indices: np.ndarray, orders: Sequence[int],
                   skewed_sampling_nodes=None, scale_factor: float = 1.0) -> Minibatch:
     """Host part of reference ``ladies_sampler`` (sampler.py:90-147), returning host arrays."""
-    np.random.seed(seed)                                   # sampler.py:96
+    # a private legacy RandomState seeded like np.random.seed(seed) (sampler.py:96): the same MT19937 stream and
+    # the same choice() algorithm as the global functions the reference calls, but safe under sampler threads
+    rs = np.random.RandomState(seed)
     previous_nodes = np.asarray(batch_nodes)
     batch = previous_nodes
     orders1 = list(orders)[::-1]
@@ -115,7 +117,7 @@ def ladies_sample(seed: int, batch_nodes, samp_num_list: Sequence[int], num_node
             pi[sel] = pi[sel] * scale_factor
         p = pi / np.sum(pi)                                                        # :124
         s_num = np.min([np.sum(p > 0), samp_num_list[d]])                          # :126
-        after_nodes = np.random.choice(num_nodes, s_num, p=p, replace=False)       # :128
+        after_nodes = rs.choice(num_nodes, s_num, p=p, replace=False)              # :128
         after_nodes = np.unique(np.concatenate((after_nodes, previous_nodes)))     # :131
         rowptr, local_cols = column_slice(u_cols, lens, after_nodes, num_nodes)    # :133
         normfact = 1 / np.clip(s_num * p[after_nodes], 1e-10, 1).astype(np.float32)  # :137

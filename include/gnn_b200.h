@@ -170,6 +170,9 @@ int gnn_gather_rows_f32(const float *const *xrows, int64_t n0, int64_t F,
  * GNN_SRC_DEVICES = every row held by some GPU), so transfers from different sources can be put on
  * different streams.  Host rows are PCIe-bound and use a deliberately small grid. */
 #define GNN_SRC_DEVICES (-100)
+/* GNN_SRC_NOT(i): every valid row NOT held by source i (e.g. everything that is not in the local shard);
+ * the macro is its own inverse: GNN_SRC_NOT(GNN_SRC_NOT(i)) == i. */
+#define GNN_SRC_NOT(i) (-200 - (i))
 int gnn_gather_rows_src_f32(const float *const *xrows, const int32_t *src_dev, int32_t only_src,
                             int64_t n0, int64_t F, float *out, int64_t ld_out, gnn_stream_t stream);
 
@@ -179,6 +182,34 @@ int gnn_gather_rows_src_f32(const float *const *xrows, const int32_t *src_dev, i
  * ------------------------------------------------------------------------- */
 int gnn_index_rows_f32(const float *X, int64_t ldx, const int64_t *idx, int64_t n, int64_t F,
                        float *out, int64_t ld_out, gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * LADIES layer construction on the device - the array work of the sampler.
+ * The weighted draw without replacement stays numpy on the host (np.random.choice on the exact same
+ * probabilities), so sampled node sets remain bit-identical to the reference; these entry points replace
+ * the scipy/numpy array passes around it.  The graph structure (indptr int64 [N+1], indices int32 [nnz])
+ * is resident on the device.
+ *
+ * gnn_row_slice_count  : U = lap_matrix[nodes, :]  (sampler.py:113-114): out_fullrowptr[M+1] = row pointer of
+ *                        the selected rows (exclusive scan of their full-graph degrees); scratch_lens int32 [M].
+ * gnn_row_slice_fill   : column ids of every selected row into out_cols[fullrowptr[M]]; when col_counts != NULL
+ *                        also col_counts[c] += 1 per entry = sp.linalg.norm(U, ord=0, axis=0) (sampler.py:117);
+ *                        col_counts must be zero on entry.
+ * gnn_lookup_set       : lookup[after_nodes[j]] = j (set != 0) or -1 (set == 0) for j < K; lookup is int32 [N],
+ *                        -1 everywhere between uses.
+ * gnn_column_slice_count / _fill : adj = U[:, after_nodes] (sampler.py:133-136): per-row kept counts and their
+ *                        exclusive scan (out_rowptr[M+1]), then the kept entries renumbered to positions inside
+ *                        after_nodes, ascending within a row, as int16 (reference hand-off) or int32.
+ * ------------------------------------------------------------------------- */
+int gnn_row_slice_count(const int64_t *indptr, const int64_t *nodes, int64_t M, int32_t *scratch_lens,
+                        int32_t *out_fullrowptr, gnn_stream_t stream);
+int gnn_row_slice_fill(const int64_t *indptr, const int32_t *indices, const int64_t *nodes, int64_t M,
+                       const int32_t *fullrowptr, int32_t *out_cols, int32_t *col_counts, gnn_stream_t stream);
+int gnn_lookup_set(int32_t *lookup, const int64_t *after_nodes, int64_t K, int set, gnn_stream_t stream);
+int gnn_column_slice_count(const int32_t *ucols, const int32_t *fullrowptr, int64_t M, const int32_t *lookup,
+                           int32_t *scratch_counts, int32_t *out_rowptr, gnn_stream_t stream);
+int gnn_column_slice_fill(const int32_t *ucols, const int32_t *fullrowptr, int64_t M, const int32_t *lookup,
+                          const int32_t *rowptr, void *out_colidx, int colidx_bytes, gnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Feature-shard memory that peers can map (one process per GPU).

@@ -163,3 +163,30 @@ def test_feature_store_prefetch_matches_gather(cso):
     ref = store.gather_from_reference_tuple(masks, ~masks[0], [idx[nodes.cpu().numpy()[masks[0]]]], nodes.cpu().numpy()[~masks[0]], 200)
     assert torch.equal(ref, out)
     store.close()
+
+
+def test_feature_store_fused_gather_spmm(cso):
+    """Hybrid fused gather+SpMM: local rows read in place, remote (other shard / host) rows staged once."""
+    from gnn_b200 import gather, graphgen, placement, sampler
+    shape = graphgen.SHAPES["small"]
+    g = graphgen.generate(shape, seed=0)
+    feats = graphgen.features(shape, seed=1)
+    world = 3
+    pl = placement.create_placement(g.to_scipy(np.float64), g.train_nodes, int(0.1 * shape.num_nodes), list(range(world)), 3, alpha=0.0)
+    for rank in (0, 2):
+        store = gather.FeatureStore(torch.from_numpy(feats), pl.gpu_buffer_group, pl.device_id_of_nodes_group[rank],
+                                    pl.idx_of_nodes_on_device_group[rank], list(range(world)), rank, torch.device("cuda", 0))
+        mbx = sampler.ladies_sample(77 + rank, g.train_nodes[:128], [1024] * 3, shape.num_nodes, g.indptr, g.indices, [1, 1, 1])
+        layer = mbx.layers[0]
+        a = cso.create_coo_tensor(*_upload(layer))
+        nodes = torch.from_numpy(mbx.input_nodes).cuda()
+        y = store.gather_spmm(cso.adjacency_of(a), nodes)
+        x = store.gather(nodes)
+        assert np.array_equal(x.cpu().numpy(), feats[mbx.input_nodes])
+        assert torch.equal(y, cso.adjacency_of(a).matmul(x)), "fused and staged paths must agree bit for bit"
+        _, _, vals = oracle.build_adj(layer.fullrowptr, layer.rowptr, layer.colidx, layer.normfact, layer.nrows)
+        yref = oracle.spmm_f64acc(layer.rowptr, layer.colidx32, vals, layer.nrows, feats[mbx.input_nodes])
+        assert oracle.rel_err(y.cpu().numpy(), yref)[0] <= TOL
+        src = store.remap(nodes)[0].cpu().numpy()
+        assert (src == rank).any() and (src != rank).any()
+        store.close()
