@@ -43,9 +43,10 @@ def algorithmic_bytes(nnz, M, K, D):
     return 8 * nnz + 4 * (M + 1) + 4 * K * D + 4 * M * D
 
 
-def layer_widths(feat_dim, nlayers):
-    """GraphSAGE aggregates before the linear: nfeat, then 2*nhid (reference models.py:18-19,34-36)."""
-    return [feat_dim] + [2 * NHID] * (nlayers - 1)
+def layer_widths(feat_dim, nlayers, gcn=False):
+    """SpMM operand widths. GraphSAGE aggregates before the linear and concatenates: nfeat, then 2*nhid
+    (reference models.py:18-19,34-36); GCN: nfeat, then nhid (models.py:60-61,73-76)."""
+    return [feat_dim] + [(NHID if gcn else 2 * NHID)] * (nlayers - 1)
 
 
 def build_workload(args, rank, world, log):
@@ -240,7 +241,7 @@ def main():
     if world > 1 and rank == 0:
         barrier()
     nl = len(mbs[0].layers)
-    widths = layer_widths(shape.feat_dim, nl)
+    widths = layer_widths(shape.feat_dim, nl, gcn=shape.self_loops)
 
     # ---- device-resident operands per minibatch
     gen = torch.Generator(device=device)
@@ -381,7 +382,9 @@ def main():
         e2e = run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
 
     # ---- training minibatches/s (full step incl. NCCL allreduce), secondary metric of BASELINE.json
-    if not args.no_train:
+    if not args.no_train and shape.self_loops:
+        train = {"skipped": "the training harness restates the GraphSAGE model only; GCN shapes report the SpMM path"}
+    elif not args.no_train:
         from gnn_b200 import harness
         train = harness.bench_train(args, cso, store, shape, g, mbs, ORDERS, NHID, device, rank, world, log)
         try:
@@ -405,7 +408,8 @@ def main():
             "metric": "LADIES-layer SpMM HBM GB/s (fwd+bwd)", "value": round(value, 2), "unit": "GB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms_max / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{shape.name}-shaped GraphSAGE LADIES samp_num {samp} batch {batch} (BASELINE configs[1])",
+            "config": {"workload": f"{shape.name}-shaped {'GCN' if shape.self_loops else 'GraphSAGE'} LADIES samp_num {samp} batch {batch}"
+                                   + (" (BASELINE configs[1])" if shape.name == "reddit" else ""),
                        "graph": {"nodes": g.num_nodes, "directed_nnz": g.nnz, "feat_dim": shape.feat_dim, "alpha": shape.alpha,
                                  "max_degree": int(g.degrees().max())},
                        "blocks": block_stats(mbs[0], widths), "minibatches_rotated": len(mbs),
@@ -457,51 +461,61 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
     import torch
     import torch.distributed as dist
     nl = len(widths)
-    host_mbs = []
-    for mb in mbs:
-        arrs = []
-        for layer in mb.layers:
-            arrs.append(tuple(torch.from_numpy(a).pin_memory() for a in (layer.fullrowptr, layer.rowptr, layer.colidx, layer.normfact)))
-        host_mbs.append((arrs, torch.from_numpy(mb.input_nodes).pin_memory()))
+    from gnn_b200 import pipeline
+    host_mbs = [pipeline.PinnedMinibatch(mb) for mb in mbs]
     gen = torch.Generator(device=device)
     gen.manual_seed(11 + rank)
     acts = [[torch.randn(mb.layers[li].ncols, widths[li], device=device, generator=gen).requires_grad_(True) for li in range(1, nl)]
             for mb in mbs]
-
+    # the reference uploads CSR pieces and builds adjacencies in sampler threads (sampler.py:135-139); same shape here:
+    # one worker thread + side stream prepares minibatch i+1 (H2D, create_coo_tensor, remap, gather) while i computes
+    pre = pipeline.DevicePrefetcher(store, cso.create_coo_tensor, device, depth=2)
     src_counts = []
 
-    def step(i):
-        mb = mbs[i % len(mbs)]
-        arrs, inp = host_mbs[i % len(mbs)]
-        adjs = []
-        for layer, (frp, rp, ci, nf) in zip(mb.layers, arrs):
-            adjs.append(cso.create_coo_tensor(frp.to(device, non_blocking=True), rp.to(device, non_blocking=True),
-                                              ci.to(device, non_blocking=True), nf.to(device, non_blocking=True),
-                                              layer.nrows, layer.ncols))
-        nodes = inp.to(device, non_blocking=True)
-        src_dev, slot, xrows, counts = store.remap(nodes)
-        x0 = store.ext.gather_rows(xrows, store.feat_dim, store.ld)
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    losses = []
+
+    def step(i, prev_ready):
+        """Launch minibatch i, then read the loss of minibatch i-1 (one D2H read per step, one step late, so the
+        GPU is never idle while the host launches the next step)."""
+        adjs, x0, counts = pre.get()
         loss = cso.spmm(adjs[0], x0).sum()
         for li in range(1, nl):
             h = acts[i % len(mbs)][li - 1]
             h.grad = None
             loss = loss + cso.spmm(adjs[li], h).sum()
         loss.backward()
-        return float(loss.item()), counts
+        if prev_ready is not None:
+            prev_ready.synchronize()
+            losses.append(float(loss_host[0]))
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record()
+        return ready, counts
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
+    nwarm = max(args.warmup, 3)
+    for i in range(nwarm + args.steps):
+        pre.submit(host_mbs[i % len(mbs)])
+    ready = None
+    for i in range(nwarm):
+        ready, _ = step(i, ready)
+    ready.synchronize()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    ready = None
     t0 = time.perf_counter()
     for s in range(args.steps):
-        _, counts = step(s)
+        ready, counts = step(nwarm + s, ready)
         src_counts.append(counts)
+    ready.synchronize()                       # the last step's loss is read inside the timed region too
+    losses.append(float(loss_host[0]))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     dt = time.perf_counter() - t0
+    pre.close()
+    assert len(losses) >= args.steps and all(np.isfinite(losses)), "every step's loss must have been read on the host"
     counts = torch.stack(src_counts).double().mean(0).cpu().numpy()      # rows per source per step
     bytes_all = float(sum(step_bytes[s % len(mbs)] for s in range(args.steps)))
     if world > 1:
@@ -512,8 +526,7 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
         dist.all_reduce(b, op=dist.ReduceOp.SUM)
         bytes_all = float(b.item())
     F4 = store.ld * 4
-    csr_bytes = float(np.mean([sum(sum(a.numel() * a.element_size() for a in t4) for t4 in arrs) + inp.numel() * 8
-                               for arrs, inp in host_mbs]))
+    csr_bytes = float(np.mean([pm.h2d_bytes() for pm in host_mbs]))
     host_rows = float(counts[world])
     peer_rows = float(sum(counts[i] for i in range(world) if i != rank))
     out = {"value": round(bytes_all / dt / 1e9, 2), "unit": "GB/s", "ms_per_step": round(dt / args.steps * 1e3, 4),
@@ -522,9 +535,11 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
                           "host_feature_bytes_zero_copy": int(host_rows * F4)},
            "gather_rows_per_step": {"local": int(counts[rank]), "peer": int(peer_rows), "host": int(host_rows)},
            "peer_bytes_per_step": int(peer_rows * F4),
-           "api": "custom_sparse_ops.create_coo_tensor + FeatureStore.remap/gather + custom_sparse_ops.spmm (autograd)"}
+           "api": "pipeline.DevicePrefetcher (H2D of pinned sampler arrays + custom_sparse_ops.create_coo_tensor + "
+                  "FeatureStore remap/gather on a worker thread and side stream) + custom_sparse_ops.spmm (autograd) + loss.item()",
+           "pipelining": "inputs of minibatch i+1 are copied/gathered while minibatch i computes and the loss of minibatch i is read (pinned D2H) after i+1 is launched; every copy and read is inside the timed region"}
     # gather alone, for the NVLink / PCIe roofs
-    nodes = host_mbs[0][1].to(device)
+    nodes = host_mbs[0].input_nodes.to(device)
     src_dev, slot, xrows, c = store.remap(nodes)
     outbuf = torch.empty((nodes.numel(), store.ld), device=device)
     c = c.cpu().numpy()
@@ -609,7 +624,7 @@ def run_reference(args, log):
     """--impl reference: the reference's CPU path on the host cores (rank 0 only)."""
     from gnn_b200 import graphgen  # noqa: F401
     shape, g, mbs, samp, batch = build_workload(args, 0, 1, log)
-    widths = layer_widths(shape.feat_dim, len(mbs[0].layers))
+    widths = layer_widths(shape.feat_dim, len(mbs[0].layers), gcn=shape.self_loops)
     cpu, times = cpu_reference_sample(mbs[0], widths, args.cpu_seconds, log, steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": "LADIES-layer SpMM HBM GB/s (fwd+bwd)", "value": round(cpu["value"], 4), "unit": "GB/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(float(np.mean(times)) * 1e3, 3),

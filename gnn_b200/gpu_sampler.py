@@ -73,9 +73,35 @@ class DeviceGraph:
         return self._default_scratch
 
 
+def legacy_choice_on_support(rs: np.random.RandomState, p_nz: np.ndarray, size: int) -> np.ndarray:
+    """``rs.choice(N, size, p=p, replace=False)`` of numpy's legacy RandomState, evaluated on the SUPPORT of p only.
+
+    ``p_nz`` holds the non-zero probabilities in index order; the result indexes into that support.  It is exactly
+    what ``choice`` would return on the full-length p (mtrand.pyx, replace=False branch): zero entries neither change
+    the running sums of ``np.cumsum`` nor can ``searchsorted(..., side='right')`` land on them, and the same uniform
+    draws are consumed (``random_sample(size - n_uniq)`` per round).  Checked against ``choice`` in the tests."""
+    p = np.array(p_nz, dtype=np.float64, copy=True)
+    found = np.zeros(size, dtype=np.int64)
+    n_uniq = 0
+    while n_uniq < size:
+        x = rs.random_sample(size - n_uniq)
+        if n_uniq > 0:
+            p[found[0:n_uniq]] = 0
+        cdf = np.cumsum(p)
+        cdf /= cdf[-1]
+        new = cdf.searchsorted(x, side="right")
+        _, unique_indices = np.unique(new, return_index=True)
+        unique_indices.sort()
+        new = new.take(unique_indices)
+        found[n_uniq:n_uniq + new.size] = new
+        n_uniq += new.size
+    return found
+
+
 def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], graph: DeviceGraph, orders: Sequence[int],
                          create_coo_tensor=None, int16_ids: bool = True, skewed_sampling_nodes=None,
-                         scale_factor: float = 1.0, scratch: Optional[SamplerScratch] = None) -> DeviceMinibatch:
+                         scale_factor: float = 1.0, scratch: Optional[SamplerScratch] = None,
+                         prebuild_transpose: bool = True) -> DeviceMinibatch:
     ext = _native.extension()
     if create_coo_tensor is None:
         from .custom_sparse_ops import create_coo_tensor
@@ -99,15 +125,21 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
         total = int(fullrowptr[-1].item())
         scratch.counts.zero_()
         ucols = ext.row_slice_fill(graph.indptr, graph.indices, prev_dev, fullrowptr, total, scratch.counts)
-        pi = scratch.counts.cpu().numpy().astype(np.int64)                                    # :117
+        # only the columns that occur at all carry probability: compact them on the device and bring back
+        # (index, count) pairs instead of an N-long array (N = 111 M on the papers100M shape)
+        nz_dev = torch.nonzero(scratch.counts).flatten()
+        nz = nz_dev.cpu().numpy()
+        pi_nz = scratch.counts[nz_dev].cpu().numpy().astype(np.int64)                       # :117 on the support
         if scale_factor > 1:                                                                # :119-121
-            pi = pi.astype(np.float64)
-            sel = skewed_sampling_nodes[len(orders1) - d - 1]
-            pi[sel] = pi[sel] * scale_factor
-        p = pi / np.sum(pi)                                                                 # :124
-        s_num = np.min([np.sum(p > 0), samp_num_list[d]])                                   # :126
-        after_nodes = rs.choice(n, s_num, p=p, replace=False)                               # :128
+            pi_nz = pi_nz.astype(np.float64)
+            sel = np.isin(nz, skewed_sampling_nodes[len(orders1) - d - 1])
+            pi_nz[sel] = pi_nz[sel] * scale_factor
+        p_nz = pi_nz / np.sum(pi_nz)                                                        # :124 (same quotients)
+        s_num = np.min([nz.size, samp_num_list[d]])                                         # :126 (count of p > 0)
+        after_nodes = nz[legacy_choice_on_support(rs, p_nz, int(s_num))]                    # :128
         after_nodes = np.unique(np.concatenate((after_nodes, previous_nodes)))              # :131
+        pos = np.minimum(np.searchsorted(nz, after_nodes), nz.size - 1)
+        p_after = np.where(nz[pos] == after_nodes, p_nz[pos], 0.0)                          # p[after_nodes]
         after_dev = torch.from_numpy(after_nodes.astype(np.int64, copy=False)).to(dev)
         ext.lookup_set(scratch.lookup, after_dev, True)
         rowptr = ext.column_slice_count(ucols, fullrowptr, scratch.lookup)                    # :133,135
@@ -115,7 +147,7 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
         use16 = int16_ids and after_nodes.size <= 32768
         colidx = ext.column_slice_fill(ucols, fullrowptr, scratch.lookup, rowptr, nnz, use16)  # :136
         ext.lookup_set(scratch.lookup, after_dev, False)
-        normfact = 1 / np.clip(s_num * p[after_nodes], 1e-10, 1).astype(np.float32)         # :137
+        normfact = 1 / np.clip(s_num * p_after, 1e-10, 1).astype(np.float32)                # :137
         nf_dev = torch.from_numpy(normfact).to(dev)
         layer = DeviceLayer(fullrowptr, rowptr, colidx, nf_dev, int(previous_nodes.size), int(after_nodes.size))
         layers.append(layer)
@@ -125,6 +157,13 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
     layers.reverse()
     adjs.reverse()
     sampled.reverse()
+    if prebuild_transpose:
+        # every layer but the deepest gets a backward: build its A^T index here, on the sampler's
+        # stream, so the training stream never pays for it
+        from .custom_sparse_ops import adjacency_of
+        for adj in adjs[1:]:
+            if adj is not None:
+                adjacency_of(adj).transpose()
     return DeviceMinibatch(layers, adjs, sampled, np.asarray(previous_nodes, dtype=np.int64), np.asarray(batch))
 
 
@@ -134,6 +173,9 @@ def record_stream(mb: DeviceMinibatch, stream) -> None:
     for layer, adj in zip(mb.layers, mb.adjs):
         if layer is None:
             continue
-        for t in (layer.fullrowptr, layer.rowptr, layer.colidx, layer.normfact, adj._indices(), adj._values(),
-                  adjacency_of(adj).colidx):
+        a = adjacency_of(adj)
+        ts = [layer.fullrowptr, layer.rowptr, layer.colidx, layer.normfact, adj._indices(), adj._values(), a.colidx]
+        if a._t is not None:
+            ts += [a._t.rowptr, a._t.colidx, a._t.vals]
+        for t in ts:
             t.record_stream(stream)

@@ -1,0 +1,116 @@
+"""Host -> device minibatch pipeline (the reference's sampler threads, reference sampler.py:135-139 + main.py:118-134).
+
+In the reference every sampler job uploads its CSR pieces (``torch.from_numpy(...).to(device)``) and calls
+``create_coo_tensor`` inside a pool thread, so uploads and adjacency construction overlap with training; only the
+feature gather is synchronous in the training loop.  ``DevicePrefetcher`` keeps that shape with one worker thread and
+one side stream per instance: for each host minibatch it copies the pinned CSR arrays, builds the adjacencies, runs
+the placement remap + feature gather, and hands the training stream an event to wait on.  PCIe traffic of minibatch
+i+1 (CSR arrays and zero-copy host feature rows) therefore overlaps with the SpMMs of minibatch i.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from typing import Iterable, Optional
+
+import numpy as np
+import torch
+
+
+class PinnedMinibatch:
+    """A sampler.Minibatch with its hand-off arrays in pinned host memory (what a sampler thread would own)."""
+    def __init__(self, mb):
+        self.mb = mb
+        self.layers = []
+        for layer in mb.layers:
+            if layer is None:
+                self.layers.append(None)
+                continue
+            self.layers.append(tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+                                     for a in (layer.fullrowptr, layer.rowptr, layer.colidx, layer.normfact)))
+        self.input_nodes = torch.from_numpy(np.ascontiguousarray(mb.input_nodes, dtype=np.int64)).pin_memory()
+
+    def h2d_bytes(self) -> int:
+        n = self.input_nodes.numel() * 8
+        for t4 in self.layers:
+            if t4 is not None:
+                n += sum(t.numel() * t.element_size() for t in t4)
+        return n
+
+
+class DevicePrefetcher:
+    def __init__(self, store, create_coo_tensor, device, depth: int = 2, prebuild_transpose: bool = False):
+        self.store, self.create = store, create_coo_tensor
+        self.device = torch.device(device)
+        self.depth = depth
+        self.prebuild_transpose = prebuild_transpose
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._in: "queue.Queue" = queue.Queue()
+        self._out: "queue.Queue" = queue.Queue(maxsize=depth)
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def submit(self, pinned: Optional[PinnedMinibatch]):
+        self._in.put(pinned)
+
+    def _run(self):
+        torch.cuda.set_device(self.device)
+        while True:
+            item = self._in.get()
+            if item is None:
+                self._out.put(None)
+                return
+            try:
+                self._out.put(self._build(item))
+            except Exception as exc:  # noqa: BLE001  surfaced in get()
+                self._out.put(exc)
+
+    def _build(self, pm: PinnedMinibatch):
+        dev = self.device
+        with torch.cuda.stream(self.stream):
+            adjs = []
+            for layer, t4 in zip(pm.mb.layers, pm.layers):
+                if t4 is None:
+                    adjs.append(None)
+                    continue
+                frp, rp, ci, nf = (t.to(dev, non_blocking=True) for t in t4)
+                adjs.append(self.create(frp, rp, ci, nf, layer.nrows, layer.ncols))
+            nodes = pm.input_nodes.to(dev, non_blocking=True)
+            src_dev, _, xrows, counts = self.store.remap(nodes)
+            buf = torch.empty((nodes.numel(), self.store.ld), dtype=torch.float32, device=dev)
+            self.store.ext.gather_rows_src(xrows, src_dev, -100, self.store.feat_dim, buf)   # HBM / NVLink rows
+            self.store.ext.gather_rows_src(xrows, src_dev, -1, self.store.feat_dim, buf)     # host rows (PCIe)
+            if self.prebuild_transpose:
+                from .custom_sparse_ops import adjacency_of
+                for a in adjs[1:]:
+                    if a is not None:
+                        adjacency_of(a).transpose()
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return adjs, buf[:, :self.store.feat_dim], counts, ev
+
+    def get(self):
+        """Next device-ready minibatch; makes the CURRENT stream wait for its uploads/gather."""
+        item = self._out.get()
+        if isinstance(item, Exception):
+            raise item
+        if item is None:
+            return None
+        adjs, x0, counts, ev = item
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        from .custom_sparse_ops import adjacency_of
+        tensors = [x0, counts]
+        for a in adjs:
+            if a is not None:
+                adj = adjacency_of(a)
+                tensors += [a._indices(), a._values(), adj.rowptr, adj.colidx]
+                if adj._t is not None:
+                    tensors += [adj._t.rowptr, adj._t.colidx, adj._t.vals]
+        for t in tensors:
+            t.record_stream(cur)
+        return adjs, x0, counts
+
+    def close(self):
+        self._in.put(None)
+        self._thread.join(timeout=10)

@@ -190,3 +190,39 @@ def test_feature_store_fused_gather_spmm(cso):
         src = store.remap(nodes)[0].cpu().numpy()
         assert (src == rank).any() and (src != rank).any()
         store.close()
+
+
+def test_device_prefetcher_matches_direct_path(cso):
+    """pipeline.DevicePrefetcher (worker thread + side stream) hands over the same adjacencies and gathered rows as
+    the direct calls, for several minibatches in flight."""
+    from gnn_b200 import gather, graphgen, pipeline, sampler
+    shape = graphgen.SHAPES["small"]
+    g = graphgen.generate(shape, seed=0)
+    feats = graphgen.features(shape, seed=1)
+    n = shape.num_nodes
+    top = np.arange(0, n, 4)
+    did = np.full(n, -1, dtype=np.int64)
+    did[top] = 0
+    idx = np.arange(n, dtype=np.int64)
+    idx[top] = np.arange(top.size)
+    store = gather.FeatureStore(torch.from_numpy(feats), [top], did, idx, [0], 0, torch.device("cuda", 0))
+    mbs = [sampler.ladies_sample(900 + i, g.train_nodes[i * 64:(i + 1) * 64], [512] * 3, n, g.indptr, g.indices, [1, 1, 1]) for i in range(5)]
+    pre = pipeline.DevicePrefetcher(store, cso.create_coo_tensor, torch.device("cuda", 0), depth=2, prebuild_transpose=True)
+    for mbx in mbs:
+        pre.submit(pipeline.PinnedMinibatch(mbx))
+    for mbx in mbs:
+        adjs, x0, counts = pre.get()
+        assert np.array_equal(x0.cpu().numpy(), feats[mbx.input_nodes])
+        assert int(counts.sum().item()) == mbx.input_nodes.size
+        for a, layer in zip(adjs, mbx.layers):
+            rows, cols, vals = oracle.build_adj(layer.fullrowptr, layer.rowptr, layer.colidx, layer.normfact, layer.nrows)
+            assert np.array_equal(a._indices().cpu().numpy(), np.stack([rows, cols]))
+            assert np.array_equal(a._values().cpu().numpy().view(np.uint32), vals.view(np.uint32))
+        y = cso.spmm(adjs[0], x0)
+        yref = oracle.spmm_f64acc(mbx.layers[0].rowptr, mbx.layers[0].colidx32, oracle.build_adj(
+            mbx.layers[0].fullrowptr, mbx.layers[0].rowptr, mbx.layers[0].colidx, mbx.layers[0].normfact, mbx.layers[0].nrows)[2],
+            mbx.layers[0].nrows, feats[mbx.input_nodes])
+        assert oracle.rel_err(y.cpu().numpy(), yref)[0] <= TOL
+        assert cso.adjacency_of(adjs[1])._t is not None and cso.adjacency_of(adjs[0])._t is None
+    pre.close()
+    store.close()

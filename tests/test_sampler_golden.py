@@ -92,3 +92,26 @@ def test_oracle_sampled_nodes_direct():
         after = np.unique(np.concatenate([extra, prev]))
         assert np.array_equal(oracle.sampled_nodes(after, prev), np.where(np.isin(after, prev))[0])
         assert np.array_equal(sampler.sampled_nodes_remap(after, prev), np.where(np.isin(after, prev))[0])
+
+
+def test_legacy_choice_on_support_equals_numpy_choice():
+    """The device sampler evaluates numpy's legacy weighted draw on the support of p only; it must return exactly what
+    RandomState.choice(N, size, p=p, replace=False) returns on the full-length p (reference sampler.py:128)."""
+    from gnn_b200.gpu_sampler import legacy_choice_on_support
+    rng = np.random.Generator(np.random.PCG64(0))
+    for trial in range(40):
+        n = int(rng.integers(50, 20000))
+        counts = rng.integers(0, 9, n) * (rng.random(n) < rng.uniform(0.05, 0.9))
+        nz = np.flatnonzero(counts)
+        if nz.size == 0:
+            continue
+        size = int(min(nz.size, rng.integers(1, n)))
+        p = counts / counts.sum()
+        a = np.random.RandomState(trial).choice(n, size, p=p, replace=False)
+        rs = np.random.RandomState(trial)
+        b = nz[legacy_choice_on_support(rs, p[nz], size)]
+        assert np.array_equal(a, b), trial
+        # and the generator state afterwards is the same (the next layer's draw continues the stream)
+        rs2 = np.random.RandomState(trial)
+        rs2.choice(n, size, p=p, replace=False)
+        assert rs.random_sample() == rs2.random_sample()
