@@ -474,6 +474,9 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
 
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
     losses = []
+    defer = os.environ.get("BENCH_E2E_DEFER", "1") == "1"
+    if os.environ.get("BENCH_SWITCH"):
+        sys.setswitchinterval(float(os.environ["BENCH_SWITCH"]))
 
     def step(i, prev_ready):
         """Launch minibatch i, then read the loss of minibatch i-1 (one D2H read per step, one step late, so the
@@ -485,6 +488,9 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
             h.grad = None
             loss = loss + cso.spmm(adjs[li], h).sum()
         loss.backward()
+        if not defer:
+            losses.append(float(loss.item()))
+            return None, counts
         if prev_ready is not None:
             prev_ready.synchronize()
             losses.append(float(loss_host[0]))
@@ -499,8 +505,10 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
     ready = None
     for i in range(nwarm):
         ready, _ = step(i, ready)
-    ready.synchronize()
+    if ready is not None:
+        ready.synchronize()
     torch.cuda.synchronize()
+    losses.clear()
     if world > 1:
         dist.barrier()
     ready = None
@@ -508,8 +516,9 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
     for s in range(args.steps):
         ready, counts = step(nwarm + s, ready)
         src_counts.append(counts)
-    ready.synchronize()                       # the last step's loss is read inside the timed region too
-    losses.append(float(loss_host[0]))
+    if ready is not None:
+        ready.synchronize()                   # the last step's loss is read inside the timed region too
+        losses.append(float(loss_host[0]))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
