@@ -386,12 +386,19 @@ def main():
         train = {"skipped": "the training harness restates the GraphSAGE model only; GCN shapes report the SpMM path"}
     elif not args.no_train:
         from gnn_b200 import harness
+        # reference-shaped model first (the reference's own models.py would run exactly these torch ops), then the
+        # same model with the fused ELU+row-norm epilogue of gnn_b200/models.py
         train = harness.bench_train(args, cso, store, shape, g, mbs, ORDERS, NHID, device, rank, world, log)
-        try:
-            train["live_sampler"] = harness.bench_train_live(args, cso, store, shape, g, ORDERS, NHID, samp, batch, device, rank,
-                                                             world, log)
-        except Exception as exc:                       # the secondary number must not take the headline down
-            train["live_sampler"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        for key, fn, kw in [("fused_epilogue_model", harness.bench_train, dict(fused=True)),
+                            ("live_sampler", harness.bench_train_live, dict(fused=False)),
+                            ("live_sampler_fused_epilogue", harness.bench_train_live, dict(fused=True))]:
+            try:
+                if fn is harness.bench_train:
+                    train[key] = fn(args, cso, store, shape, g, mbs, ORDERS, NHID, device, rank, world, log, **kw)
+                else:
+                    train[key] = fn(args, cso, store, shape, g, ORDERS, NHID, samp, batch, device, rank, world, log, **kw)
+            except Exception as exc:                   # secondary numbers must not take the headline down
+                train[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if store is not None:
         store.close()
 

@@ -732,6 +732,159 @@ column_slice_kernel(const int *__restrict__ ucols, const int *__restrict__ fullr
 }
 
 // ---------------------------------------------------------------------------
+// Fused layer epilogue: y = rownorm(elu(x)) * scale + offset of reference
+// models.py:21-25 / :61-64  (out = F.elu(feat); mean, var(unbiased=False)+1e-9; (out-mean)*scale*rsqrt(var)+offset).
+// One warp per row; the row stays in registers between the ELU, the two reductions and the affine output.
+// ---------------------------------------------------------------------------
+constexpr int kEpiMaxPerLane = 64;   // columns per lane kept in registers => C <= 2048
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+  return v;
+}
+
+template <int PER>   // PER = ceil(C / 32) rounded up to a multiple of 4
+__global__ void __launch_bounds__(256)
+elu_rownorm_fwd_kernel(const float *__restrict__ x, int64_t ldx, int M, int C, const float *__restrict__ scale,
+                       const float *__restrict__ offset, float *__restrict__ y, int64_t ldy, float *__restrict__ mean_out,
+                       float *__restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
+    const float *xr = x + (int64_t)r * ldx;
+    float o[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int c = j * 32 + lane;
+      float v = 0.f;
+      if (c < C) {
+        v = xr[c];
+        v = v > 0.f ? v : expf(v) - 1.f;
+        s += v;
+      }
+      o[j] = v;
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int c = j * 32 + lane;
+      if (c < C) { const float d = o[j] - mean; q += d * d; }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-9f);
+    float *yr = y + (int64_t)r * ldy;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int c = j * 32 + lane;
+      if (c < C) yr[c] = (o[j] - mean) * __ldg(scale + c) * rstd + __ldg(offset + c);
+    }
+    if (lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
+  }
+}
+
+// dx for every row; per-CTA partial column sums of dscale / doffset (reduced in fixed order by the second kernel)
+template <int PER>
+__global__ void __launch_bounds__(256)
+elu_rownorm_bwd_kernel(const float *__restrict__ dy, int64_t lddy, const float *__restrict__ x, int64_t ldx, int M, int C,
+                       const float *__restrict__ scale, const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
+                       float *__restrict__ dx, int64_t lddx, float *__restrict__ part_scale, float *__restrict__ part_offset) {
+  extern __shared__ float sm[];                     // [2][wpb][C] partial sums of this CTA's warps
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  float ds[PER], db[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) { ds[j] = 0.f; db[j] = 0.f; }
+  for (int r = blockIdx.x * wpb + warp; r < M; r += gridDim.x * wpb) {
+    const float *xr = x + (int64_t)r * ldx;
+    const float *gr = dy + (int64_t)r * lddy;
+    const float mean = __ldg(mean_in + r), rstd = __ldg(rstd_in + r);
+    float xh[PER], g[PER], ep[PER];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int c = j * 32 + lane;
+      xh[j] = 0.f; g[j] = 0.f; ep[j] = 0.f;
+      if (c < C) {
+        const float v = xr[c];
+        const float e = v > 0.f ? v : expf(v) - 1.f;
+        ep[j] = v > 0.f ? 1.f : e + 1.f;            // d elu / dx
+        xh[j] = (e - mean) * rstd;
+        const float gy = gr[c];
+        ds[j] += gy * xh[j];
+        db[j] += gy;
+        g[j] = gy * __ldg(scale + c);               // d loss / d xhat
+        s1 += g[j];
+        s2 += g[j] * xh[j];
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+    float *dr = dx + (int64_t)r * lddx;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int c = j * 32 + lane;
+      if (c < C) dr[c] = rstd * (g[j] - s1 - xh[j] * s2) * ep[j];
+    }
+  }
+  // CTA-level reduction of the column partials in fixed warp order
+  float *ss = sm, *sb = sm + (size_t)wpb * C;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int c = j * 32 + lane;
+    if (c < C) { ss[(size_t)warp * C + c] = ds[j]; sb[(size_t)warp * C + c] = db[j]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < wpb; ++w) { a += ss[(size_t)w * C + c]; b += sb[(size_t)w * C + c]; }
+    part_scale[(size_t)blockIdx.x * C + c] = a;
+    part_offset[(size_t)blockIdx.x * C + c] = b;
+  }
+}
+
+__global__ void column_partials_reduce_kernel(const float *__restrict__ part_scale, const float *__restrict__ part_offset,
+                                              int nparts, int C, float *__restrict__ dscale, float *__restrict__ doffset) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int p = 0; p < nparts; ++p) { a += part_scale[(size_t)p * C + c]; b += part_offset[(size_t)p * C + c]; }
+  dscale[c] = a;
+  doffset[c] = b;
+}
+
+constexpr int kEpiCtas = 296;        // 2 per SM: row loop is grid-strided, partial buffers stay small
+
+template <int PER>
+int elu_rownorm_fwd_launch(const float *x, int64_t ldx, int64_t M, int64_t C, const float *scale, const float *offset,
+                                  float *y, int64_t ldy, float *mean, float *rstd, cudaStream_t st) {
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(M, 8), 148 * 8);
+  elu_rownorm_fwd_kernel<PER><<<grid, 256, 0, st>>>(x, ldx, (int)M, (int)C, scale, offset, y, ldy, mean, rstd);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int PER>
+int elu_rownorm_bwd_launch(const float *dy, int64_t lddy, const float *x, int64_t ldx, int64_t M, int64_t C,
+                                  const float *scale, const float *mean, const float *rstd, float *dx, int64_t lddx,
+                                  float *dscale, float *doffset, float *ws, cudaStream_t st) {
+  // warps per CTA limited by the 2 x wpb x C floats of shared memory (<= 96 KB)
+  int wpb = 8;
+  while (wpb > 1 && (size_t)2 * wpb * C * sizeof(float) > 96 * 1024) wpb >>= 1;
+  const size_t smem = (size_t)2 * wpb * C * sizeof(float);
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(M, wpb), kEpiCtas);
+  if (smem > 48 * 1024) GNN_CUDA(cudaFuncSetAttribute(elu_rownorm_bwd_kernel<PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  float *ps = ws, *po = ws + (size_t)kEpiCtas * C;
+  elu_rownorm_bwd_kernel<PER><<<grid, wpb * 32, smem, st>>>(dy, lddy, x, ldx, (int)M, (int)C, scale, mean, rstd, dx, lddx, ps, po);
+  GNN_LAUNCH_CHECK();
+  column_partials_reduce_kernel<<<(unsigned)cdiv(C, 256), 256, 0, st>>>(ps, po, (int)grid, (int)C, dscale, doffset);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // placement remap + gathers
 // ---------------------------------------------------------------------------
 __global__ void placement_remap_kernel(const int64_t *__restrict__ input_nodes, int64_t n0,
@@ -1034,6 +1187,47 @@ int gnn_column_slice_fill(const int32_t *ucols, const int32_t *fullrowptr, int64
                                                                     (int *)out_colidx);
   GNN_LAUNCH_CHECK();
   return 0;
+}
+
+size_t gnn_elu_rownorm_workspace_bytes(int64_t C) { return (size_t)2 * kEpiCtas * (size_t)(C > 0 ? C : 1) * sizeof(float); }
+
+int gnn_elu_rownorm_fwd_f32(const float *x, int64_t ldx, int64_t M, int64_t C, const float *scale, const float *offset,
+                            float *y, int64_t ldy, float *mean, float *rstd, gnn_stream_t stream) {
+  if (M < 0 || C < 0) return GNN_E_BADARG;
+  if (M == 0 || C == 0) return 0;
+  if (C > 32 * kEpiMaxPerLane || M >= (1ll << 31)) return GNN_E_RANGE;
+  if (!x || !scale || !offset || !y || !mean || !rstd || ldx < C || ldy < C) return GNN_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int per = (int)cdiv(C, 32);
+  if (per <= 4) return elu_rownorm_fwd_launch<4>(x, ldx, M, C, scale, offset, y, ldy, mean, rstd, st);
+  if (per <= 8) return elu_rownorm_fwd_launch<8>(x, ldx, M, C, scale, offset, y, ldy, mean, rstd, st);
+  if (per <= 16) return elu_rownorm_fwd_launch<16>(x, ldx, M, C, scale, offset, y, ldy, mean, rstd, st);
+  if (per <= 32) return elu_rownorm_fwd_launch<32>(x, ldx, M, C, scale, offset, y, ldy, mean, rstd, st);
+  return elu_rownorm_fwd_launch<64>(x, ldx, M, C, scale, offset, y, ldy, mean, rstd, st);
+}
+
+int gnn_elu_rownorm_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx, int64_t M, int64_t C,
+                            const float *scale, const float *mean, const float *rstd, float *dx, int64_t lddx,
+                            float *dscale, float *doffset, void *workspace, size_t workspace_bytes, gnn_stream_t stream) {
+  if (M < 0 || C < 0) return GNN_E_BADARG;
+  if (C > 32 * kEpiMaxPerLane || M >= (1ll << 31)) return GNN_E_RANGE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 0) return 0;
+  if (!dscale || !doffset) return GNN_E_BADARG;
+  if (M == 0) {
+    GNN_CUDA(cudaMemsetAsync(dscale, 0, (size_t)C * sizeof(float), st));
+    GNN_CUDA(cudaMemsetAsync(doffset, 0, (size_t)C * sizeof(float), st));
+    return 0;
+  }
+  if (!dy || !x || !scale || !mean || !rstd || !dx || lddy < C || ldx < C || lddx < C) return GNN_E_BADARG;
+  if (!workspace || workspace_bytes < gnn_elu_rownorm_workspace_bytes(C)) return GNN_E_WORKSPACE;
+  float *ws = reinterpret_cast<float *>(workspace);
+  const int per = (int)cdiv(C, 32);
+  if (per <= 4) return elu_rownorm_bwd_launch<4>(dy, lddy, x, ldx, M, C, scale, mean, rstd, dx, lddx, dscale, doffset, ws, st);
+  if (per <= 8) return elu_rownorm_bwd_launch<8>(dy, lddy, x, ldx, M, C, scale, mean, rstd, dx, lddx, dscale, doffset, ws, st);
+  if (per <= 16) return elu_rownorm_bwd_launch<16>(dy, lddy, x, ldx, M, C, scale, mean, rstd, dx, lddx, dscale, doffset, ws, st);
+  if (per <= 32) return elu_rownorm_bwd_launch<32>(dy, lddy, x, ldx, M, C, scale, mean, rstd, dx, lddx, dscale, doffset, ws, st);
+  return elu_rownorm_bwd_launch<64>(dy, lddy, x, ldx, M, C, scale, mean, rstd, dx, lddx, dscale, doffset, ws, st);
 }
 
 int gnn_shard_alloc(size_t bytes, void **dev_ptr, unsigned char ipc_handle[64]) {

@@ -290,6 +290,43 @@ torch::Tensor column_slice_fill(const torch::Tensor &ucols, const torch::Tensor 
   return colidx;
 }
 
+// ---- fused layer epilogue (models.py:21-25 / :61-64) ---------------------------------------
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> elu_rownorm_fwd(const torch::Tensor &x, const torch::Tensor &scale,
+                                                                         const torch::Tensor &offset) {
+  CHECK_CUDA(x); CHECK_DENSE(scale); CHECK_DENSE(offset);
+  TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.scalar_type() == torch::kFloat, "x must be a row-major float32 matrix");
+  TORCH_CHECK(scale.numel() == x.size(1) && offset.numel() == x.size(1), "scale/offset must have one entry per column");
+  c10::cuda::CUDAGuard g(x.device());
+  const int64_t M = x.size(0), C = x.size(1);
+  auto y = torch::empty({M, C}, x.options());
+  auto mean = torch::empty({M}, x.options());
+  auto rstd = torch::empty({M}, x.options());
+  check_rc(gnn_elu_rownorm_fwd_f32(x.data_ptr<float>(), M > 1 ? x.stride(0) : C, M, C, scale.data_ptr<float>(),
+                                   offset.data_ptr<float>(), y.data_ptr<float>(), C, mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                                   cur_stream()),
+           "gnn_elu_rownorm_fwd_f32");
+  return {y, mean, rstd};
+}
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> elu_rownorm_bwd(const torch::Tensor &dy, const torch::Tensor &x,
+                                                                         const torch::Tensor &scale, const torch::Tensor &mean,
+                                                                         const torch::Tensor &rstd) {
+  CHECK_CUDA(dy); CHECK_CUDA(x); CHECK_DENSE(scale); CHECK_DENSE(mean); CHECK_DENSE(rstd);
+  TORCH_CHECK(dy.dim() == 2 && dy.stride(1) == 1 && x.stride(1) == 1 && dy.sizes() == x.sizes(), "dy and x must be row-major and equal-shaped");
+  c10::cuda::CUDAGuard g(x.device());
+  const int64_t M = x.size(0), C = x.size(1);
+  auto dx = torch::empty({M, C}, x.options());
+  auto dscale = torch::empty({C}, x.options());
+  auto doffset = torch::empty({C}, x.options());
+  const size_t wsb = gnn_elu_rownorm_workspace_bytes(C);
+  auto ws = workspace(wsb, x.device());
+  check_rc(gnn_elu_rownorm_bwd_f32(dy.data_ptr<float>(), M > 1 ? dy.stride(0) : C, x.data_ptr<float>(), M > 1 ? x.stride(0) : C, M, C,
+                                   scale.data_ptr<float>(), mean.data_ptr<float>(), rstd.data_ptr<float>(), dx.data_ptr<float>(), C,
+                                   dscale.data_ptr<float>(), doffset.data_ptr<float>(), ws.data_ptr(), wsb, cur_stream()),
+           "gnn_elu_rownorm_bwd_f32");
+  return {dx, dscale, doffset};
+}
+
 // ---- peer-mappable feature shards ---------------------------------------
 std::tuple<torch::Tensor, py::bytes> shard_alloc(int64_t rows, int64_t ld, int64_t device_index) {
   c10::cuda::CUDAGuard g(c10::Device(c10::kCUDA, (c10::DeviceIndex)device_index));
@@ -343,6 +380,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lookup_set", &lookup_set, "lookup[after_nodes[j]] = j or -1", rel());
   m.def("column_slice_count", &column_slice_count, "rowptr of U[:, after_nodes]", rel());
   m.def("column_slice_fill", &column_slice_fill, "local column ids of U[:, after_nodes]", rel());
+  m.def("elu_rownorm_fwd", &elu_rownorm_fwd, "y, mean, rstd = rownorm(elu(x)) * scale + offset", rel());
+  m.def("elu_rownorm_bwd", &elu_rownorm_bwd, "dx, dscale, doffset", rel());
   m.def("shard_alloc", &shard_alloc, "peer-mappable feature shard + IPC handle", rel());
   m.def("shard_open", &shard_open, "map a peer's shard", rel());
   m.def("host_register", &host_register, "pin+map a host table, returns the device alias", rel());

@@ -24,8 +24,9 @@ import torch.nn.functional as F
 
 
 class SageLayer(nn.Module):
-    def __init__(self, n_in, n_out, order, spmm):
+    def __init__(self, n_in, n_out, order, spmm, fused=False):
         super().__init__()
+        self.fused = fused
         self.linearW = nn.Linear(n_in, n_out)
         self.linearB = nn.Linear(n_in, n_out)
         self.offset = nn.Parameter(torch.zeros((1 + order) * n_out))
@@ -39,6 +40,9 @@ class SageLayer(nn.Module):
             feat = torch.cat([self.linearB(x[sampled_nodes]), self.linearW(feat)], 1)
         else:
             feat = self.linearW(x)
+        if self.fused:                       # one kernel per direction instead of ~10 / ~20 (gnn_b200/models.py)
+            from .models import elu_rownorm
+            return elu_rownorm(feat, self.scale, self.offset)
         out = F.elu(feat)
         mean = out.mean(dim=1, keepdim=True)
         var = out.var(dim=1, unbiased=False, keepdim=True) + 1e-9
@@ -46,11 +50,11 @@ class SageLayer(nn.Module):
 
 
 class SageNet(nn.Module):
-    def __init__(self, nfeat, nhid, orders, num_classes, spmm, dropout=0.1):
+    def __init__(self, nfeat, nhid, orders, num_classes, spmm, dropout=0.1, fused=False):
         super().__init__()
-        self.layers = nn.ModuleList([SageLayer(nfeat, nhid, orders[0], spmm)])
+        self.layers = nn.ModuleList([SageLayer(nfeat, nhid, orders[0], spmm, fused)])
         for i in range(len(orders) - 1):
-            self.layers.append(SageLayer((1 + orders[i]) * nhid, nhid, orders[i + 1], spmm))
+            self.layers.append(SageLayer((1 + orders[i]) * nhid, nhid, orders[i + 1], spmm, fused))
         self.dropout = nn.Dropout(dropout)
         self.head = nn.Linear((1 + orders[-1]) * nhid, num_classes)
 
@@ -83,12 +87,12 @@ def exchange_gradients(params, world):
     return flat.numel() * 4
 
 
-def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, world, log):
+def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, world, log, fused=False):
     """Full training steps over the rotated pre-sampled minibatches (sampling excluded, as stated in the line)."""
     import torch.distributed as dist
     from . import graphgen
     torch.manual_seed(1234)                      # same initial replica on every rank (reference main.py:91-97 builds one per thread)
-    model = SageNet(shape.feat_dim, nhid, orders, shape.num_classes, cso.spmm).to(device)
+    model = SageNet(shape.feat_dim, nhid, orders, shape.num_classes, cso.spmm, fused=fused).to(device)
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=0.01)
     labels_all = graphgen.labels(shape, seed=3)
@@ -160,11 +164,12 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
     return {"minibatches_per_s": round(world * steps / max(ms * 1e-3, wall), 2), "unit": "minibatches/s", "steps": steps,
             "ms_per_step_device": round(ms / steps, 3), "ms_per_step_wall": round(wall / steps * 1e3, 3),
             "allreduce_bytes_per_step": int(comm_bytes), "parameters": int(nparams), "final_loss": round(last, 4),
+            "fused_epilogue": bool(fused),
             "note": "gather (next minibatch prefetched on a side stream) + GraphSAGE fwd + BCE loss + bwd + clip + NCCL "
                     "allreduce(sum) + Adam on pre-sampled minibatches (host LADIES sampling and adjacency upload excluded)"}
 
 
-def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log, pool_num=4):
+def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log, pool_num=4, fused=False):
     """Training with the sampler IN the loop (BASELINE's second minibatches/s number): ``pool_num`` sampler threads
     (reference main.py:77 uses a ThreadPoolExecutor of --pool_num=4 per GPU) run the device LADIES sampler
     (gnn_b200/gpu_sampler.py: numpy draw on the host, array passes on the GPU) and the feature gather on their own
@@ -175,7 +180,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
     import torch.distributed as dist
     from . import gpu_sampler, graphgen
     torch.manual_seed(1234)
-    model = SageNet(shape.feat_dim, nhid, orders, shape.num_classes, cso.spmm).to(device)
+    model = SageNet(shape.feat_dim, nhid, orders, shape.num_classes, cso.spmm, fused=fused).to(device)
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=0.01)
     labels_all = graphgen.labels(shape, seed=3)
@@ -252,5 +257,6 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         wall = float(t.item())
     return {"minibatches_per_s": round(world * steps / wall, 2), "unit": "minibatches/s", "steps": steps,
             "ms_per_step_wall": round(wall / steps * 1e3, 3), "sampler_threads": pool_num, "final_loss": round(last, 4),
+            "fused_epilogue": bool(fused),
             "note": "live LADIES sampling: numpy draw on the host + device array passes (bit-identical sampled sets), "
                     "gather in the sampler threads, then the same training step; wall clock incl. sampling"}

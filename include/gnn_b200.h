@@ -212,6 +212,23 @@ int gnn_column_slice_fill(const int32_t *ucols, const int32_t *fullrowptr, int64
                           const int32_t *rowptr, void *out_colidx, int colidx_bytes, gnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Fused layer epilogue - the elementwise tail of every reference layer,
+ * models.py:21-25 (GraphSageConvolution) and :61-64 (GraphConvolution):
+ *     out = elu(x);  mean = out.mean(1);  var = out.var(1, unbiased=False) + 1e-9
+ *     y = (out - mean) * scale * rsqrt(var) + offset
+ * gnn_elu_rownorm_fwd_f32 also returns mean[M] and rstd[M] for the backward.
+ * gnn_elu_rownorm_bwd_f32: dx[M,C], dscale[C], doffset[C] from dy; column sums are reduced in a fixed order
+ * (per-CTA partials in the workspace, gnn_elu_rownorm_workspace_bytes(C) bytes), so results are reproducible.
+ * C <= 2048.
+ * ------------------------------------------------------------------------- */
+size_t gnn_elu_rownorm_workspace_bytes(int64_t C);
+int gnn_elu_rownorm_fwd_f32(const float *x, int64_t ldx, int64_t M, int64_t C, const float *scale, const float *offset,
+                            float *y, int64_t ldy, float *mean, float *rstd, gnn_stream_t stream);
+int gnn_elu_rownorm_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx, int64_t M, int64_t C,
+                            const float *scale, const float *mean, const float *rstd, float *dx, int64_t lddx,
+                            float *dscale, float *doffset, void *workspace, size_t workspace_bytes, gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Feature-shard memory that peers can map (one process per GPU).
  *
  * gnn_shard_alloc   : cudaMalloc'd buffer + its 64-byte IPC handle.
