@@ -379,7 +379,7 @@ int launch_spmm_t(const SpmmParams &p, const XSrc<GATHER> &xs, cudaStream_t st) 
 }
 
 #ifdef GNN_TUNE
-// experiment build only (scratch/tune.py): pick (NV, U, MINB) from the environment
+// experiment build only (tools/tune_spmm.py): pick (NV, U, MINB) from the environment
 inline int env_int(const char *name, int dflt) { const char *v = getenv(name); return v ? atoi(v) : dflt; }
 template <int NV, int U>
 int launch_tune_minb(int minb, const SpmmParams &p, const XSrc<false> &xs, cudaStream_t st) {

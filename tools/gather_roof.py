@@ -2,7 +2,7 @@
 import ctypes, sys
 import numpy as np, torch
 sys.path.insert(0, '.')
-lib = ctypes.CDLL('scratch/libgnn_b200_tune.so')
+lib = ctypes.CDLL('tools/_build/libgnn_b200_tune.so')
 z = np.load('.cache/mb_reddit_0.npz')
 P = lambda t: ctypes.c_void_p(t.data_ptr())
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

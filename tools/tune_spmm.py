@@ -3,7 +3,7 @@ import ctypes, os, sys, itertools, json
 import numpy as np, torch
 sys.path.insert(0, '.')
 import oracle
-lib = ctypes.CDLL('scratch/libgnn_b200_tune.so')
+lib = ctypes.CDLL('tools/_build/libgnn_b200_tune.so')
 vp, i64, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t
 lib.gnn_csr_spmm_workspace_bytes.restype = sz
 lib.gnn_csr_spmm_workspace_bytes.argtypes = [i64, i64, i64]
