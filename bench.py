@@ -258,7 +258,7 @@ def main():
                                       layer.nrows, layer.ncols)
             adjs.append(cso.adjacency_of(a))
             # rows padded to 16 bytes, exactly like the buffer the product's gather hands to the first SpMM
-            ld = (D + 3) // 4 * 4
+            ld = gmod.padded_ld(D)
             xs.append(torch.randn(layer.ncols, ld, device=device, generator=gen)[:, :D])
             gs.append(torch.randn(layer.nrows, D, device=device, generator=gen) if li > 0 else None)
         dev_mbs.append((adjs, xs, gs))
@@ -295,6 +295,11 @@ def main():
                 events[k][1].record()
             k += 1
 
+    # the clock sampler (nvidia-smi -lms) starts BEFORE the warm-up: its start-up (NVML init, first query) stalls
+    # launches for milliseconds, which must not land inside the timed region
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+
     # ---- warm-up
     for i in range(args.warmup):
         flush_l2()
@@ -303,9 +308,12 @@ def main():
     barrier()
 
     # ---- timed region: K steps, CUDA events per step and per op on the launching (current) stream
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    time.sleep(0.25)
+    import gc
+    gc.collect()
+    gc.disable()            # a generational collection pause between two event records would be billed to that op
+    t_wait = time.time()
+    while len(clocks.rows) < 2 and time.time() - t_wait < 5.0:
+        time.sleep(0.05)
     launches0 = ext.launch_count()
     step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     op_ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in op_names] for _ in range(args.steps)]
@@ -322,10 +330,14 @@ def main():
     barrier()
     wall = time.perf_counter() - wall0
     t_end = time.time()
+    gc.enable()
     launches = ext.launch_count() - launches0
     clk = clocks.stop(t_begin, t_end)
 
     step_ms = np.array([a.elapsed_time(b) for a, b in step_ev])
+    if os.environ.get("BENCH_DUMP_OPS"):
+        print(np.array2string(np.array([[a.elapsed_time(b) for a, b in row] for row in op_ev]), precision=3, max_line_width=200),
+              file=sys.stderr)
     op_ms = np.array([[a.elapsed_time(b) for a, b in row] for row in op_ev])          # [steps, ops]
     total_ms = float(step_ms.sum())
     total_bytes = float(sum(step_bytes[s % len(mbs)] for s in range(args.steps)))
@@ -359,7 +371,8 @@ def main():
         t_hbm = bytes_k.mean() / (hbm_peak * 1e9)
         t_l2 = 4 * nnzD.mean() / L2_GATHER_ROOF_BPS                            # gather bytes / measured pure-gather roof
         t_fma = nnzD.mean() / (148 * 128 * sm_clk_ghz * 1e9)
-        ops.append({"op": name, "ms": round(float(ms.mean()), 4), "share": round(float(ms.sum() / op_ms.sum()), 4),
+        ops.append({"op": name, "ms": round(float(ms.mean()), 4), "ms_median": round(float(np.median(ms)), 4),
+                    "ms_max": round(float(ms.max()), 4), "share": round(float(ms.sum() / op_ms.sum()), 4),
                     "algorithmic_GBps": round(float(bytes_k.sum() / (ms.sum() * 1e-3) / 1e9), 1),
                     "bytes": int(bytes_k.mean()), "gather_GB": round(float(4 * nnzD.mean() / 1e9), 3),
                     "gflop": round(float(2 * nnzD.mean() / 1e9), 3),

@@ -369,8 +369,54 @@ inline size_t spmm_counter_bytes(int64_t M, int64_t nnz, int64_t D) {
   return ((size_t)M * (size_t)cdiv(D, 32) * sizeof(int) + 255) / 256 * 256;
 }
 
+// Wave fitting: every warp item costs the same (C nonzeros of one slab), so the kernel runs in waves of
+// `slots` = SMs x resident warps.  A grid that is 1 % over a wave boundary takes a whole extra wave (+24 % measured
+// at 1.02 waves), so the chunk is shrunk - never below half the base size, which the workspace bound assumes - until
+// the items fill an integral number of waves as exactly as possible.
+inline int wave_fit_chunk(int64_t nnz, int nslabs, int base_c, int64_t slots) {
+  if (slots <= 0) return base_c;
+  const int64_t items0 = cdiv(nnz, base_c) * nslabs;
+  if (2 * items0 < slots) return base_c;            // small problems are latency-bound: keep the tuned chunk
+  const int64_t waves = std::max<int64_t>(1, cdiv(items0, slots));
+  const int64_t chunks_per_slab = std::max<int64_t>(1, waves * slots / nslabs);
+  int64_t c = cdiv(nnz, chunks_per_slab);
+  c = std::max<int64_t>(c, std::max(32, base_c / 2));
+  c = std::min<int64_t>(c, base_c);
+  return (int)c;
+}
+
+inline int device_sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 template <int VEC, int NV, int LPR, bool GATHER, int U = default_u(NV), int MINB = default_minb(NV)>
-int launch_spmm_t(const SpmmParams &p, const XSrc<GATHER> &xs, cudaStream_t st) {
+int launch_spmm_t(const SpmmParams &p0, const XSrc<GATHER> &xs, cudaStream_t st) {
+  static std::atomic<int> ctas_per_sm{0};            // of this instantiation (registers decide it)
+  int occ = ctas_per_sm.load(std::memory_order_relaxed);
+  if (occ == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_rowsplit_kernel<VEC, NV, LPR, GATHER, U, MINB>, kThreads, 0) !=
+            cudaSuccess || occ <= 0) {
+      (void)cudaGetLastError();
+      occ = MINB;
+    }
+    ctas_per_sm.store(occ, std::memory_order_relaxed);
+  }
+  SpmmParams p = p0;
+#ifdef GNN_TUNE
+  if (!getenv("GNN_TUNE_C"))
+#endif
+  {
+    p.C = wave_fit_chunk(p.nnz, p.nslabs, p0.C, (int64_t)device_sm_count() * occ * kWarpsPerCta);
+    p.nchunks = (int)cdiv(p.nnz, p.C);
+  }
   const int64_t items = (int64_t)p.nchunks * p.nslabs;
   const unsigned grid = (unsigned)cdiv(items, kWarpsPerCta);
   spmm_rowsplit_kernel<VEC, NV, LPR, GATHER, U, MINB><<<grid, kThreads, 0, st>>>(p, xs);
@@ -1050,7 +1096,7 @@ int gnn_coo_to_csr(const int64_t *indices, int64_t M, int64_t nnz, int32_t *out_
 
 size_t gnn_csr_spmm_workspace_bytes(int64_t M, int64_t nnz, int64_t D) {
   if (M <= 0 || nnz <= 0 || D <= 0) return 256;
-  const int C = spmm_chunk(nnz, D);
+  const int C = std::max(32, spmm_chunk(nnz, D) / 2);     // wave fitting may halve the base chunk
   const size_t nchunks = (size_t)cdiv(nnz, C);
   const size_t Dp = (size_t)cdiv(D, 4) * 4;
   const size_t counter_bytes = spmm_counter_bytes(M, nnz, D);

@@ -25,8 +25,9 @@ from . import _native
 
 
 def padded_ld(feat_dim: int) -> int:
-    """Rows of shards / gathered buffers are padded to 16 bytes so every row is float4-aligned."""
-    return (int(feat_dim) + 3) // 4 * 4
+    """Rows of shards / gathered buffers start on 128-byte lines (ld = multiple of 32 floats): float4 loads for any F,
+    and no X row of the first SpMM straddles a cache line it does not own (measured -10 % on the F=602 block)."""
+    return (int(feat_dim) + 31) // 32 * 32
 
 
 class FeatureStore:
