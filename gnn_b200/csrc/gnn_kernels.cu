@@ -98,8 +98,8 @@ struct XSrc {
 };
 
 // nonzeros kept in flight per warp step (U) and CTAs per SM asked of ptxas (MINB), by vectors per lane
-// (tuned on B200 over the Reddit-shaped blocks, profiles/tune_r1.txt)
-constexpr int default_u(int nv) { return nv >= 4 ? 2 : (nv >= 2 ? 4 : 8); }
+// (tuned on B200 over the Reddit-shaped blocks with wave fitting active, profiles/tune_r1.txt)
+constexpr int default_u(int nv) { return nv >= 5 ? 1 : (nv == 4 ? 2 : (nv >= 2 ? 4 : 8)); }
 constexpr int default_minb(int nv) { return (nv == 3 || nv == 4) ? 3 : (nv >= 6 ? 2 : 4); }
 
 // Dload = floats readable per X row (D, or D rounded up to 4 when rows are padded to 16 bytes)
@@ -328,7 +328,7 @@ inline int spmm_chunk(int64_t nnz, int64_t D) {
 
 struct SpmmPlan { int vec, nv, lpr, nslabs, C, nchunks, Dp; };
 
-constexpr int64_t kTargetItems = 2048;   // warp items wanted before wider slabs are preferred
+constexpr int64_t kTargetItems = 3072;   // warp items (~2/3 of a wave) wanted before wider slabs are preferred
 
 inline SpmmPlan make_plan(int64_t nnz, int64_t D, int vec) {
   SpmmPlan pl;

@@ -15,7 +15,7 @@ blocks = []
 for li, D in [(0, 602), (1, 1024), (2, 1024)]:
     M, K = [int(v) for v in z[f'l{li}_shape']]
     rows, cols, vals = oracle.build_adj(z[f'l{li}_fullrowptr'], z[f'l{li}_rowptr'], z[f'l{li}_colidx'], z[f'l{li}_normfact'], M)
-    ld = (D + 3) // 4 * 4
+    ld = (D + 31) // 32 * 32
     X = torch.randn(K, ld, device='cuda')
     blocks.append(dict(li=li, M=M, K=K, D=D, ld=ld, nnz=len(vals), rowptr=torch.from_numpy(z[f'l{li}_rowptr']).cuda(),
                        col=torch.from_numpy(cols.astype(np.int32)).cuda(), vals=torch.from_numpy(vals).cuda(), X=X,
@@ -43,10 +43,12 @@ for b in blocks:
     print(f"layer{b['li']} D={b['D']} default: {t*1e3:.1f} us", flush=True)
 res = []
 for b in blocks:
-    cs = [512, 1024] if b['li'] < 2 else [32, 64]
+    cs = [0] if b['li'] < 2 else [0, 64]            # 0 = leave the chunk to the wave-fitting planner
     for nv, u, minb, c in itertools.product([1, 2, 3, 4, 5], [1, 2, 4, 8], [2, 3, 4], cs):
         if nv * u > 16 or nv * u < 4: continue
-        os.environ.update(GNN_TUNE_NV=str(nv), GNN_TUNE_U=str(u), GNN_TUNE_MINB=str(minb), GNN_TUNE_C=str(c))
+        os.environ.update(GNN_TUNE_NV=str(nv), GNN_TUNE_U=str(u), GNN_TUNE_MINB=str(minb))
+        if c: os.environ['GNN_TUNE_C'] = str(c)
+        else: os.environ.pop('GNN_TUNE_C', None)
         t = run(b, reps=3)
         ok = torch.allclose(b['Y'], ref[b['li']], rtol=1e-4, atol=1e-5)
         res.append((b['li'], nv, u, minb, c, t, ok))
