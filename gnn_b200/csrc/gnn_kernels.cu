@@ -45,11 +45,6 @@ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // ---------------------------------------------------------------------------
 // vector helpers
 // ---------------------------------------------------------------------------
-template <int VEC> struct Vec;
-template <> struct Vec<4> { float4 v; };
-template <> struct Vec<2> { float2 v; };
-template <> struct Vec<1> { float v; };
-
 template <int VEC>
 __device__ __forceinline__ void vzero(float (&a)[VEC]) {
 #pragma unroll
