@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _native
-from .sampler import sampled_nodes_remap
+from .sampler import sampled_nodes_remap, sorted_unique
 
 
 @dataclasses.dataclass
@@ -90,8 +90,13 @@ def legacy_choice_on_support(rs: np.random.RandomState, p_nz: np.ndarray, size: 
         cdf = np.cumsum(p)
         cdf /= cdf[-1]
         new = cdf.searchsorted(x, side="right")
-        _, unique_indices = np.unique(new, return_index=True)
-        unique_indices.sort()
+        # == `_, unique_indices = np.unique(new, return_index=True); unique_indices.sort()`: first occurrences, in draw order
+        order = np.argsort(new, kind="stable")
+        snew = new[order]
+        first = np.empty(snew.size, dtype=bool)
+        first[0] = True
+        np.not_equal(snew[1:], snew[:-1], out=first[1:])
+        unique_indices = np.sort(order[first])
         new = new.take(unique_indices)
         found[n_uniq:n_uniq + new.size] = new
         n_uniq += new.size
@@ -137,7 +142,7 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
         p_nz = pi_nz / np.sum(pi_nz)                                                        # :124 (same quotients)
         s_num = np.min([nz.size, samp_num_list[d]])                                         # :126 (count of p > 0)
         after_nodes = nz[legacy_choice_on_support(rs, p_nz, int(s_num))]                    # :128
-        after_nodes = np.unique(np.concatenate((after_nodes, previous_nodes)))              # :131
+        after_nodes = sorted_unique(np.concatenate((after_nodes, previous_nodes)))          # :131 (np.unique)
         pos = np.minimum(np.searchsorted(nz, after_nodes), nz.size - 1)
         p_after = np.where(nz[pos] == after_nodes, p_nz[pos], 0.0)                          # p[after_nodes]
         after_dev = torch.from_numpy(after_nodes.astype(np.int64, copy=False)).to(dev)

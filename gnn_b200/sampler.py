@@ -87,9 +87,25 @@ def column_slice(u_cols: np.ndarray, lens: np.ndarray, after_nodes: np.ndarray, 
     return rowptr, local[keep]
 
 
+def sorted_unique(a: np.ndarray) -> np.ndarray:
+    """``np.unique(a)`` through sort + neighbour compare (numpy 2.3's hash-based unique is several times slower here)."""
+    if a.size == 0:
+        return a
+    s = np.sort(a)
+    keep = np.empty(s.size, dtype=bool)
+    keep[0] = True
+    np.not_equal(s[1:], s[:-1], out=keep[1:])
+    return s[keep]
+
+
 def sampled_nodes_remap(after_nodes: np.ndarray, previous_nodes: np.ndarray) -> np.ndarray:
-    """reference sampler.py:143: positions of ``previous_nodes`` inside sorted-unique ``after_nodes``."""
-    return np.where(np.isin(after_nodes, previous_nodes))[0]
+    """reference sampler.py:143, ``np.where(np.in1d(after_nodes, previous_nodes))[0]``: positions inside the
+    sorted-unique ``after_nodes`` of the nodes that also occur in ``previous_nodes`` (ascending)."""
+    prev = sorted_unique(np.asarray(previous_nodes))
+    pos = np.searchsorted(after_nodes, prev)
+    ok = pos < after_nodes.size
+    ok[ok] = after_nodes[pos[ok]] == prev[ok]
+    return pos[ok]
 
 
 def ladies_sample(seed: int, batch_nodes, samp_num_list: Sequence[int], num_nodes: int,
@@ -118,7 +134,7 @@ def ladies_sample(seed: int, batch_nodes, samp_num_list: Sequence[int], num_node
         p = pi / np.sum(pi)                                                        # :124
         s_num = np.min([np.sum(p > 0), samp_num_list[d]])                          # :126
         after_nodes = rs.choice(num_nodes, s_num, p=p, replace=False)              # :128
-        after_nodes = np.unique(np.concatenate((after_nodes, previous_nodes)))     # :131
+        after_nodes = sorted_unique(np.concatenate((after_nodes, previous_nodes)))  # :131 (np.unique)
         rowptr, local_cols = column_slice(u_cols, lens, after_nodes, num_nodes)    # :133
         normfact = 1 / np.clip(s_num * p[after_nodes], 1e-10, 1).astype(np.float32)  # :137
         layers.append(LayerCSR(
