@@ -81,3 +81,56 @@ def test_dropin_graphsage_matches_reference_golden(models, golden_dir):
         ref = z["g_" + name]
         got = p.grad.cpu().numpy()
         assert np.allclose(got, ref, rtol=2e-4, atol=2e-6), name
+
+
+def test_training_loop_converges_on_tiny_graph(models):
+    """End-to-end sanity in the reference's calling pattern (main.py:118-170): device LADIES sampler -> FeatureStore
+    gather -> drop-in GraphSage/GNN on custom_sparse_ops.spmm -> BCE loss -> backward -> clip -> Adam; the loss of a
+    fixed evaluation minibatch must fall."""
+    import custom_sparse_ops as cso
+    from gnn_b200 import gather, gpu_sampler, harness
+    shape = graphgen.SHAPES["tiny"]
+    g = graphgen.generate(shape, seed=0)
+    feats = graphgen.features(shape, seed=1)
+    # learnable labels: class = argmax of a fixed random projection of the node's own features
+    rng = np.random.Generator(np.random.PCG64(0))
+    labels = (feats @ rng.standard_normal((shape.feat_dim, shape.num_classes))).argmax(1)
+    n = shape.num_nodes
+    top = np.arange(0, n, 2)
+    did = np.full(n, -1, dtype=np.int64)
+    did[top] = 0
+    idx = np.arange(n, dtype=np.int64)
+    idx[top] = np.arange(top.size)
+    dev = torch.device("cuda", 0)
+    store = gather.FeatureStore(torch.from_numpy(feats), [top], did, idx, [0], 0, dev)
+    dg = gpu_sampler.DeviceGraph(g.indptr, g.indices, dev)
+    torch.manual_seed(0)
+    enc = models.GraphSage(nfeat=shape.feat_dim, nhid=32, orders=[1, 1], dropout=0.0)
+    net = models.GNN(encoder=enc, num_classes=shape.num_classes, dropout=0.0, inp=shape.feat_dim).to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=0.01)
+
+    def loss_of(mb):
+        x0 = store.gather(torch.from_numpy(mb.input_nodes).to(dev))
+        out = net(x0, mb.adjs, mb.sampled_nodes)
+        y = torch.nn.functional.one_hot(torch.from_numpy(labels[mb.batch_nodes]), shape.num_classes).float().to(dev)
+        return harness.bce_loss(out, y)
+
+    eval_mb = gpu_sampler.ladies_sample_device(999, g.train_nodes[:64], [128] * 3, dg, [1, 1])
+    net.eval()
+    with torch.no_grad():
+        before = loss_of(eval_mb).item()
+    net.train()
+    perm = np.random.Generator(np.random.PCG64(1)).permutation(g.train_nodes.size)
+    for it in range(60):
+        bn = g.train_nodes[perm[(it * 32) % (perm.size - 32):][:32]]
+        mb = gpu_sampler.ladies_sample_device(1000 + it, bn, [128] * 3, dg, [1, 1])
+        opt.zero_grad()
+        loss = loss_of(mb)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 5)
+        opt.step()
+    net.eval()
+    with torch.no_grad():
+        after = loss_of(eval_mb).item()
+    store.close()
+    assert np.isfinite(after) and after < 0.8 * before, (before, after)
