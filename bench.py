@@ -156,32 +156,55 @@ def cpu_reference_sample(mb, widths, target_s, log, steps=1, warmup=0):
     ncpu = len(os.sched_getaffinity(0))
     sweep = sorted({t for t in (1, 2, 4, 8, 16, 32, ncpu) if t <= ncpu})
 
-    def one_pass():
+    def one_pass(split=None):
         t0 = time.perf_counter()
         for li, a, x, gq in blocks:
-            a.mm(x)
+            t1 = time.perf_counter()
+            a.mm(x)                                          # custom_sparse_ops.py:25
+            t2 = time.perf_counter()
             if li > 0:
-                a.transpose(0, 1).mm(gq)
+                a.transpose(0, 1).mm(gq)                     # custom_sparse_ops.py:36
+            if split is not None:
+                split[0] += t2 - t1
+                split[1] += time.perf_counter() - t2
         return time.perf_counter() - t0
 
+    default_threads = torch.get_num_threads()
+    sweep_ms = {}
     best_t, best_threads = None, 1
     for th in sweep:
         torch.set_num_threads(th)
         one_pass()
         t = min(one_pass() for _ in range(2))
+        sweep_ms[str(th)] = round(t * 1e3, 1)
         if best_t is None or t < best_t:
             best_t, best_threads = t, th
     torch.set_num_threads(best_threads)
-    for _ in range(warmup):
+    for _ in range(max(warmup, 2)):
         one_pass()
-    times = [one_pass() for _ in range(max(steps, 1))]
-    t = float(np.mean(times))
+    split = [0.0, 0.0]
+    nrep = max(steps, 5) if steps <= 1 else steps
+    times = [one_pass(split) for _ in range(nrep)]
+    t = float(np.median(times))
+    # the reference's gather block (main.py:129-134) on CPU tensors: boolean-mask scatter of fancy-indexed rows
+    n0, F = mb.layers[0].ncols, widths[0]
+    table = torch.randn(max(4 * n0, 1024), F)
+    ids = torch.randint(0, table.shape[0], (n0,))
+    mask = torch.ones(n0, dtype=torch.bool)
+    tg = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        out = torch.empty(n0, F)
+        out[mask] = table[ids].float()
+        tg.append(time.perf_counter() - t0)
     sample = (f"first {frac * 100:.1f}% of the rows of each of the {len(blocks)} layer blocks of one minibatch "
               f"(torch.sparse COO mm fwd + transpose().mm bwd, reference custom_sparse_ops.py:25,36), "
-              f"best of threads {sweep} on {ncpu} usable cores")
+              f"best of threads {sweep} on {ncpu} usable cores, median of {nrep} passes after 2 warm-ups")
     log(f"cpu reference: {nbytes / t / 1e9:.3f} GB/s at {best_threads} threads, {t * 1e3:.1f} ms per sampled pass, frac {frac:.4f}")
     return {"value": nbytes / t / 1e9, "unit": "GB/s", "cores": best_threads, "kind": "reference", "sample": sample,
-            "ms_per_sample": t * 1e3, "total_nnz_full": total_nnz}, times
+            "ms_per_sample": t * 1e3, "fwd_ms": round(split[0] / nrep * 1e3, 1), "bwd_ms": round(split[1] / nrep * 1e3, 1),
+            "thread_sweep_ms": sweep_ms, "host_cpus": os.cpu_count(), "usable_cores": ncpu, "torch_default_threads": default_threads,
+            "gather_cpu_ms": round(float(np.median(tg)) * 1e3, 2), "total_nnz_full": total_nnz}, times
 
 
 # ----------------------------------------------------------------------------- main

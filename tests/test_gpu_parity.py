@@ -380,3 +380,31 @@ def test_concurrent_threads_and_streams(cu, small_mb):
         t.join()
     assert not errors, errors
     assert all(all(v) for v in results.values()) and len(results) == 4
+
+
+def test_spmm_and_transpose_randomised_shapes(cu):
+    """Differential fuzz: random shapes, densities, skew, widths and leading dimensions against the oracle."""
+    rng = np.random.Generator(np.random.PCG64(20261018))
+    for trial in range(40):
+        M = int(rng.integers(1, 3000))
+        K = int(rng.integers(1, 6000))
+        D = int(rng.choice([1, 2, 5, 16, 24, 33, 64, 96, 100, 128, 200, 256, 300, 512, 602, 640, 1000, 1024]))
+        mean = float(rng.choice([0.5, 3, 20, 150]))
+        lens = np.minimum(rng.poisson(mean, M) * (rng.random(M) < 0.9), K)
+        if rng.random() < 0.3:
+            lens[rng.integers(0, M)] = min(K, int(rng.integers(500, 5000)))       # a hub row
+        rowptr, cols, vals = _random_csr(rng, M, K, lens)
+        pad = int(rng.choice([0, 0, 1, 2, 4, 6, 30]))
+        Xfull = rng.standard_normal((K, D + pad)).astype(np.float32)
+        X = np.ascontiguousarray(Xfull[:, :D])
+        d_rowptr, d_cols, d_vals = cu.dev(rowptr), cu.dev(cols), cu.dev(vals)
+        Y = cu.csr_spmm(d_rowptr, d_cols, d_vals, M, K, cu.dev(Xfull)[:, :D], ldx=D + pad, ldy=D + int(rng.choice([0, 3]))).cpu().numpy()
+        assert not np.isnan(Y).any(), (trial, M, K, D)
+        ref = oracle.spmm_f64acc(rowptr, cols, vals, M, X)
+        err, maxerr = oracle.rel_err(Y, ref)
+        assert (err if D >= 16 else maxerr) <= TOL, (trial, M, K, D, pad, err, maxerr)
+        if cols.size:
+            t_rowptr, t_col, t_vals = cu.csr_transpose(d_rowptr, d_cols, d_vals, M, K)
+            o_rowptr, o_col, perm = oracle.csr_transpose(rowptr, cols, M, K)
+            assert np.array_equal(t_rowptr.cpu().numpy(), o_rowptr) and np.array_equal(t_col.cpu().numpy(), o_col)
+            assert np.array_equal(t_vals.cpu().numpy(), vals[perm])
