@@ -1002,40 +1002,7 @@ inline unsigned warp_grid(int64_t n_warps, int wpb) {
 }
 
 #ifdef GNN_TUNE
-// experiment build only: speed-of-light of the L2->SM gather the SpMM performs (random rows of X, float4 per lane,
-// NV vectors per lane, U rows in flight, nothing but the loads and one FADD per float)
-template <int NV, int U>
-__global__ void __launch_bounds__(256)
-gather_roof_kernel(const float *__restrict__ X, int ldx, int K, const int *__restrict__ colidx, int nnz, int per_warp,
-                   float *__restrict__ sink) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  int s = (int)((w * per_warp) % nnz);
-  float acc[NV][4];
-#pragma unroll
-  for (int n = 0; n < NV; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-  for (int base = 0; base < per_warp; base += 32) {
-    const int cl = __ldg(colidx + (s + base + lane) % nnz);
-    for (int t = 0; t < 32; t += U) {
-      float4 x[U][NV];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int c = __shfl_sync(kFull, cl, t + u);
-        const float4 *xr = reinterpret_cast<const float4 *>(X + (int64_t)c * ldx) + lane;
-#pragma unroll
-        for (int n = 0; n < NV; ++n) x[u][n] = __ldg(xr + n * 32);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int n = 0; n < NV; ++n) { acc[n][0] += x[u][n].x; acc[n][1] += x[u][n].y; acc[n][2] += x[u][n].z; acc[n][3] += x[u][n].w; }
-    }
-  }
-  float t = 0.f;
-#pragma unroll
-  for (int n = 0; n < NV; ++n) t += acc[n][0] + acc[n][1] + acc[n][2] + acc[n][3];
-  if (t == 12345.678f) sink[0] = t;
-}
+#include "experiments_device.cuh"   // gather-roof microbenchmark, hub-cache prototype (tools/ only)
 #endif
 
 }  // namespace
@@ -1309,20 +1276,7 @@ int gnn_elu_rownorm_bwd_f32(const float *dy, int64_t lddy, const float *x, int64
 }
 
 #ifdef GNN_TUNE
-int gnn_debug_gather_roof(const float *X, int ldx, int K, const int *colidx, int nnz, int nv, int u, int warps, int per_warp,
-                          float *sink, gnn_stream_t stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = (unsigned)cdiv(warps, 8);
-#define GR(NV_, U_) gather_roof_kernel<NV_, U_><<<grid, 256, 0, st>>>(X, ldx, K, colidx, nnz, per_warp, sink)
-  if (nv == 8 && u == 1) GR(8, 1); else if (nv == 8 && u == 2) GR(8, 2);
-  else if (nv == 4 && u == 2) GR(4, 2); else if (nv == 4 && u == 4) GR(4, 4);
-  else if (nv == 2 && u == 4) GR(2, 4); else if (nv == 2 && u == 8) GR(2, 8);
-  else if (nv == 1 && u == 8) GR(1, 8); else if (nv == 1 && u == 16) GR(1, 16);
-  else return GNN_E_BADARG;
-#undef GR
-  GNN_LAUNCH_CHECK();
-  return 0;
-}
+#include "experiments_host.cuh"
 #endif
 
 int gnn_shard_alloc(size_t bytes, void **dev_ptr, unsigned char ipc_handle[64]) {
