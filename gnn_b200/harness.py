@@ -169,7 +169,8 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
                     "allreduce(sum) + Adam on pre-sampled minibatches (host LADIES sampling and adjacency upload excluded)"}
 
 
-def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log, pool_num=4, fused=False):
+def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log, pool_num=4, fused=False,
+                     prebuild_transpose=True):
     """Training with the sampler IN the loop (BASELINE's second minibatches/s number): ``pool_num`` sampler threads
     (reference main.py:77 uses a ThreadPoolExecutor of --pool_num=4 per GPU) run the device LADIES sampler
     (gnn_b200/gpu_sampler.py: numpy draw on the host, array passes on the GPU) and the feature gather on their own
@@ -188,7 +189,12 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
     tls = threading.local()
     main_stream = torch.cuda.current_stream(device)
     steps = max(4, min(args.steps, 24))
-    total = steps + 4
+    # every sampler thread owns a stream, and the caching allocator keeps one block pool per stream: until each pool
+    # has seen the largest adjacency it will hold, jobs hit cudaMalloc (device-synchronising).  Warm up long enough
+    # for that (untimed, like any production run's first steps); measured: 4 steps left runs at 19-52 ms/step, then
+    # the same code settles at 7.2 ms/step.
+    warm = 8 * pool_num
+    total = steps + warm
     rng = np.random.Generator(np.random.PCG64(77 + rank))
     chunk = (g.train_nodes.size + world - 1) // world
     own = g.train_nodes[rank * chunk: min((rank + 1) * chunk, g.train_nodes.size)]
@@ -201,7 +207,8 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
             tls.scratch = dg.scratch()
         with torch.cuda.stream(tls.stream):
             mb = gpu_sampler.ladies_sample_device(5000 + 1000 * rank + i, batches[i], [samp] * 5, dg, orders,
-                                                  create_coo_tensor=cso.create_coo_tensor, scratch=tls.scratch)
+                                                  create_coo_tensor=cso.create_coo_tensor, scratch=tls.scratch,
+                                                  prebuild_transpose=prebuild_transpose)
             nodes = torch.from_numpy(mb.input_nodes).to(device)
             x0 = store.gather(nodes)
             sn = [torch.from_numpy(np.ascontiguousarray(s_, dtype=np.int64)).to(device) for s_ in mb.sampled_nodes]
@@ -237,7 +244,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         opt.step()
         return loss
 
-    for _ in range(4):
+    for _ in range(warm):
         step()
     torch.cuda.synchronize()
     if world > 1:
@@ -256,7 +263,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wall = float(t.item())
     return {"minibatches_per_s": round(world * steps / wall, 2), "unit": "minibatches/s", "steps": steps,
-            "ms_per_step_wall": round(wall / steps * 1e3, 3), "sampler_threads": pool_num, "final_loss": round(last, 4),
+            "ms_per_step_wall": round(wall / steps * 1e3, 3), "sampler_threads": pool_num, "warmup_steps": warm, "final_loss": round(last, 4),
             "fused_epilogue": bool(fused),
             "note": "live LADIES sampling: numpy draw on the host + device array passes (bit-identical sampled sets), "
                     "gather in the sampler threads, then the same training step; wall clock incl. sampling"}
