@@ -561,9 +561,11 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
         dist.barrier()
     ready = None
     t0 = time.perf_counter()
+    marks = []
     for s in range(args.steps):
         ready, counts = step(nwarm + s, ready)
         src_counts.append(counts)
+        marks.append(time.perf_counter())
     if ready is not None:
         ready.synchronize()                   # the last step's loss is read inside the timed region too
         losses.append(float(loss_host[0]))
@@ -572,6 +574,8 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
         dist.barrier()
     dt = time.perf_counter() - t0
     pre.close()
+    log("e2e host-side step intervals (ms): " + " ".join(f"{(b - a) * 1e3:.2f}" for a, b in zip([t0] + marks, marks))
+        + f" | drain {(t0 + dt - marks[-1]) * 1e3:.2f}")
     assert len(losses) >= args.steps and all(np.isfinite(losses)), "every step's loss must have been read on the host"
     counts = torch.stack(src_counts).double().mean(0).cpu().numpy()      # rows per source per step
     bytes_all = float(sum(step_bytes[s % len(mbs)] for s in range(args.steps)))

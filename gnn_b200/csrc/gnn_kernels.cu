@@ -368,6 +368,13 @@ inline size_t spmm_counter_bytes(int64_t M, int64_t nnz, int64_t D) {
 // `slots` = SMs x resident warps.  A grid that is 1 % over a wave boundary takes a whole extra wave (+24 % measured
 // at 1.02 waves), so the chunk is shrunk - never below half the base size, which the workspace bound assumes - until
 // the items fill an integral number of waves as exactly as possible.
+constexpr int kHostGatherCtas = 16;
+
+// CTA slots that kernels on OTHER streams hold while an SpMM runs (gnn_set_corunner_ctas).  A one-wave grid that
+// finds even one slot taken by a long-running foreign CTA spills into a second wave: measured 1.46 -> 2.0 ms per
+// Reddit-shaped minibatch beside a single-CTA host-row gather.  The wave fit therefore leaves these slots out.
+std::atomic<int> g_corunner_ctas{0};
+
 inline int wave_fit_chunk(int64_t nnz, int nslabs, int base_c, int64_t slots) {
   if (slots <= 0) return base_c;
   const int64_t items0 = cdiv(nnz, base_c) * nslabs;
@@ -409,7 +416,8 @@ int launch_spmm_t(const SpmmParams &p0, const XSrc<GATHER> &xs, cudaStream_t st)
   if (!getenv("GNN_TUNE_C"))
 #endif
   {
-    p.C = wave_fit_chunk(p.nnz, p.nslabs, p0.C, (int64_t)device_sm_count() * occ * kWarpsPerCta);
+    const int64_t ctas = std::max<int64_t>(1, (int64_t)device_sm_count() * occ - g_corunner_ctas.load(std::memory_order_relaxed));
+    p.C = wave_fit_chunk(p.nnz, p.nslabs, p0.C, ctas * kWarpsPerCta);
     p.nchunks = (int)cdiv(p.nnz, p.C);
   }
   const int64_t items = (int64_t)p.nchunks * p.nslabs;
@@ -538,24 +546,58 @@ int spmm_entry(const int32_t *rowptr, const int32_t *colidx, const float *vals, 
 // ---------------------------------------------------------------------------
 // build_adj: one warp per row, lanes stride over the row's entries (coalesced)
 // ---------------------------------------------------------------------------
+constexpr int kAdjChunk = 256;
+
+// largest r in [lo, hi] with rowptr[r] <= i  (skips empty rows that share the same start)
+__device__ __forceinline__ int row_of_nnz(const int *__restrict__ rowptr, int lo, int hi, int i) {
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(rowptr + mid) <= i) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// One warp per 256 consecutive stored entries (not per row: a hub row of a LADIES layer holds thousands of entries and
+// a warp-per-row grid waited 65 us for it on a 3.9 M-entry layer).  Lane-strided, so every store instruction of the
+// warp covers one contiguous 128/256-byte run; the row of an entry is a bounded binary search between the rows of the
+// chunk's first and last entry (0-2 steps for all but the sparsest layers).
 template <typename ColT>
 __global__ void __launch_bounds__(256)
 build_adj_kernel(const int *__restrict__ fullrowptr, const int *__restrict__ rowptr, const ColT *__restrict__ colidx,
                  const float *__restrict__ normfact, int M, int64_t nnz, int64_t *__restrict__ out_idx,
                  float *__restrict__ out_vals, int *__restrict__ out_col32) {
   const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
-    const int b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
-    if (b == e) continue;
-    // cuda_spmm.cu:800: `1. / deg * normfact` - double quotient, double product, one rounding to float
-    const double inv_deg = 1. / (double)(__ldg(fullrowptr + r + 1) - __ldg(fullrowptr + r));
-    for (int i = b + lane; i < e; i += 32) {
-      const int c = (int)colidx[i];
-      out_vals[i] = (float)(inv_deg * (double)__ldg(normfact + c));
-      if (out_col32) out_col32[i] = c;
-      if (out_idx) { out_idx[i] = r; out_idx[nnz + i] = c; }
+  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t s64 = item * kAdjChunk;
+  if (s64 >= nnz) return;
+  const int s = (int)s64, e = (int)min((int64_t)s + kAdjChunk, nnz);
+  const int r_lo = row_of_nnz(rowptr, 0, M - 1, s);
+  const int r_hi = row_of_nnz(rowptr, r_lo, M - 1, e - 1);
+  constexpr int J = kAdjChunk / 32;
+  int c[J];
+  float nf[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int i = s + lane + 32 * j;
+    c[j] = i < e ? (int)colidx[i] : 0;
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) nf[j] = __ldg(normfact + c[j]);
+  int r_prev = -1;
+  double inv_deg = 0.;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int i = s + lane + 32 * j;
+    if (i >= e) break;
+    const int r = row_of_nnz(rowptr, max(r_lo, r_prev), r_hi, i);
+    if (r != r_prev) {
+      // cuda_spmm.cu:800: `1. / deg * normfact` - double quotient, double product, one rounding to float
+      inv_deg = 1. / (double)(__ldg(fullrowptr + r + 1) - __ldg(fullrowptr + r));
+      r_prev = r;
     }
+    out_vals[i] = (float)(inv_deg * (double)nf[j]);
+    if (out_col32) out_col32[i] = c[j];
+    if (out_idx) { out_idx[i] = r; out_idx[nnz + i] = c[j]; }
   }
 }
 
@@ -585,15 +627,6 @@ __global__ void coo_to_csr_kernel(const int64_t *__restrict__ idx, int64_t M, in
 // finds the rows its chunk touches with one uniform binary search, keeps 8 independent loads per lane in
 // flight, and resolves each nonzero's row by a search restricted to the chunk's few rows.
 constexpr int kTrChunk = 256;
-
-__device__ __forceinline__ int row_of_nnz(const int *__restrict__ rowptr, int lo, int hi, int i) {
-  // largest r in [lo, hi] with rowptr[r] <= i  (skips empty rows that share the same start)
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(rowptr + mid) <= i) lo = mid; else hi = mid - 1;
-  }
-  return lo;
-}
 
 template <bool FILL>
 __global__ void __launch_bounds__(256)
@@ -1014,6 +1047,13 @@ extern "C" {
 
 int gnn_abi_version(void) { return GNN_B200_ABI_VERSION; }
 
+int gnn_set_corunner_ctas(int ctas) {
+  if (ctas < 0) return GNN_E_BADARG;
+  return g_corunner_ctas.exchange(ctas, std::memory_order_relaxed);
+}
+
+int gnn_host_gather_ctas(void) { return kHostGatherCtas; }
+
 const char *gnn_error_string(int code) {
   switch (code) {
     case 0: return "success";
@@ -1035,7 +1075,7 @@ int gnn_build_adj(const int32_t *fullrowptr, const int32_t *rowptr, const void *
   if (M == 0 || nnz == 0) return 0;
   if (!fullrowptr || !rowptr || !colidx || !normfact || !out_vals) return GNN_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = warp_grid(M, 8);
+  const unsigned grid = (unsigned)cdiv(cdiv(nnz, kAdjChunk), 8);
   if (colidx_bytes == 2)
     build_adj_kernel<int16_t><<<grid, 256, 0, st>>>(fullrowptr, rowptr, (const int16_t *)colidx, normfact, (int)M, nnz,
                                                     out_indices, out_vals, out_colidx32);
@@ -1149,10 +1189,13 @@ int gnn_gather_rows_src_f32(const float *const *xrows, const int32_t *src_dev, i
   if (n0 < 0 || F < 0 || F >= (1ll << 31)) return GNN_E_BADARG;
   if (n0 == 0 || F == 0) return 0;
   if (!xrows || !src_dev || !out || ld_out < F) return GNN_E_BADARG;
-  // host rows (only_src == -1) are PCIe-bound: a few CTAs keep the link full and leave the SMs to whatever
-  // else is running (the gather of the next minibatch is typically prefetched next to the current step)
+  // host rows (only_src == -1) are PCIe-bound and normally run NEXT TO the current step's SpMMs (prefetch of the
+  // next minibatch).  The grid is capped for the co-runners' sake, not the link's: every kernel launch fetches its
+  // commands over the same PCIe link, behind whatever zero-copy reads are queued - 48 CTAs (47.6 GB/s) add 16 us to
+  // each launch on every other stream, 24 CTAs (45.4 GB/s) 5 us, 16 CTAs (38.8 GB/s) 2.5 us, <= 8 nothing
+  // (measured on B200: 100 tiny kernels beside a looping host gather).
   unsigned grid = warp_grid(n0, 8);
-  if (only_src == -1) grid = std::min(grid, 48u);
+  if (only_src == -1) grid = std::min(grid, (unsigned)kHostGatherCtas);
   gather_rows_kernel<true, false><<<grid, 256, 0, (cudaStream_t)stream>>>(xrows, src_dev, only_src, nullptr, 0, nullptr, n0,
                                                                          (int)F, out, ld_out);
   GNN_LAUNCH_CHECK();

@@ -387,5 +387,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("host_register", &host_register, "pin+map a host table, returns the device alias", rel());
   m.def("host_unregister", &host_unregister, rel());
   m.def("launch_count", []() { return gnn_launch_count(); });
+  m.def("set_corunner_ctas", [](int ctas) {
+    const int prev = gnn_set_corunner_ctas(ctas);
+    TORCH_CHECK(prev >= 0, "set_corunner_ctas: ", gnn_error_string(prev));
+    return prev;
+  });
+  m.def("host_gather_ctas", []() { return gnn_host_gather_ctas(); });
   m.def("abi_version", []() { return gnn_abi_version(); });
 }

@@ -38,13 +38,38 @@ class PinnedMinibatch:
         return n
 
 
+def reserve_stream_pool(stream: "torch.cuda.Stream", nbytes: int) -> None:
+    """Put one ``nbytes`` block into the caching allocator's pool of ``stream``.
+
+    PyTorch keeps one block pool per stream, and a pool only grows through ``cudaMalloc`` - 1.7-2.9 ms per call for the
+    60-70 MB pieces of a Reddit-shaped minibatch (torch.profiler trace of bench.py's e2e leg), paid by the first
+    dozen minibatches of every side stream until the pool covers the pipeline depth.  With 180 GB of HBM the pool is
+    simply sized up front: the block is allocated and freed here, stays cached for this stream, and later requests
+    split it.  Call once per side stream, before the loop."""
+    if nbytes <= 0:
+        return
+    with torch.cuda.stream(stream):
+        block = torch.empty(int(nbytes), dtype=torch.uint8, device=stream.device)
+        del block
+
+
 class DevicePrefetcher:
-    def __init__(self, store, create_coo_tensor, device, depth: int = 2, prebuild_transpose: bool = False):
+    def __init__(self, store, create_coo_tensor, device, depth: int = 2, prebuild_transpose: bool = False,
+                 reserve_bytes: int = 2 << 30):
         self.store, self.create = store, create_coo_tensor
         self.device = torch.device(device)
         self.depth = depth
         self.prebuild_transpose = prebuild_transpose
+        # two side streams: the feature gather (PCIe-bound on its host rows, ~0.8 ms for a Reddit-shaped minibatch)
+        # and the CSR uploads + adjacency builds are independent, so they run side by side; on one stream the
+        # worker needed 2.1 ms per minibatch and the 1.5 ms training step waited for it
         self.stream = torch.cuda.Stream(device=self.device)
+        self.gather_stream = torch.cuda.Stream(device=self.device)
+        reserve_stream_pool(self.stream, reserve_bytes)
+        reserve_stream_pool(self.gather_stream, reserve_bytes // 2)
+        # the host-row gather of minibatch i+1 is resident for most of step i: tell the SpMM planner to leave its
+        # CTA slots out of the one-wave fit (include/gnn_b200.h, gnn_set_corunner_ctas)
+        self._prev_corunner = store.ext.set_corunner_ctas(store.ext.host_gather_ctas()) if store.host is not None else None
         self._in: "queue.Queue" = queue.Queue()
         self._out: "queue.Queue" = queue.Queue(maxsize=depth)
         self._thread = threading.Thread(target=self._run, daemon=True)
@@ -67,6 +92,14 @@ class DevicePrefetcher:
 
     def _build(self, pm: PinnedMinibatch):
         dev = self.device
+        with torch.cuda.stream(self.gather_stream):
+            nodes = pm.input_nodes.to(dev, non_blocking=True)
+            src_dev, _, xrows, counts = self.store.remap(nodes)
+            buf = torch.empty((nodes.numel(), self.store.ld), dtype=torch.float32, device=dev)
+            self.store.ext.gather_rows_src(xrows, src_dev, -100, self.store.feat_dim, buf)   # HBM / NVLink rows
+            self.store.ext.gather_rows_src(xrows, src_dev, -1, self.store.feat_dim, buf)     # host rows (PCIe)
+            gathered = torch.cuda.Event()
+            gathered.record(self.gather_stream)
         with torch.cuda.stream(self.stream):
             adjs = []
             for layer, t4 in zip(pm.mb.layers, pm.layers):
@@ -75,16 +108,12 @@ class DevicePrefetcher:
                     continue
                 frp, rp, ci, nf = (t.to(dev, non_blocking=True) for t in t4)
                 adjs.append(self.create(frp, rp, ci, nf, layer.nrows, layer.ncols))
-            nodes = pm.input_nodes.to(dev, non_blocking=True)
-            src_dev, _, xrows, counts = self.store.remap(nodes)
-            buf = torch.empty((nodes.numel(), self.store.ld), dtype=torch.float32, device=dev)
-            self.store.ext.gather_rows_src(xrows, src_dev, -100, self.store.feat_dim, buf)   # HBM / NVLink rows
-            self.store.ext.gather_rows_src(xrows, src_dev, -1, self.store.feat_dim, buf)     # host rows (PCIe)
             if self.prebuild_transpose:
                 from .custom_sparse_ops import adjacency_of
                 for a in adjs[1:]:
                     if a is not None:
                         adjacency_of(a).transpose()
+            self.stream.wait_event(gathered)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         return adjs, buf[:, :self.store.feat_dim], counts, ev
@@ -114,3 +143,6 @@ class DevicePrefetcher:
     def close(self):
         self._in.put(None)
         self._thread.join(timeout=10)
+        if self._prev_corunner is not None:
+            self.store.ext.set_corunner_ctas(self._prev_corunner)
+            self._prev_corunner = None

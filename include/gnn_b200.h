@@ -45,6 +45,15 @@ const char *gnn_error_string(int code);
  * (all threads; used by bench.py for its `gpu_launches` claim). */
 int64_t gnn_launch_count(void);
 
+/* Tell the SpMM planner how many CTA slots kernels on OTHER streams hold while it runs (process-wide; default 0;
+ * returns the previous value, GNN_E_BADARG for a negative count).  The SpMM sizes its grid to fill the GPU in exactly
+ * one wave; a long-running CTA of a co-running kernel - the host-row gather of the next minibatch, which the
+ * reference issues next to the step from its sampler threads (sampler.py:135-139, main.py:129-134) - would push one
+ * SpMM CTA into a second wave, so the plan leaves `ctas` slots out.  gnn_host_gather_ctas() is the grid of the
+ * host-row gather (gnn_gather_rows_src_f32 with only_src == -1), i.e. the value a prefetching caller passes. */
+int gnn_set_corunner_ctas(int ctas);
+int gnn_host_gather_ctas(void);
+
 /* ---------------------------------------------------------------------------
  * gnn_build_adj - sampled CSR + LADIES weights -> COO (API) + CSR (kernels).
  *

@@ -44,6 +44,12 @@ def test_abi_version_and_errors(built):
     assert lib.gnn_csr_spmm_f32(None, None, None, -1, 1, 1, 1, None, 1, None, 1, None, 0, None) == -1
     assert lib.gnn_csr_spmm_workspace_bytes(100, 1000, 64) >= 2 * (1000 // 64) * 64 * 4
     assert lib.gnn_csr_transpose_workspace_bytes(64, 10, 5) >= 10 * 2 * 4
+    # planner hint: returns the previous value, rejects negatives, no CUDA call involved
+    g = lib.gnn_host_gather_ctas()
+    assert 1 <= g <= 148
+    assert lib.gnn_set_corunner_ctas(g) == 0
+    assert lib.gnn_set_corunner_ctas(-1) == -1
+    assert lib.gnn_set_corunner_ctas(0) == g
 
 
 def test_extension_keeps_reference_names(built):
