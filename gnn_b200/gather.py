@@ -105,9 +105,32 @@ class FeatureStore:
         _, _, xrows, _ = self.remap(input_nodes)
         return self.ext.gather_rows(xrows, self.feat_dim, self.ld)
 
-    def prefetch(self, input_nodes: torch.Tensor, stream: "torch.cuda.Stream"):
-        """Issue remap + gather for a FUTURE minibatch on ``stream`` (host rows cross PCIe while the current step
-        computes).  Returns (buffer view, event); wait on the event before the first use."""
+    def begin_co_running(self):
+        """Declare that host-row gathers of this store will run on side streams NEXT TO SpMMs (prefetch of the next
+        minibatch): the SpMM planner then keeps the gather's CTA slots out of its one-wave grid
+        (include/gnn_b200.h, gnn_set_corunner_ctas).  Returns a token for :meth:`end_co_running`."""
+        if self.host is None:
+            return None
+        return self.ext.set_corunner_ctas(self.ext.host_gather_ctas())
+
+    def end_co_running(self, token) -> None:
+        if token is not None:
+            self.ext.set_corunner_ctas(token)
+
+    def side_stream(self) -> "torch.cuda.Stream":
+        """The store's own prefetch stream, created once, with its allocator pool sized up front: a fresh stream
+        starts with an empty pool, and the ``cudaMalloc`` calls that fill it were the 20-160 ms stalls seen in
+        training loops that made a new side stream per run (pipeline.reserve_stream_pool)."""
+        if getattr(self, "_side", None) is None:
+            from .pipeline import reserve_stream_pool
+            self._side = torch.cuda.Stream(device=self.device)
+            reserve_stream_pool(self._side, 8 * 4 * self.ld * 32768)      # eight Reddit-sized input blocks
+        return self._side
+
+    def prefetch(self, input_nodes: torch.Tensor, stream: "Optional[torch.cuda.Stream]" = None):
+        """Issue remap + gather for a FUTURE minibatch on ``stream`` (default: :meth:`side_stream`; host rows cross
+        PCIe while the current step computes).  Returns (buffer view, event); wait on the event before the first use."""
+        stream = stream or self.side_stream()
         with torch.cuda.stream(stream):
             src_dev, _, xrows, _ = self.remap(input_nodes)
             buf = torch.empty((input_nodes.numel(), self.ld), dtype=torch.float32, device=self.device)

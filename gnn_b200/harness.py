@@ -109,7 +109,7 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
     comm_bytes = 0
     # input features of minibatch i+1 are gathered on a side stream while minibatch i computes (the reference
     # prefetches whole minibatches in sampler threads; its gather itself is synchronous, main.py:129-137)
-    side = torch.cuda.Stream(device=device)
+    side = store.side_stream()
     pending = {}
 
     def step(i):
@@ -135,6 +135,7 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
         return loss
 
     steps = max(2, min(args.steps, 20))
+    co_token = store.begin_co_running()          # the prefetched host-row gather runs beside the step's SpMMs
     for i in range(3):
         step(i)
     pending.clear()
@@ -156,6 +157,7 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
         dist.barrier()
     wall = time.perf_counter() - t0
     ms = ev0.elapsed_time(ev1)
+    store.end_co_running(co_token)
     if world > 1:
         t = torch.tensor([ms, wall * 1e3], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -179,7 +181,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
     import threading
     from concurrent.futures import ThreadPoolExecutor
     import torch.distributed as dist
-    from . import gpu_sampler, graphgen
+    from . import gpu_sampler, graphgen, pipeline
     torch.manual_seed(1234)
     model = SageNet(shape.feat_dim, nhid, orders, shape.num_classes, cso.spmm, fused=fused).to(device)
     params = [p for p in model.parameters() if p.requires_grad]
@@ -204,6 +206,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         torch.cuda.set_device(device)
         if not hasattr(tls, "stream"):
             tls.stream = torch.cuda.Stream(device=device)
+            pipeline.reserve_stream_pool(tls.stream, 1 << 30)     # no cudaMalloc in the loop (pipeline.py)
             tls.scratch = dg.scratch()
         with torch.cuda.stream(tls.stream):
             mb = gpu_sampler.ladies_sample_device(5000 + 1000 * rank + i, batches[i], [samp] * 5, dg, orders,
@@ -244,6 +247,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         opt.step()
         return loss
 
+    co_token = store.begin_co_running()          # sampler threads gather host rows beside the step's SpMMs
     for _ in range(warm):
         step()
     torch.cuda.synchronize()
@@ -258,6 +262,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         dist.barrier()
     wall = time.perf_counter() - t0
     pool.shutdown(wait=True)
+    store.end_co_running(co_token)
     if world > 1:
         t = torch.tensor([wall], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

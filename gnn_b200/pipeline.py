@@ -69,7 +69,7 @@ class DevicePrefetcher:
         reserve_stream_pool(self.gather_stream, reserve_bytes // 2)
         # the host-row gather of minibatch i+1 is resident for most of step i: tell the SpMM planner to leave its
         # CTA slots out of the one-wave fit (include/gnn_b200.h, gnn_set_corunner_ctas)
-        self._prev_corunner = store.ext.set_corunner_ctas(store.ext.host_gather_ctas()) if store.host is not None else None
+        self._prev_corunner = store.begin_co_running()
         self._in: "queue.Queue" = queue.Queue()
         self._out: "queue.Queue" = queue.Queue(maxsize=depth)
         self._thread = threading.Thread(target=self._run, daemon=True)
@@ -143,6 +143,5 @@ class DevicePrefetcher:
     def close(self):
         self._in.put(None)
         self._thread.join(timeout=10)
-        if self._prev_corunner is not None:
-            self.store.ext.set_corunner_ctas(self._prev_corunner)
-            self._prev_corunner = None
+        self.store.end_co_running(self._prev_corunner)
+        self._prev_corunner = None
