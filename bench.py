@@ -517,7 +517,8 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
             for mb in mbs]
     # the reference uploads CSR pieces and builds adjacencies in sampler threads (sampler.py:135-139); same shape here:
     # one worker thread + side stream prepares minibatch i+1 (H2D, create_coo_tensor, remap, gather) while i computes
-    pre = pipeline.DevicePrefetcher(store, cso.create_coo_tensor, device, depth=2)
+    pre = pipeline.DevicePrefetcher(store, cso.create_coo_tensor, device, depth=2,
+                                    prebuild_transpose=os.environ.get("BENCH_E2E_PREBUILD", "1") == "1")
     src_counts = []
 
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
@@ -596,8 +597,8 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
                           "host_feature_bytes_zero_copy": int(host_rows * F4)},
            "gather_rows_per_step": {"local": int(counts[rank]), "peer": int(peer_rows), "host": int(host_rows)},
            "peer_bytes_per_step": int(peer_rows * F4),
-           "api": "pipeline.DevicePrefetcher (H2D of pinned sampler arrays + custom_sparse_ops.create_coo_tensor + "
-                  "FeatureStore remap/gather on a worker thread and side stream) + custom_sparse_ops.spmm (autograd) + loss.item()",
+           "api": "pipeline.DevicePrefetcher (H2D of pinned sampler arrays + custom_sparse_ops.create_coo_tensor + A^T index + "
+                  "FeatureStore remap/gather on a worker thread and two side streams) + custom_sparse_ops.spmm (autograd) + loss read",
            "pipelining": "inputs of minibatch i+1 are copied/gathered while minibatch i computes and the loss of minibatch i is read (pinned D2H) after i+1 is launched; every copy and read is inside the timed region"}
     # gather alone, for the NVLink / PCIe roofs
     nodes = host_mbs[0].input_nodes.to(device)
