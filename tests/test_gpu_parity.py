@@ -408,3 +408,54 @@ def test_spmm_and_transpose_randomised_shapes(cu):
             o_rowptr, o_col, perm = oracle.csr_transpose(rowptr, cols, M, K)
             assert np.array_equal(t_rowptr.cpu().numpy(), o_rowptr) and np.array_equal(t_col.cpu().numpy(), o_col)
             assert np.array_equal(t_vals.cpu().numpy(), vals[perm])
+
+
+def test_corunner_reserve_changes_the_grid_not_the_result(cu):
+    """gnn_set_corunner_ctas only changes how many chunks the planner cuts (include/gnn_b200.h): every setting stays
+    within the fp32 bar of the oracle, repeats bit-identically, and the setter returns the previous value."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    M, K, D = 6000, 9000, 256
+    lens = np.minimum(rng.poisson(180, M), K)
+    lens[17] = 5000                                                        # a hub row spanning many chunks
+    rowptr, cols, vals = _random_csr(rng, M, K, lens)
+    X = rng.standard_normal((K, D)).astype(np.float32)
+    ref = oracle.spmm_f64acc(rowptr, cols, vals, M, X)
+    d = [cu.dev(a) for a in (rowptr, cols, vals, X)]
+    from gnn_b200 import _native
+    lib = _native.cabi()
+    assert lib.gnn_set_corunner_ctas(0) >= 0
+    try:
+        outs = {}
+        for reserve in (0, 16, 64, 10 ** 6):                               # the last one leaves a single CTA slot
+            prev = lib.gnn_set_corunner_ctas(reserve)
+            assert prev >= 0
+            y1 = cu.csr_spmm(d[0], d[1], d[2], M, K, d[3]).cpu().numpy()
+            y2 = cu.csr_spmm(d[0], d[1], d[2], M, K, d[3]).cpu().numpy()
+            assert np.array_equal(y1.view(np.uint32), y2.view(np.uint32)), reserve
+            assert oracle.rel_err(y1, ref)[0] <= TOL, reserve
+            outs[reserve] = y1
+        assert lib.gnn_set_corunner_ctas(0) == 10 ** 6
+    finally:
+        lib.gnn_set_corunner_ctas(0)
+
+
+def test_build_adj_hub_rows_and_chunk_boundaries(cu):
+    """build_adj walks the entries in 256-entry chunks: rows far longer than a chunk, empty rows between them and a
+    last partial chunk must still give the reference's (row, col, value) triples bit for bit."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    M, K = 700, 30000
+    lens = rng.integers(0, 4, M)
+    lens[[3, 4, 350, 699]] = [4000, 257, 9000, 1]
+    lens[5:40] = 0
+    rowptr, cols, _ = _random_csr(rng, M, K, lens)
+    full_lens = lens + rng.integers(1, 50, M)                                # full-graph degree >= sampled degree
+    fullrowptr = np.zeros(M + 1, dtype=np.int32)
+    np.cumsum(full_lens, out=fullrowptr[1:])
+    normfact = (1.0 / rng.uniform(1e-3, 1.0, K)).astype(np.float32)
+    for colt in (np.int16, np.int32):
+        c = cols.astype(colt)
+        idx, v, c32 = cu.build_adj(cu.dev(fullrowptr), cu.dev(rowptr), cu.dev(c), cu.dev(normfact), M, K)
+        rows_o, cols_o, vals_o = oracle.build_adj(fullrowptr, rowptr, c, normfact, M)
+        assert np.array_equal(idx.cpu().numpy(), np.stack([rows_o, cols_o]))
+        assert np.array_equal(v.cpu().numpy().view(np.uint32), vals_o.view(np.uint32))
+        assert np.array_equal(c32.cpu().numpy(), cols_o.astype(np.int32))
