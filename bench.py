@@ -375,6 +375,20 @@ def main():
         total_ms_max, total_bytes_all = total_ms, total_bytes
     value = total_bytes_all / (total_ms_max * 1e-3) / 1e9
 
+    # ---- companion number: the same K steps WITHOUT the flush, one minibatch repeated - in training X
+    # was just produced and A just built, so the operands of a step are partly L2-resident.  Not the headline.
+    wev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    for _ in range(2):
+        run_step(0)
+    wev[0].record()
+    for s in range(args.steps):
+        run_step(0)
+    wev[1].record()
+    torch.cuda.synchronize()
+    warm_ms = wev[0].elapsed_time(wev[1]) / args.steps
+    warm_l2 = {"value": round(step_bytes[0] / (warm_ms * 1e-3) / 1e9, 2), "unit": "GB/s per GPU", "ms_per_step": round(warm_ms, 4),
+               "note": "no L2 flush, one minibatch repeated back to back (rank 0's figure)"}
+
     # ---- per-op table + roofline of the dominant launch
     peaks = {}
     try:
@@ -430,9 +444,13 @@ def main():
         # reference-shaped model first (the reference's own models.py would run exactly these torch ops), then the
         # same model with the fused ELU+row-norm epilogue of gnn_b200/models.py
         train = harness.bench_train(args, cso, store, shape, g, mbs, ORDERS, NHID, device, rank, world, log)
+        # sampler threads per GPU: the reference's default --pool_num is 4 (main.py:77); with the host cores to spare
+        # (>= 2 per thread and rank) the second live number uses 8, since 4 threads x 26 ms per minibatch is sampler-bound
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
+        pool_wide = 8 if cores // max(world, 1) >= 16 else 4
         for key, fn, kw in [("fused_epilogue_model", harness.bench_train, dict(fused=True)),
-                            ("live_sampler", harness.bench_train_live, dict(fused=False)),
-                            ("live_sampler_fused_epilogue", harness.bench_train_live, dict(fused=True))]:
+                            ("live_sampler", harness.bench_train_live, dict(fused=False, pool_num=4)),
+                            ("live_sampler_fused_epilogue", harness.bench_train_live, dict(fused=True, pool_num=pool_wide))]:
             try:
                 if fn is harness.bench_train:
                     train[key] = fn(args, cso, store, shape, g, mbs, ORDERS, NHID, device, rank, world, log, **kw)
@@ -465,7 +483,7 @@ def main():
                        "sharding": "each rank its own minibatches, no data-path collective in `value`",
                        "bwd_includes": "CSR-of-A^T build (gnn_csr_transpose) every step"},
             "wall_ms_per_step_incl_flush": round(wall / args.steps * 1e3, 4),
-            "gpu_launches": int(launches), "clocks": clk, "ops": ops, "roofline": roofline,
+            "gpu_launches": int(launches), "clocks": clk, "ops": ops, "warm_l2": warm_l2, "roofline": roofline,
             "e2e": e2e, "train": train, "cpu_baseline": cpu_baseline,
         }
         if ref_gpu is not None:
