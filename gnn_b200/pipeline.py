@@ -60,9 +60,9 @@ class DevicePrefetcher:
         self.device = torch.device(device)
         self.depth = depth
         self.prebuild_transpose = prebuild_transpose
-        # two side streams: the feature gather (PCIe-bound on its host rows, ~0.8 ms for a Reddit-shaped minibatch)
-        # and the CSR uploads + adjacency builds are independent, so they run side by side; on one stream the
-        # worker needed 2.1 ms per minibatch and the 1.5 ms training step waited for it
+        # two side streams: the feature gather (PCIe-bound on its host rows, ~1 ms for a Reddit-shaped minibatch) and
+        # the CSR uploads + adjacency builds are independent, so they run side by side instead of queueing behind each
+        # other (e2e step 2.13 -> 2.02 ms when this was the only change; DESIGN.md 8a has the rest)
         self.stream = torch.cuda.Stream(device=self.device)
         self.gather_stream = torch.cuda.Stream(device=self.device)
         reserve_stream_pool(self.stream, reserve_bytes)
