@@ -94,8 +94,8 @@ struct XSrc {
 
 // nonzeros kept in flight per warp step (U) and CTAs per SM asked of ptxas (MINB), by vectors per lane
 // (tuned on B200 over the Reddit-shaped blocks with wave fitting active, profiles/tune_r1.txt)
-constexpr int default_u(int nv) { return nv >= 5 ? 1 : (nv == 4 ? 2 : (nv >= 2 ? 4 : 8)); }
-constexpr int default_minb(int nv) { return (nv == 3 || nv == 4) ? 3 : (nv >= 6 ? 2 : 4); }
+[[maybe_unused]] constexpr int default_u(int nv) { return nv >= 5 ? 1 : (nv == 4 ? 2 : (nv >= 2 ? 4 : 8)); }
+[[maybe_unused]] constexpr int default_minb(int nv) { return (nv == 3 || nv == 4) ? 3 : (nv >= 6 ? 2 : 4); }
 
 // Dload = floats readable per X row (D, or D rounded up to 4 when rows are padded to 16 bytes)
 template <int VEC, int NV, int LPR, bool GATHER, int U>
