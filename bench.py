@@ -540,7 +540,7 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
     src_counts = []
 
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
-    losses = []
+    losses, waits, syncs = [], [], []
     defer = os.environ.get("BENCH_E2E_DEFER", "1") == "1"
     if os.environ.get("BENCH_SWITCH"):
         sys.setswitchinterval(float(os.environ["BENCH_SWITCH"]))
@@ -548,7 +548,9 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
     def step(i, prev_ready):
         """Launch minibatch i, then read the loss of minibatch i-1 (one D2H read per step, one step late, so the
         GPU is never idle while the host launches the next step)."""
+        t_a = time.perf_counter()
         adjs, x0, counts = pre.get()
+        waits.append((time.perf_counter() - t_a) * 1e3)
         loss = cso.spmm(adjs[0], x0).sum()
         for li in range(1, nl):
             h = acts[i % len(mbs)][li - 1]
@@ -559,7 +561,9 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
             losses.append(float(loss.item()))
             return None, counts
         if prev_ready is not None:
+            t_a = time.perf_counter()
             prev_ready.synchronize()
+            syncs.append((time.perf_counter() - t_a) * 1e3)
             losses.append(float(loss_host[0]))
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         ready = torch.cuda.Event()
@@ -576,6 +580,11 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
         ready.synchronize()
     torch.cuda.synchronize()                  # the pipeline is EMPTY here: nothing of the timed steps has been copied yet
     losses.clear()
+    waits.clear()
+    syncs.clear()
+    import gc
+    gc.collect()
+    gc.disable()            # a full collection of a torch process takes 5-12 ms: two of them landed in 20 timed steps
     if world > 1:
         dist.barrier()
     ready = None
@@ -594,9 +603,12 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
     if world > 1:
         dist.barrier()
     dt = time.perf_counter() - t0
+    gc.enable()
     pre.close()
     log("e2e host-side step intervals (ms): " + " ".join(f"{(b - a) * 1e3:.2f}" for a, b in zip([t0] + marks, marks))
         + f" | drain {(t0 + dt - marks[-1]) * 1e3:.2f}")
+    log("e2e wait for the prefetcher (ms): " + " ".join(f"{w:.2f}" for w in waits))
+    log("e2e wait for the previous loss (ms): " + " ".join(f"{w:.2f}" for w in syncs))
     assert len(losses) >= args.steps and all(np.isfinite(losses)), "every step's loss must have been read on the host"
     counts = torch.stack(src_counts).double().mean(0).cpu().numpy()      # rows per source per step
     bytes_all = float(sum(step_bytes[(nwarm + s) % len(mbs)] for s in range(args.steps)))

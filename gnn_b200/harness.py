@@ -15,6 +15,7 @@ here with the same math, only to drive the hot path in its real calling pattern:
 """
 from __future__ import annotations
 
+import gc
 import time
 
 import numpy as np
@@ -142,6 +143,8 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
     torch.cuda.synchronize()
 
     torch.cuda.synchronize()
+    gc.collect()
+    gc.disable()              # a full collection of a torch process takes 5-12 ms; training scripts freeze/disable it too
     if world > 1:
         dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -156,6 +159,7 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - t0
+    gc.enable()
     ms = ev0.elapsed_time(ev1)
     store.end_co_running(co_token)
     if world > 1:
@@ -251,6 +255,8 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
     for _ in range(warm):
         step()
     torch.cuda.synchronize()
+    gc.collect()
+    gc.disable()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
@@ -261,6 +267,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - t0
+    gc.enable()
     pool.shutdown(wait=True)
     store.end_co_running(co_token)
     if world > 1:
