@@ -588,6 +588,8 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
     if world > 1:
         dist.barrier()
     ready = None
+    mallocs0 = torch.cuda.memory_stats(device).get("num_device_alloc", 0)
+    seg0 = {k: torch.cuda.memory_stats(device).get(f"segment.{k}.allocated", 0) for k in ("small_pool", "large_pool")}
     t0 = time.perf_counter()
     for s in range(args.steps):               # the sampler side hands over K host minibatches; every H2D copy, build and
         pre.submit(host_mbs[(nwarm + s) % len(mbs)])     # gather of the K timed steps happens after t0 (pipeline fill included)
@@ -604,6 +606,9 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
         dist.barrier()
     dt = time.perf_counter() - t0
     gc.enable()
+    mallocs = torch.cuda.memory_stats(device).get("num_device_alloc", 0) - mallocs0
+    log("e2e cudaMalloc in the timed region: %d (%s)" % (mallocs, ", ".join(
+        f"{k} +{torch.cuda.memory_stats(device).get(f'segment.{k}.allocated', 0) - v}" for k, v in seg0.items())))
     pre.close()
     log("e2e host-side step intervals (ms): " + " ".join(f"{(b - a) * 1e3:.2f}" for a, b in zip([t0] + marks, marks))
         + f" | drain {(t0 + dt - marks[-1]) * 1e3:.2f}")
@@ -628,7 +633,7 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
            "h2d_detail": {"sampler_csr_bytes": int(csr_bytes), "host_feature_rows": int(host_rows),
                           "host_feature_bytes_zero_copy": int(host_rows * F4)},
            "gather_rows_per_step": {"local": int(counts[rank]), "peer": int(peer_rows), "host": int(host_rows)},
-           "peer_bytes_per_step": int(peer_rows * F4),
+           "peer_bytes_per_step": int(peer_rows * F4), "cuda_mallocs_in_timed_region": int(mallocs),
            "api": "pipeline.DevicePrefetcher (H2D of pinned sampler arrays + custom_sparse_ops.create_coo_tensor + A^T index + "
                   "FeatureStore remap/gather on a worker thread and two side streams) + custom_sparse_ops.spmm (autograd) + loss read",
            "pipelining": "the pipeline is empty when the clock starts (the K host minibatches are handed over at t0, so the fill is timed); inputs of minibatch i+1 are copied/built/gathered while minibatch i computes and the loss of minibatch i is read (pinned D2H) after i+1 is launched; every copy and read of the K steps is inside the timed region"}

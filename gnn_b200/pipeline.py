@@ -38,24 +38,29 @@ class PinnedMinibatch:
         return n
 
 
-def reserve_stream_pool(stream: "torch.cuda.Stream", nbytes: int) -> None:
+def reserve_stream_pool(stream: "torch.cuda.Stream", nbytes: int, small_blocks: int = 64) -> None:
     """Put one ``nbytes`` block into the caching allocator's pool of ``stream``.
 
     PyTorch keeps one block pool per stream, and a pool only grows through ``cudaMalloc`` - 1.7-2.9 ms per call for the
     60-70 MB pieces of a Reddit-shaped minibatch (torch.profiler trace of bench.py's e2e leg), paid by the first
     dozen minibatches of every side stream until the pool covers the pipeline depth.  With 180 GB of HBM the pool is
     simply sized up front: the block is allocated and freed here, stays cached for this stream, and later requests
-    split it.  Call once per side stream, before the loop."""
+    split it.  Call once per side stream, before the loop.  Size it generously (DevicePrefetcher: 8 GiB for ~0.2 GB
+    minibatches): blocks handed to another stream come back only after that stream's recorded events completed, so
+    several minibatches beyond the queue depth are outstanding, and ONE late ``cudaMalloc`` on a side stream stalls
+    the launches of every other thread for its duration (87 ms observed with a 2 GiB pool)."""
     if nbytes <= 0:
         return
     with torch.cuda.stream(stream):
         block = torch.empty(int(nbytes), dtype=torch.uint8, device=stream.device)
-        del block
+        # requests up to 1 MiB (index arrays, counters) are served from a separate pool of 2 MiB segments
+        small = [torch.empty((1 << 20) - 512, dtype=torch.uint8, device=stream.device) for _ in range(small_blocks)]
+        del block, small
 
 
 class DevicePrefetcher:
     def __init__(self, store, create_coo_tensor, device, depth: int = 2, prebuild_transpose: bool = False,
-                 reserve_bytes: int = 2 << 30):
+                 reserve_bytes: int = 8 << 30):
         self.store, self.create = store, create_coo_tensor
         self.device = torch.device(device)
         self.depth = depth
@@ -66,7 +71,7 @@ class DevicePrefetcher:
         self.stream = torch.cuda.Stream(device=self.device)
         self.gather_stream = torch.cuda.Stream(device=self.device)
         reserve_stream_pool(self.stream, reserve_bytes)
-        reserve_stream_pool(self.gather_stream, reserve_bytes // 2)
+        reserve_stream_pool(self.gather_stream, reserve_bytes // 4)
         # the host-row gather of minibatch i+1 is resident for most of step i: tell the SpMM planner to leave its
         # CTA slots out of the one-wave fit (include/gnn_b200.h, gnn_set_corunner_ctas)
         self._prev_corunner = store.begin_co_running()
