@@ -7,7 +7,6 @@ import numpy as np
 import pytest
 import torch
 
-import oracle
 from gnn_b200 import graphgen, sampler
 
 pytestmark = pytest.mark.gpu

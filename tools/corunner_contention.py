@@ -4,10 +4,9 @@ Main stream: the five SpMMs of one Reddit-shaped minibatch / 100 tiny kernels / 
 Side stream: nothing / a looping host-row gather (zero-copy PCIe reads) / device-row gathers / H2D DMA copies.
 CORUN=<n> sets gnn_set_corunner_ctas(n) first.   usage: CORUN=16 python tools/corunner_contention.py
 """
-import sys, os, json; sys.path.insert(0, '.')
-import numpy as np
+import sys, os; sys.path.insert(0, '.')
 import torch, bench, custom_sparse_ops as cso
-from gnn_b200 import gather as gmod, pipeline
+from gnn_b200 import gather as gmod
 class A: pass
 args = A(); args.workload='reddit'; args.minibatches=3; args.buffer_size=0.1; args.steps=12; args.warmup=3
 log = lambda m: None

@@ -1,6 +1,5 @@
 """torch.profiler (CUPTI) timeline of bench.py's e2e leg -> gpurun_out/e2e_trace.json; summarise with tools/e2e_timeline_summary.py"""
-import sys, os, json; sys.path.insert(0, '.')
-import numpy as np
+import sys, os; sys.path.insert(0, '.')
 import torch, bench, custom_sparse_ops as cso
 from gnn_b200 import gather as gmod
 from torch.profiler import profile, ProfilerActivity
