@@ -51,6 +51,8 @@ def reserve_stream_pool(stream: "torch.cuda.Stream", nbytes: int, small_blocks: 
     the launches of every other thread for its duration (87 ms observed with a 2 GiB pool)."""
     if nbytes <= 0:
         return
+    free, _ = torch.cuda.mem_get_info(stream.device)
+    nbytes = min(int(nbytes), free // 4)            # never more than a quarter of what is free right now
     with torch.cuda.stream(stream):
         block = torch.empty(int(nbytes), dtype=torch.uint8, device=stream.device)
         # requests up to 1 MiB (index arrays, counters) are served from a separate pool of 2 MiB segments
