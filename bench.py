@@ -12,7 +12,10 @@ prints ONE JSON line on rank 0.
             in HBM, CUDA-event time of the steps, max over ranks; L2 flushed between steps.
   e2e       same metric through the public API with HOST inputs: pinned sampler CSR arrays -> H2D ->
             create_coo_tensor, placement remap + feature gather (local shard / peer shards over NVLink /
-            mapped pinned host), spmm forward + autograd backward, D2H of the loss.
+            mapped pinned host), spmm forward + autograd backward, D2H of the loss.  The hand-off runs in
+            pipeline.DevicePrefetcher (worker thread, two side streams); the pipeline is EMPTY when the clock
+            starts, so every copy/build/gather of the K timed steps is inside the timed region.
+  warm_l2   companion of `value` without the L2 flush.
   roofline  dominant kernel (the forward/backward row-split SpMM launch with the largest share).
   cpu_baseline / --impl reference
             the reference's CPU path, torch.sparse COO mm (reference custom_sparse_ops.py:25,36), on a
