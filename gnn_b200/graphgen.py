@@ -212,6 +212,10 @@ def labels(shape: GraphShape | str, seed: int = 3) -> np.ndarray:
 def cache_path(shape: GraphShape, seed: int, root: str | None = None) -> str:
     root = root or os.environ.get("GNN_B200_CACHE", "/tmp/gnn_b200_cache")
     tag = hashlib.sha1(repr((dataclasses.astuple(shape), seed)).encode()).hexdigest()[:12]
+    # graphs above ~64 MB (Reddit-shaped: 460 MB) go to a sub-directory that .gpurunignore lists, so a cache written
+    # by a local run never rides along in the repository snapshot; ranks of one box still share it
+    if shape.num_undirected_edges * 8 > (64 << 20):
+        root = os.path.join(root, "big")
     return os.path.join(root, f"graph_{shape.name}_{tag}.npz")
 
 
