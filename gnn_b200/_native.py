@@ -52,13 +52,20 @@ def cabi() -> ctypes.CDLL:
                 "gnn_launch_count": (i64, []),
                 "gnn_set_corunner_ctas": (ctypes.c_int, [ctypes.c_int]),
                 "gnn_host_gather_ctas": (ctypes.c_int, []),
-                "gnn_build_adj": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, vp, i64, i64, i64, vp, vp, vp, vp]),
+                "gnn_build_adj": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, vp, i64, i64, i64, vp, vp, vp, vp, vp]),
                 "gnn_coo_to_csr": (ctypes.c_int, [vp, i64, i64, vp, vp, vp]),
                 "gnn_csr_spmm_workspace_bytes": (sz, [i64, i64, i64]),
                 "gnn_csr_spmm_f32": (ctypes.c_int, [vp, vp, vp, i64, i64, i64, i64, vp, i64, vp, i64, vp, sz, vp]),
                 "gnn_gather_spmm_f32": (ctypes.c_int, [vp, vp, vp, i64, i64, i64, i64, vp, vp, i64, vp, sz, vp]),
+                "gnn_csr_spmm_counter_bytes": (sz, [i64, i64, i64]),
+                "gnn_csr_spmm_partial_bytes": (sz, [i64, i64, i64]),
+                "gnn_csr_spmm_f32_ex": (ctypes.c_int, [vp, vp, vp, vp, i64, i64, i64, i64, vp, i64, vp, i64, vp, vp, sz, ctypes.c_uint, vp]),
+                "gnn_gather_spmm_f32_ex": (ctypes.c_int, [vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, i64, vp, vp, sz, ctypes.c_uint, vp]),
+                "gnn_csr_spmm_t_f32": (ctypes.c_int, [vp, vp, vp, vp, i64, i64, i64, i64, vp, i64, vp, i64, vp]),
+                "gnn_set_transpose_budget": (i64, [i64]),
+                "gnn_probe_row_gather_f32": (ctypes.c_int, [vp, i64, i64, vp, i64, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(i64), vp]),
                 "gnn_csr_transpose_workspace_bytes": (sz, [i64, i64, i64]),
-                "gnn_csr_transpose": (ctypes.c_int, [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, sz, vp]),
+                "gnn_csr_transpose": (ctypes.c_int, [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, sz, vp]),
                 "gnn_placement_remap": (ctypes.c_int, [vp, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp]),
                 "gnn_gather_rows_f32": (ctypes.c_int, [vp, i64, i64, vp, i64, vp]),
                 "gnn_gather_rows_src_f32": (ctypes.c_int, [vp, vp, i32, i64, i64, vp, i64, vp]),

@@ -22,7 +22,7 @@ CSRC = os.path.join(HERE, "csrc")
 INC = os.path.join(REPO, "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic", "--use_fast_math=false"]
 
 
 def _newer(target: str, deps) -> bool:
@@ -43,10 +43,11 @@ def build_kernels(verbose: bool = False, force: bool = False) -> str:
     out = os.path.join(LIB, "libgnn_b200.so")
     src = os.path.join(CSRC, "gnn_kernels.cu")
     hdr = os.path.join(INC, "gnn_b200.h")
-    if force or _newer(out, [src, hdr]):
+    deps = [src, hdr] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    if force or _newer(out, deps):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-        _run([nvcc, *flags, "-I", INC, "-o", out + ".tmp", src], verbose)
+        _run([nvcc, *flags, "-I", INC, "-I", CSRC, "-o", out + ".tmp", src], verbose)
         os.replace(out + ".tmp", out)
     return out
 

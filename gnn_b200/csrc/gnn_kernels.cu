@@ -65,6 +65,8 @@ __device__ __forceinline__ void ldg_vec(const float *p, float (&x)[VEC]) {
   }
 }
 
+#include "chunk_rows.cuh"
+
 // ---------------------------------------------------------------------------
 // Row-split CSR SpMM
 //
@@ -204,6 +206,7 @@ __device__ __forceinline__ void zero_row(float *row, bool vec_ok, int lane, int 
 
 struct SpmmParams {
   const int *rowptr;
+  const int *rowidx;   // row id per stored entry (optional, flat kernel only)
   const int *colidx;
   const float *vals;
   int M;
@@ -218,7 +221,11 @@ struct SpmmParams {
   int *counters;     // [M*nslabs], zero on entry
   int Dp;
   int Dload;         // floats readable per X row (>= D)
+  int cshift;        // log2(C) (flat kernel: C is a power of two)
 };
+
+#include "spmm_flat.cuh"
+#include "spmm_scatter_t.cuh"
 
 template <int VEC, int NV, int LPR, bool GATHER, int U, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
@@ -237,18 +244,8 @@ spmm_rowsplit_kernel(const SpmmParams p, const XSrc<GATHER> xs) {
   int s = chunk * p.C;
   const int e = min(s + p.C, p.nnz);
 
-  // first row with rowptr[r+1] > s: warp-wide 32-ary search (3 dependent loads for M <= 32 K instead of 15).
-  // rowptr is non-decreasing and rowptr[M] == nnz > s, so the predicate is monotone and true at hi.
-  int lo = 0, hi = p.M - 1;
-  while (hi > lo) {
-    const int step = (hi - lo + 32) >> 5;
-    const int probe = min(lo + (lane + 1) * step - 1, hi);
-    const unsigned m = __ballot_sync(kFull, __ldg(p.rowptr + probe + 1) > s);
-    const int first = __ffs(m) - 1;
-    const int nhi = min(lo + (first + 1) * step - 1, hi);
-    lo += first * step;
-    hi = nhi;
-  }
+  // first row with rowptr[r+1] > s: warp-wide 32-ary search (3 dependent loads for M <= 32 K instead of 15)
+  const int lo = warp_first_row(p.rowptr, p.M, s, lane);
   int r = lo;
   if (chunk == 0) {  // leading empty rows
     for (int z = 0; z < r; ++z) zero_row<VEC, NV, LPR>(p.Y + (int64_t)z * p.ldy, y_vec_ok, lane, col0, p.D);
@@ -275,7 +272,10 @@ spmm_rowsplit_kernel(const SpmmParams p, const XSrc<GATHER> xs) {
       __threadfence();
       __syncwarp();
       int last = 0;
-      if (lane == 0) last = (atomicAdd(p.counters + (int64_t)r * p.nslabs + slab, 1) == c_last - c_first);
+      // atomicInc wraps to 0 on the last arrival: counters that are zero on entry are zero again on exit
+      if (lane == 0)
+        last = (atomicInc(reinterpret_cast<unsigned *>(p.counters) + (int64_t)r * p.nslabs + slab, (unsigned)(c_last - c_first)) ==
+                (unsigned)(c_last - c_first));
       last = __shfl_sync(kFull, last, 0);
       if (last) {
         __threadfence();
@@ -321,17 +321,63 @@ inline int spmm_chunk(int64_t nnz, int64_t D) {
   return c;
 }
 
-struct SpmmPlan { int vec, nv, lpr, nslabs, C, nchunks, Dp; };
+// Which kernel: the flat (nonzero-split) kernel for short-row or small blocks - top LADIES layer, the transpose of
+// any sparse layer, papers100M-shaped blocks - where the per-row dependent loads of the row-split kernel, not
+// bandwidth, are the run time; the row-split kernel (longer register-resident row segments, fewer shared-memory
+// trips per nonzero) for the dense LADIES blocks.  A function of (M, nnz, D) only: the workspace query must agree.
+constexpr int64_t kFlatMaxNnz = 4 << 20;
+constexpr int64_t kFlatMeanRow = 96;
+constexpr int64_t kFlatTargetItems = 8192;
+
+inline bool flat_wanted(int64_t M, int64_t nnz, int64_t D) {
+  (void)D;
+#ifdef GNN_TUNE
+  if (getenv("GNN_TUNE_FLAT")) return atoi(getenv("GNN_TUNE_FLAT")) != 0;
+#endif
+  return nnz <= kFlatMaxNnz && nnz < kFlatMeanRow * std::max<int64_t>(M, 1);
+}
+
+// flat chunk: 128 entries per warp item, halved (down to 32) while the grid would stay under ~2 waves of warps
+inline int flat_chunk(int64_t nnz, int64_t D) {
+#ifdef GNN_TUNE
+  if (getenv("GNN_TUNE_FC")) return atoi(getenv("GNN_TUNE_FC"));
+#endif
+  const int64_t slabs = cdiv(D, 128);
+  int c = kFlatMaxC;
+  while (c > 32 && cdiv(nnz, c) * slabs < kFlatTargetItems) c >>= 1;
+  return c;
+}
+
+struct SpmmPlan { int kind, vec, nv, lpr, nslabs, C, nchunks, Dp, u; };   // kind: 0 row-split, 1 flat
 
 constexpr int64_t kTargetItems = 3072;   // warp items (~2/3 of a wave) wanted before wider slabs are preferred
 
-inline SpmmPlan make_plan(int64_t nnz, int64_t D, int vec) {
+inline SpmmPlan make_plan(int64_t M, int64_t nnz, int64_t D, int vec) {
   SpmmPlan pl;
   pl.vec = vec;
+  pl.Dp = (int)(cdiv(D, 4) * 4);
+  pl.u = 0;
+  const int64_t nvec = cdiv(D, vec);               // vectors per row
+  if (flat_wanted(M, nnz, D)) {
+    pl.kind = 1;
+    pl.lpr = 32;
+    pl.C = flat_chunk(nnz, D);
+    pl.nchunks = (int)cdiv(nnz, pl.C);
+    const int64_t n = cdiv(nvec, 32);              // vector columns per lane
+    pl.nv = 1;
+    for (int nv : {4, 2})                          // wider slabs (fewer passes over the index stream) once the grid is large
+      if (nv <= n && (int64_t)pl.nchunks * cdiv(n, nv) >= 2 * kFlatTargetItems) { pl.nv = nv; break; }
+    pl.u = pl.nv == 1 ? 16 : (pl.nv == 2 ? 8 : 4);
+#ifdef GNN_TUNE
+    if (getenv("GNN_TUNE_FNV")) pl.nv = atoi(getenv("GNN_TUNE_FNV"));
+    if (getenv("GNN_TUNE_FU")) pl.u = atoi(getenv("GNN_TUNE_FU"));
+#endif
+    pl.nslabs = (int)cdiv(n, pl.nv);
+    return pl;
+  }
+  pl.kind = 0;
   pl.C = spmm_chunk(nnz, D);
   pl.nchunks = (int)cdiv(nnz, pl.C);
-  pl.Dp = (int)(cdiv(D, 4) * 4);
-  const int64_t nvec = cdiv(D, vec);               // vectors per row
   if (vec == 4 && nvec <= 16) {                    // narrow rows: several nonzeros per warp step
     pl.lpr = nvec <= 4 ? 4 : (nvec <= 8 ? 8 : 16);
     pl.nv = 1;
@@ -462,8 +508,29 @@ inline int launch_tune(const SpmmPlan &pl, const SpmmParams &p, const XSrc<false
 }
 #endif
 
+template <int VEC, int NV, bool GATHER, int U>
+int launch_flat_t(const SpmmParams &p, const XSrc<GATHER> &xs, cudaStream_t st) {
+  const int64_t items = (int64_t)p.nchunks * p.nslabs;
+  const unsigned grid = (unsigned)cdiv(items, kFlatWarps);
+  if (p.rowidx) spmm_flat_kernel<VEC, NV, GATHER, U, true><<<grid, kFlatWarps * 32, 0, st>>>(p, xs);
+  else spmm_flat_kernel<VEC, NV, GATHER, U, false><<<grid, kFlatWarps * 32, 0, st>>>(p, xs);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int VEC, bool GATHER>
+int launch_flat(const SpmmPlan &pl, const SpmmParams &p, const XSrc<GATHER> &xs, cudaStream_t st) {
+  switch (pl.nv) {
+    case 1: return pl.u >= 16 ? launch_flat_t<VEC, 1, GATHER, 16>(p, xs, st) : launch_flat_t<VEC, 1, GATHER, 8>(p, xs, st);
+    case 2: return launch_flat_t<VEC, 2, GATHER, 8>(p, xs, st);
+    case 4: return launch_flat_t<VEC, 4, GATHER, 4>(p, xs, st);
+    default: return GNN_E_BADARG;
+  }
+}
+
 template <int VEC, bool GATHER>
 int launch_spmm_nv(const SpmmPlan &pl, const SpmmParams &p, const XSrc<GATHER> &xs, cudaStream_t st) {
+  if (pl.kind == 1) return launch_flat<VEC, GATHER>(pl, p, xs, st);
 #ifdef GNN_TUNE
   if constexpr (VEC == 4 && !GATHER) {
     if (pl.lpr == 32 && getenv("GNN_TUNE_U")) return launch_tune(pl, p, xs, st);
@@ -496,10 +563,11 @@ __global__ void zero_rows_kernel(float *Y, int64_t ldy, int64_t M, int64_t D) {
 }
 
 template <bool GATHER>
-int spmm_entry(const int32_t *rowptr, const int32_t *colidx, const float *vals, int64_t M, int64_t K, int64_t nnz,
+int spmm_entry(const int32_t *rowptr, const int32_t *rowidx, const int32_t *colidx, const float *vals, int64_t M, int64_t K, int64_t nnz,
                int64_t D, const float *X, int64_t ldx, const float *const *xrows, float *Y, int64_t ldy,
-               void *workspace, size_t workspace_bytes, cudaStream_t st) {
+               int *counters, void *partials, size_t partial_bytes, unsigned flags, cudaStream_t st) {
   if (M < 0 || K < 0 || nnz < 0 || D < 0) return GNN_E_BADARG;
+  if (flags & ~(unsigned)GNN_SPMM_COUNTERS_ZEROED) return GNN_E_BADARG;
   if (M == 0 || D == 0) return 0;
   if (!Y || ldy < D) return GNN_E_BADARG;
   if (M >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 2048 || K >= (1ll << 31) || D >= (1ll << 24) || ldx >= (1ll << 31)) return GNN_E_RANGE;
@@ -522,19 +590,21 @@ int spmm_entry(const int32_t *rowptr, const int32_t *colidx, const float *vals, 
     if ((a & 15) == 0 && (D % 4 == 0 || ldx >= D4)) { vec = 4; Dload = D4; }
     else if ((a & 7) == 0 && (D % 2 == 0 || ldx >= D + 1)) { vec = 2; Dload = cdiv(D, 2) * 2; }
   }
-  const SpmmPlan pl = make_plan(nnz, D, vec);
-  const size_t need = gnn_csr_spmm_workspace_bytes(M, nnz, D);
-  if (!workspace || workspace_bytes < need) return GNN_E_WORKSPACE;
+  const SpmmPlan pl = make_plan(M, nnz, D, vec);
+  if (!counters || !partials || partial_bytes < gnn_csr_spmm_partial_bytes(M, nnz, D)) return GNN_E_WORKSPACE;
 
   SpmmParams p;
-  p.rowptr = rowptr; p.colidx = colidx; p.vals = vals;
+  p.rowptr = rowptr; p.rowidx = rowidx; p.colidx = colidx; p.vals = vals;
   p.M = (int)M; p.nnz = (int)nnz; p.D = (int)D;
   p.C = pl.C; p.nchunks = pl.nchunks; p.nslabs = pl.nslabs; p.Dp = pl.Dp;
   p.Y = Y; p.ldy = ldy; p.Dload = (int)Dload;
-  p.counters = reinterpret_cast<int *>(workspace);
-  const size_t counter_bytes = spmm_counter_bytes(M, nnz, D);
-  p.partials = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + counter_bytes);
-  GNN_CUDA(cudaMemsetAsync(p.counters, 0, (size_t)M * pl.nslabs * sizeof(int), st));
+  p.cshift = 0;
+  while ((1 << p.cshift) < pl.C) ++p.cshift;
+  p.counters = counters;
+  p.partials = reinterpret_cast<float *>(partials);
+  // the arrival counters wrap back to zero inside the kernel (atomicInc), so a caller that keeps one workspace per
+  // stream zeroes it once and passes GNN_SPMM_COUNTERS_ZEROED afterwards: one launch per SpMM instead of two
+  if (!(flags & GNN_SPMM_COUNTERS_ZEROED)) GNN_CUDA(cudaMemsetAsync(p.counters, 0, (size_t)M * pl.nslabs * sizeof(int), st));
   XSrc<GATHER> xs{X, (int)ldx, xrows};
   switch (vec) {
     case 4: return launch_spmm_nv<4, GATHER>(pl, p, xs, st);
@@ -544,36 +614,27 @@ int spmm_entry(const int32_t *rowptr, const int32_t *colidx, const float *vals, 
 }
 
 // ---------------------------------------------------------------------------
-// build_adj: one warp per row, lanes stride over the row's entries (coalesced)
+// build_adj
 // ---------------------------------------------------------------------------
 constexpr int kAdjChunk = 256;
 
-// largest r in [lo, hi] with rowptr[r] <= i  (skips empty rows that share the same start)
-__device__ __forceinline__ int row_of_nnz(const int *__restrict__ rowptr, int lo, int hi, int i) {
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(rowptr + mid) <= i) lo = mid; else hi = mid - 1;
-  }
-  return lo;
-}
-
 // One warp per 256 consecutive stored entries (not per row: a hub row of a LADIES layer holds thousands of entries and
 // a warp-per-row grid waited 65 us for it on a 3.9 M-entry layer).  Lane-strided, so every store instruction of the
-// warp covers one contiguous 128/256-byte run; the row of an entry is a bounded binary search between the rows of the
-// chunk's first and last entry (0-2 steps for all but the sparsest layers).
+// warp covers one contiguous 128/256-byte run; the row of an entry comes from the chunk's row-pointer window in shared
+// memory (chunk_rows.cuh) instead of a binary search over global memory.
 template <typename ColT>
 __global__ void __launch_bounds__(256)
 build_adj_kernel(const int *__restrict__ fullrowptr, const int *__restrict__ rowptr, const ColT *__restrict__ colidx,
                  const float *__restrict__ normfact, int M, int64_t nnz, int64_t *__restrict__ out_idx,
-                 float *__restrict__ out_vals, int *__restrict__ out_col32) {
+                 float *__restrict__ out_vals, int *__restrict__ out_col32, int *__restrict__ out_row32) {
+  constexpr int J = kAdjChunk / 32;
+  __shared__ int win_s[8][32 * J + 1];
   const int lane = threadIdx.x & 31;
-  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5;
+  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   const int64_t s64 = item * kAdjChunk;
   if (s64 >= nnz) return;
   const int s = (int)s64, e = (int)min((int64_t)s + kAdjChunk, nnz);
-  const int r_lo = row_of_nnz(rowptr, 0, M - 1, s);
-  const int r_hi = row_of_nnz(rowptr, r_lo, M - 1, e - 1);
-  constexpr int J = kAdjChunk / 32;
   int c[J];
   float nf[J];
 #pragma unroll
@@ -581,6 +642,8 @@ build_adj_kernel(const int *__restrict__ fullrowptr, const int *__restrict__ row
     const int i = s + lane + 32 * j;
     c[j] = i < e ? (int)colidx[i] : 0;
   }
+  ChunkRows<J> cr;
+  cr.load(rowptr, M, s, lane, win_s[warp]);
 #pragma unroll
   for (int j = 0; j < J; ++j) nf[j] = __ldg(normfact + c[j]);
   int r_prev = -1;
@@ -589,7 +652,7 @@ build_adj_kernel(const int *__restrict__ fullrowptr, const int *__restrict__ row
   for (int j = 0; j < J; ++j) {
     const int i = s + lane + 32 * j;
     if (i >= e) break;
-    const int r = row_of_nnz(rowptr, max(r_lo, r_prev), r_hi, i);
+    const int r = cr.row_of(rowptr, M, i);
     if (r != r_prev) {
       // cuda_spmm.cu:800: `1. / deg * normfact` - double quotient, double product, one rounding to float
       inv_deg = 1. / (double)(__ldg(fullrowptr + r + 1) - __ldg(fullrowptr + r));
@@ -597,6 +660,7 @@ build_adj_kernel(const int *__restrict__ fullrowptr, const int *__restrict__ row
     }
     out_vals[i] = (float)(inv_deg * (double)nf[j]);
     if (out_col32) out_col32[i] = c[j];
+    if (out_row32) out_row32[i] = r;
     if (out_idx) { out_idx[i] = r; out_idx[nnz + i] = c[j]; }
   }
 }
@@ -618,29 +682,37 @@ __global__ void coo_to_csr_kernel(const int64_t *__restrict__ idx, int64_t M, in
 // ---------------------------------------------------------------------------
 // CSR transpose through a column-major bitmap (deterministic: bit OR is order-free)
 //
-// cell[c][w] = { bits of rows 32w..32w+31 that have a nonzero in column c,
-//                number of nonzeros of column c in rows < 32w }
-// so the entry (r, c) lands at t_rowptr[c] + cell.prefix + popc(cell.bits below r):
+// cell[c][w] = { bits of rows row0+32w..row0+32w+31 that have a nonzero in column c,
+//                number of nonzeros of column c in rows [row0, row0+32w) }
+// so the entry (r, c) lands at base[c] + cell.prefix + popc(cell.bits below r):
 // the transposed rows come out in ascending source row without any sort.
+//
+// The bitmap covers a BLOCK of rows [row0, row1) at a time.  One block (the normal case: every LADIES layer of the
+// benchmark shapes) = memset -> set -> prefix+scan -> fill, four stream operations.  When K*ceil(M/32)*8 bytes would
+// exceed the bitmap budget (products/papers-scale samp_num, ~130 K x 130 K and up), the rows are cut into blocks that
+// fit: column totals come from a histogram pass + scan, a per-column cursor carries the fill position from block to
+// block.  Same output, any size, workspace bounded by the budget.
 // ---------------------------------------------------------------------------
-// Both passes over the nonzeros (set bits / fill) are nnz-balanced: a warp takes 256 consecutive nonzeros,
-// finds the rows its chunk touches with one uniform binary search, keeps 8 independent loads per lane in
-// flight, and resolves each nonzero's row by a search restricted to the chunk's few rows.
+// Both passes over the nonzeros (set bits / fill) are nnz-balanced: a warp takes 256 consecutive nonzeros, finds the
+// rows its chunk touches through the shared-memory row-pointer window (chunk_rows.cuh), keeps 8 independent loads per
+// lane in flight.
 constexpr int kTrChunk = 256;
+std::atomic<int64_t> g_transpose_budget{(int64_t)512 << 20};
 
 template <bool FILL>
 __global__ void __launch_bounds__(256)
-transpose_pass_kernel(uint2 *__restrict__ cells, int M, int nnz, int words_per_col, const int *__restrict__ rowptr,
-                      const int *__restrict__ colidx, const float *__restrict__ vals, const int *__restrict__ t_rowptr,
-                      int *__restrict__ t_colidx, float *__restrict__ t_vals) {
+transpose_pass_kernel(uint2 *__restrict__ cells, int M, int nnz, int words_per_col, int row0, int row1,
+                      const int *__restrict__ rowptr, const int *__restrict__ colidx, const float *__restrict__ vals,
+                      const int *__restrict__ base, int *__restrict__ t_colidx, float *__restrict__ t_vals,
+                      int *__restrict__ t_rowidx) {
+  constexpr int J = kTrChunk / 32;
+  __shared__ int win_s[8][32 * J + 1];
   const int lane = threadIdx.x & 31;
-  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5;
+  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   const int64_t s64 = item * kTrChunk;
   if (s64 >= nnz) return;
   const int s = (int)s64, e = min(s + kTrChunk, nnz);
-  const int r_lo = row_of_nnz(rowptr, 0, M - 1, s);
-  const int r_hi = row_of_nnz(rowptr, r_lo, M - 1, e - 1);
-  constexpr int J = kTrChunk / 32;
   int c[J], r[J];
   float v[J];
 #pragma unroll
@@ -649,39 +721,99 @@ transpose_pass_kernel(uint2 *__restrict__ cells, int M, int nnz, int words_per_c
     c[j] = i < e ? __ldg(colidx + i) : -1;
     if (FILL) v[j] = i < e ? __ldg(vals + i) : 0.f;
   }
+  ChunkRows<J> cr;
+  cr.load(rowptr, M, s, lane, win_s[warp]);
+  if (cr.r_lo >= row1) return;                     // the whole chunk lies after this row block (warp-uniform)
 #pragma unroll
-  for (int j = 0; j < J; ++j) r[j] = c[j] >= 0 ? row_of_nnz(rowptr, r_lo, r_hi, s + lane + 32 * j) : 0;
+  for (int j = 0; j < J; ++j) {
+    r[j] = c[j] >= 0 ? cr.row_of(rowptr, M, s + lane + 32 * j) : 0;
+    if (r[j] < row0 || r[j] >= row1) c[j] = -1;    // entry of another row block
+    r[j] -= row0;
+  }
   if (!FILL) {
 #pragma unroll
     for (int j = 0; j < J; ++j)
       if (c[j] >= 0) atomicOr(&cells[(int64_t)c[j] * words_per_col + (r[j] >> 5)].x, 1u << (r[j] & 31));
   } else {
     uint2 cell[J];
-    int base[J];
+    int b[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       if (c[j] >= 0) {
         cell[j] = __ldg(cells + (int64_t)c[j] * words_per_col + (r[j] >> 5));
-        base[j] = __ldg(t_rowptr + c[j]);
+        b[j] = __ldcg(base + c[j]);
       }
     }
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       if (c[j] >= 0) {
-        const int pos = base[j] + (int)cell[j].y + __popc(cell[j].x & ((1u << (r[j] & 31)) - 1u));
-        t_colidx[pos] = r[j];
+        const int pos = b[j] + (int)cell[j].y + __popc(cell[j].x & ((1u << (r[j] & 31)) - 1u));
+        t_colidx[pos] = r[j] + row0;
         t_vals[pos] = v[j];
+        if (t_rowidx) t_rowidx[pos] = c[j];
       }
     }
   }
 }
 
-__global__ void __launch_bounds__(256)
-bitmap_prefix_kernel(uint2 *__restrict__ cells, int K, int words_per_col, int *__restrict__ counts) {
+// exclusive scan of in[0..n) into out[0..n], out[n] = total, by ONE CTA of 1024 threads.  Tiles of 32 K elements:
+// warp w owns 1024 consecutive ones as 32 coalesced rows of 32 (all loads issued together), shuffle scans per row
+// with a running carry, then one 32-entry scan over the warp totals.
+__device__ __forceinline__ void block_exclusive_scan_1024(const int *__restrict__ in, int n, int *__restrict__ out, int *sm33) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int carry = 0;
+  for (int base = 0; base < n; base += 32768) {
+    const int seg = base + warp * 1024 + lane;
+    int v[32];
+#pragma unroll
+    for (int it = 0; it < 32; ++it) v[it] = seg + it * 32 < n ? __ldcg(in + seg + it * 32) : 0;
+    int run = 0;
+#pragma unroll
+    for (int it = 0; it < 32; ++it) {
+      int incl = v[it];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(kFull, incl, off);
+        if (lane >= off) incl += y;
+      }
+      v[it] = run + incl - v[it];                       // exclusive inside the warp's segment
+      run += __shfl_sync(kFull, incl, 31);
+    }
+    if (lane == 0) sm33[warp] = run;
+    __syncthreads();
+    if (warp == 0) {
+      int w = sm33[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(kFull, w, off);
+        if (lane >= off) w += y;
+      }
+      sm33[lane] = w;                                   // inclusive over warps
+    }
+    __syncthreads();
+    const int offset = carry + (warp ? sm33[warp - 1] : 0);
+    carry += sm33[31];
+#pragma unroll
+    for (int it = 0; it < 32; ++it)
+      if (seg + it * 32 < n) out[seg + it * 32] = v[it] + offset;
+    __syncthreads();
+  }
+  if (tid == 0) out[n] = carry;
+}
+
+// Per column: running popcount of its bitmap words (cell.y) and the column's count in this row block.
+//   cursor != NULL (multi-block mode): first cursor[c] += counts[c] (the previous block's count), then counts[c] = this block's.
+//   t_rowptr != NULL (single-block mode): the CTA that finishes last turns the counts into the row pointer of A^T
+//   (saves a launch; `done` is a zeroed word in the workspace).
+__global__ void __launch_bounds__(1024)
+bitmap_prefix_kernel(uint2 *__restrict__ cells, int K, int words_per_col, int *__restrict__ counts, int *__restrict__ cursor,
+                     int advance, int *__restrict__ t_rowptr, unsigned *__restrict__ done) {
+  __shared__ int sm33[33];
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < K; c += gridDim.x * wpb) {
     uint2 *col = cells + (int64_t)c * words_per_col;
+    if (cursor && advance && lane == 0) cursor[c] += counts[c];
     int running = 0;
     for (int w0 = 0; w0 < words_per_col; w0 += 32) {
       const int w = w0 + lane;
@@ -697,6 +829,42 @@ bitmap_prefix_kernel(uint2 *__restrict__ cells, int K, int words_per_col, int *_
     }
     if (lane == 0) counts[c] = running;
   }
+  if (t_rowptr) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) sm33[32] = (atomicInc(done, gridDim.x - 1) == gridDim.x - 1);
+    __syncthreads();
+    if (!sm33[32]) return;
+    __threadfence();
+    block_exclusive_scan_1024(counts, K, t_rowptr, sm33);
+  }
+}
+
+// multi-block mode only: column totals of the whole matrix (integer atomics: order-free) and cursor = row pointer
+__global__ void __launch_bounds__(256)
+column_histogram_kernel(const int *__restrict__ colidx, int nnz, int *__restrict__ counts) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(counts + __ldg(colidx + i), 1);
+}
+
+__global__ void copy_ints_kernel(const int *__restrict__ in, int n, int *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+// workspace of gnn_csr_transpose: [counts K ints][cursor K ints][done 256 B][cells K x wpc uint2]
+struct TrLayout { int wpc, nblocks; size_t off_counts, off_cursor, off_done, off_cells, total; };
+inline TrLayout tr_layout(int64_t M, int64_t K) {
+  TrLayout L;
+  const int64_t words = cdiv(M, 32);
+  const int64_t budget = g_transpose_budget.load(std::memory_order_relaxed);
+  const int64_t fit = std::max<int64_t>(1, budget / (K * (int64_t)sizeof(uint2)));
+  L.nblocks = (int)cdiv(words, std::min(words, fit));
+  L.wpc = (int)cdiv(words, L.nblocks);               // equal blocks
+  const size_t kal = ((size_t)K * 4 + 255) / 256 * 256;
+  L.off_counts = 0; L.off_cursor = kal; L.off_done = 2 * kal; L.off_cells = 2 * kal + 256;
+  L.total = L.off_cells + (size_t)K * L.wpc * sizeof(uint2) + 256;
+  return L;
 }
 
 // exclusive scan of counts[0..n) into out[0..n], out[n] = total; single CTA of 1024 threads, tiles of 4096
@@ -1068,7 +1236,7 @@ int64_t gnn_launch_count(void) { return g_launches.load(std::memory_order_relaxe
 
 int gnn_build_adj(const int32_t *fullrowptr, const int32_t *rowptr, const void *colidx, int colidx_bytes,
                   const float *normfact, int64_t M, int64_t K, int64_t nnz, int64_t *out_indices, float *out_vals,
-                  int32_t *out_colidx32, gnn_stream_t stream) {
+                  int32_t *out_colidx32, int32_t *out_rowidx32, gnn_stream_t stream) {
   (void)K;
   if (M < 0 || nnz < 0 || (colidx_bytes != 2 && colidx_bytes != 4)) return GNN_E_BADARG;
   if (M >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1) return GNN_E_RANGE;
@@ -1078,10 +1246,10 @@ int gnn_build_adj(const int32_t *fullrowptr, const int32_t *rowptr, const void *
   const unsigned grid = (unsigned)cdiv(cdiv(nnz, kAdjChunk), 8);
   if (colidx_bytes == 2)
     build_adj_kernel<int16_t><<<grid, 256, 0, st>>>(fullrowptr, rowptr, (const int16_t *)colidx, normfact, (int)M, nnz,
-                                                    out_indices, out_vals, out_colidx32);
+                                                    out_indices, out_vals, out_colidx32, out_rowidx32);
   else
     build_adj_kernel<int32_t><<<grid, 256, 0, st>>>(fullrowptr, rowptr, (const int32_t *)colidx, normfact, (int)M, nnz,
-                                                    out_indices, out_vals, out_colidx32);
+                                                    out_indices, out_vals, out_colidx32, out_rowidx32);
   GNN_LAUNCH_CHECK();
   return 0;
 }
@@ -1096,63 +1264,200 @@ int gnn_coo_to_csr(const int64_t *indices, int64_t M, int64_t nnz, int32_t *out_
   return 0;
 }
 
-size_t gnn_csr_spmm_workspace_bytes(int64_t M, int64_t nnz, int64_t D) {
+size_t gnn_csr_spmm_counter_bytes(int64_t M, int64_t nnz, int64_t D) {
   if (M <= 0 || nnz <= 0 || D <= 0) return 256;
-  const int C = std::max(32, spmm_chunk(nnz, D) / 2);     // wave fitting may halve the base chunk
+  return spmm_counter_bytes(M, nnz, D);
+}
+
+size_t gnn_csr_spmm_partial_bytes(int64_t M, int64_t nnz, int64_t D) {
+  if (M <= 0 || nnz <= 0 || D <= 0) return 256;
+  const int C = flat_wanted(M, nnz, D) ? flat_chunk(nnz, D)
+                                       : std::max(32, spmm_chunk(nnz, D) / 2);     // wave fitting may halve the base chunk
   const size_t nchunks = (size_t)cdiv(nnz, C);
   const size_t Dp = (size_t)cdiv(D, 4) * 4;
-  const size_t counter_bytes = spmm_counter_bytes(M, nnz, D);
-  return counter_bytes + 2 * nchunks * Dp * sizeof(float) + 256;
+  return 2 * nchunks * Dp * sizeof(float) + 256;
 }
+
+size_t gnn_csr_spmm_workspace_bytes(int64_t M, int64_t nnz, int64_t D) {
+  return gnn_csr_spmm_counter_bytes(M, nnz, D) + gnn_csr_spmm_partial_bytes(M, nnz, D);
+}
+
+// workspace of the plain entry points = [counters | partials]; size and null checks happen in spmm_entry, after the
+// argument and range checks
+#define GNN_SPLIT_WS()                                                                              \
+  const size_t cb_ = gnn_csr_spmm_counter_bytes(M, nnz, D);                                          \
+  int *counters_ = workspace_bytes >= cb_ ? reinterpret_cast<int *>(workspace) : nullptr;           \
+  void *partials_ = (workspace && workspace_bytes >= cb_) ? reinterpret_cast<char *>(workspace) + cb_ : nullptr; \
+  const size_t pb_ = workspace_bytes > cb_ ? workspace_bytes - cb_ : 0
 
 int gnn_csr_spmm_f32(const int32_t *rowptr, const int32_t *colidx, const float *vals, int64_t M, int64_t K, int64_t nnz,
                      int64_t D, const float *X, int64_t ldx, float *Y, int64_t ldy, void *workspace,
                      size_t workspace_bytes, gnn_stream_t stream) {
-  return spmm_entry<false>(rowptr, colidx, vals, M, K, nnz, D, X, ldx, nullptr, Y, ldy, workspace, workspace_bytes,
+  GNN_SPLIT_WS();
+  return spmm_entry<false>(rowptr, nullptr, colidx, vals, M, K, nnz, D, X, ldx, nullptr, Y, ldy, counters_, partials_, pb_, 0u,
                            (cudaStream_t)stream);
 }
 
 int gnn_gather_spmm_f32(const int32_t *rowptr, const int32_t *colidx, const float *vals, int64_t M, int64_t K,
                         int64_t nnz, int64_t D, const float *const *xrows, float *Y, int64_t ldy, void *workspace,
                         size_t workspace_bytes, gnn_stream_t stream) {
-  return spmm_entry<true>(rowptr, colidx, vals, M, K, nnz, D, nullptr, 0, xrows, Y, ldy, workspace, workspace_bytes,
+  GNN_SPLIT_WS();
+  return spmm_entry<true>(rowptr, nullptr, colidx, vals, M, K, nnz, D, nullptr, 0, xrows, Y, ldy, counters_, partials_, pb_, 0u,
                           (cudaStream_t)stream);
+}
+
+int gnn_csr_spmm_f32_ex(const int32_t *rowptr, const int32_t *rowidx, const int32_t *colidx, const float *vals, int64_t M,
+                        int64_t K, int64_t nnz, int64_t D, const float *X, int64_t ldx, float *Y, int64_t ldy,
+                        int32_t *counters, void *partials, size_t partial_bytes, unsigned flags, gnn_stream_t stream) {
+  return spmm_entry<false>(rowptr, rowidx, colidx, vals, M, K, nnz, D, X, ldx, nullptr, Y, ldy, counters, partials, partial_bytes,
+                           flags, (cudaStream_t)stream);
+}
+
+int gnn_gather_spmm_f32_ex(const int32_t *rowptr, const int32_t *rowidx, const int32_t *colidx, const float *vals, int64_t M,
+                           int64_t K, int64_t nnz, int64_t D, const float *const *xrows, float *Y, int64_t ldy,
+                           int32_t *counters, void *partials, size_t partial_bytes, unsigned flags, gnn_stream_t stream) {
+  return spmm_entry<true>(rowptr, rowidx, colidx, vals, M, K, nnz, D, nullptr, 0, xrows, Y, ldy, counters, partials, partial_bytes,
+                          flags, (cudaStream_t)stream);
+}
+
+int gnn_csr_spmm_t_f32(const int32_t *rowptr, const int32_t *rowidx, const int32_t *colidx, const float *vals, int64_t M,
+                       int64_t K, int64_t nnz, int64_t D, const float *G, int64_t ldg, float *dX, int64_t lddx,
+                       gnn_stream_t stream) {
+  if (M < 0 || K < 0 || nnz < 0 || D < 0) return GNN_E_BADARG;
+  if (K == 0 || D == 0) return 0;
+  if (!dX || lddx < D) return GNN_E_BADARG;
+  if (M >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 2048 || K >= (1ll << 31) || D >= (1ll << 24)) return GNN_E_RANGE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (lddx == D) {
+    GNN_CUDA(cudaMemsetAsync(dX, 0, (size_t)K * D * sizeof(float), st));
+  } else {
+    zero_rows_kernel<<<(unsigned)std::min<int64_t>(cdiv(K * D, 256), 148 * 16), 256, 0, st>>>(dX, lddx, K, D);
+    GNN_LAUNCH_CHECK();
+  }
+  if (nnz == 0 || M == 0) return 0;
+  if (!rowptr || !colidx || !vals || !G || ldg < D) return GNN_E_BADARG;
+  ScatterParams p;
+  p.rowptr = rowptr; p.rowidx = rowidx; p.colidx = colidx; p.vals = vals;
+  p.M = (int)M; p.nnz = (int)nnz; p.D = (int)D;
+  p.G = G; p.ldg = ldg; p.dX = dX; p.lddx = lddx;
+  const bool vec4 = ((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(dX) | (uintptr_t)(ldg * 4) | (uintptr_t)(lddx * 4)) & 15) == 0;
+  const int64_t nvec = cdiv(D, vec4 ? 4 : 1);
+  const int64_t n = cdiv(nvec, 32);
+  // chunk: as for the flat SpMM - enough warp items for ~2 waves, at most 128 entries each
+  int C = kFlatMaxC;
+  while (C > 32 && cdiv(nnz, C) * n < kFlatTargetItems) C >>= 1;
+  int nv = 1;
+  if (n >= 2 && cdiv(nnz, C) * cdiv(n, 2) >= 2 * kFlatTargetItems) nv = 2;
+#ifdef GNN_TUNE
+  if (getenv("GNN_TUNE_SC")) C = atoi(getenv("GNN_TUNE_SC"));
+  if (getenv("GNN_TUNE_SNV")) nv = atoi(getenv("GNN_TUNE_SNV"));
+#endif
+  p.C = C;
+  p.nchunks = (int)cdiv(nnz, C);
+  p.nslabs = (int)cdiv(n, nv);
+  const unsigned grid = (unsigned)cdiv((int64_t)p.nchunks * p.nslabs, kFlatWarps);
+#define GNN_SCATTER(V4_, NV_, U_)                                                                             \
+  do {                                                                                                        \
+    if (rowidx) spmm_scatter_t_kernel<V4_, NV_, U_, true><<<grid, kFlatWarps * 32, 0, st>>>(p);                 \
+    else spmm_scatter_t_kernel<V4_, NV_, U_, false><<<grid, kFlatWarps * 32, 0, st>>>(p);                       \
+  } while (0)
+  if (vec4) {
+    if (nv == 2) GNN_SCATTER(true, 2, 4); else GNN_SCATTER(true, 1, 8);
+  } else {
+    if (nv == 2) GNN_SCATTER(false, 2, 8); else GNN_SCATTER(false, 1, 8);
+  }
+#undef GNN_SCATTER
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnn_probe_row_gather_f32(const float *X, int64_t ldx, int64_t D, const int32_t *colidx, int64_t nnz, int nv,
+                             int warps_per_sm, float *sink, int64_t *bytes_gathered, gnn_stream_t stream) {
+  if (!X || !colidx || !sink || nnz <= 0 || nnz >= (1ll << 31) || warps_per_sm <= 0) return GNN_E_BADARG;
+  if ((nv != 1 && nv != 2 && nv != 4) || D < 128 * nv || ldx < D) return GNN_E_BADARG;
+  if (((reinterpret_cast<uintptr_t>(X) | (uintptr_t)(ldx * 4)) & 15) != 0) return GNN_E_BADARG;
+  const int nslabs = (int)(D / (128 * nv));
+  const int64_t warps = (int64_t)device_sm_count() * warps_per_sm / nslabs * nslabs;
+  if (warps <= 0) return GNN_E_BADARG;
+  const int per_warp = (int)std::max<int64_t>(32, nnz * nslabs / warps / 32 * 32);
+  const unsigned grid = (unsigned)cdiv(warps, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  // the grid is rounded up to whole CTAs: count what the launch really moves
+  const int64_t launched = (int64_t)grid * 8;
+  if (bytes_gathered) *bytes_gathered = launched * per_warp * nv * 512;
+  switch (nv) {
+    case 1: row_gather_probe_kernel<1, 8><<<grid, 256, 0, st>>>(X, ldx, colidx, (int)nnz, per_warp, 128, nslabs, sink); break;
+    case 2: row_gather_probe_kernel<2, 4><<<grid, 256, 0, st>>>(X, ldx, colidx, (int)nnz, per_warp, 256, nslabs, sink); break;
+    default: row_gather_probe_kernel<4, 2><<<grid, 256, 0, st>>>(X, ldx, colidx, (int)nnz, per_warp, 512, nslabs, sink); break;
+  }
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int64_t gnn_set_transpose_budget(int64_t bytes) {
+  if (bytes < 0) return GNN_E_BADARG;
+  return g_transpose_budget.exchange(bytes == 0 ? ((int64_t)512 << 20) : bytes, std::memory_order_relaxed);
 }
 
 size_t gnn_csr_transpose_workspace_bytes(int64_t M, int64_t K, int64_t nnz) {
   (void)nnz;
   if (M <= 0 || K <= 0) return 256;
-  const size_t words_per_col = (size_t)cdiv(M, 32);
-  return (size_t)K * words_per_col * sizeof(uint2) + ((size_t)K * 4 + 255) / 256 * 256 + 256;
+  return tr_layout(M, K).total;
 }
 
 int gnn_csr_transpose(const int32_t *rowptr, const int32_t *colidx, const float *vals, int64_t M, int64_t K, int64_t nnz,
-                      int32_t *t_rowptr, int32_t *t_colidx, float *t_vals, void *workspace, size_t workspace_bytes,
-                      gnn_stream_t stream) {
+                      int32_t *t_rowptr, int32_t *t_colidx, float *t_vals, int32_t *t_rowidx, void *workspace,
+                      size_t workspace_bytes, gnn_stream_t stream) {
   if (M < 0 || K < 0 || nnz < 0 || !t_rowptr) return GNN_E_BADARG;
   if (M >= (1ll << 31) - 1 || K >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1) return GNN_E_RANGE;
   cudaStream_t st = (cudaStream_t)stream;
   if (K == 0) { GNN_CUDA(cudaMemsetAsync(t_rowptr, 0, sizeof(int), st)); return 0; }
   if (nnz == 0 || M == 0) { GNN_CUDA(cudaMemsetAsync(t_rowptr, 0, (size_t)(K + 1) * sizeof(int), st)); return 0; }
   if (!rowptr || !colidx || !vals || !t_colidx || !t_vals) return GNN_E_BADARG;
-  const size_t need = gnn_csr_transpose_workspace_bytes(M, K, nnz);
-  if (need > ((size_t)4 << 30)) return GNN_E_RANGE;   // bitmap too large: caller falls back to a sort
-  if (!workspace || workspace_bytes < need) return GNN_E_WORKSPACE;
-  const int words_per_col = (int)cdiv(M, 32);
-  int *counts = reinterpret_cast<int *>(workspace);
-  uint2 *cells = reinterpret_cast<uint2 *>(reinterpret_cast<char *>(workspace) + ((size_t)K * 4 + 255) / 256 * 256);
-  GNN_CUDA(cudaMemsetAsync(cells, 0, (size_t)K * words_per_col * sizeof(uint2), st));
+  const TrLayout L = tr_layout(M, K);
+  if (!workspace || workspace_bytes < L.total) return GNN_E_WORKSPACE;
+  char *ws = reinterpret_cast<char *>(workspace);
+  int *counts = reinterpret_cast<int *>(ws + L.off_counts);
+  int *cursor = reinterpret_cast<int *>(ws + L.off_cursor);
+  unsigned *done = reinterpret_cast<unsigned *>(ws + L.off_done);
+  uint2 *cells = reinterpret_cast<uint2 *>(ws + L.off_cells);
+  const size_t cell_bytes = (size_t)K * L.wpc * sizeof(uint2);
   const unsigned pass_grid = (unsigned)cdiv(cdiv(nnz, kTrChunk), 8);
-  transpose_pass_kernel<false><<<pass_grid, 256, 0, st>>>(cells, (int)M, (int)nnz, words_per_col, rowptr, colidx, vals, t_rowptr,
-                                                         t_colidx, t_vals);
-  GNN_LAUNCH_CHECK();
-  bitmap_prefix_kernel<<<warp_grid(K, 8), 256, 0, st>>>(cells, (int)K, words_per_col, counts);
+  const unsigned prefix_grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(K, 32), 148 * 2));
+  if (L.nblocks == 1) {
+    // `done` sits right in front of the cells: one memset zeroes both
+    GNN_CUDA(cudaMemsetAsync(done, 0, (L.off_cells - L.off_done) + cell_bytes, st));
+    transpose_pass_kernel<false><<<pass_grid, 256, 0, st>>>(cells, (int)M, (int)nnz, L.wpc, 0, (int)M, rowptr, colidx, vals,
+                                                           nullptr, t_colidx, t_vals, nullptr);
+    GNN_LAUNCH_CHECK();
+    bitmap_prefix_kernel<<<prefix_grid, 1024, 0, st>>>(cells, (int)K, L.wpc, counts, nullptr, 0, t_rowptr, done);
+    GNN_LAUNCH_CHECK();
+    transpose_pass_kernel<true><<<pass_grid, 256, 0, st>>>(cells, (int)M, (int)nnz, L.wpc, 0, (int)M, rowptr, colidx, vals,
+                                                          t_rowptr, t_colidx, t_vals, t_rowidx);
+    GNN_LAUNCH_CHECK();
+    return 0;
+  }
+  // row-blocked: column totals first, then block after block with a per-column cursor
+  GNN_CUDA(cudaMemsetAsync(counts, 0, (size_t)K * sizeof(int), st));
+  column_histogram_kernel<<<(unsigned)std::min<int64_t>(cdiv(nnz, 256), 148 * 16), 256, 0, st>>>(colidx, (int)nnz, counts);
   GNN_LAUNCH_CHECK();
   exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, (int)K, t_rowptr);
   GNN_LAUNCH_CHECK();
-  transpose_pass_kernel<true><<<pass_grid, 256, 0, st>>>(cells, (int)M, (int)nnz, words_per_col, rowptr, colidx, vals, t_rowptr,
-                                                        t_colidx, t_vals);
+  copy_ints_kernel<<<(unsigned)cdiv(K, 256), 256, 0, st>>>(t_rowptr, (int)K, cursor);
   GNN_LAUNCH_CHECK();
+  for (int blk = 0; blk < L.nblocks; ++blk) {
+    const int row0 = blk * L.wpc * 32;
+    const int row1 = (int)std::min<int64_t>(M, (int64_t)row0 + (int64_t)L.wpc * 32);
+    GNN_CUDA(cudaMemsetAsync(cells, 0, cell_bytes, st));
+    transpose_pass_kernel<false><<<pass_grid, 256, 0, st>>>(cells, (int)M, (int)nnz, L.wpc, row0, row1, rowptr, colidx, vals,
+                                                           nullptr, t_colidx, t_vals, nullptr);
+    GNN_LAUNCH_CHECK();
+    bitmap_prefix_kernel<<<prefix_grid, 1024, 0, st>>>(cells, (int)K, L.wpc, counts, cursor, blk > 0 ? 1 : 0, nullptr, done);
+    GNN_LAUNCH_CHECK();
+    transpose_pass_kernel<true><<<pass_grid, 256, 0, st>>>(cells, (int)M, (int)nnz, L.wpc, row0, row1, rowptr, colidx, vals,
+                                                          cursor, t_colidx, t_vals, t_rowidx);
+    GNN_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -17,6 +17,10 @@
 #include <c10/cuda/CUDAStream.h>
 #include <torch/extension.h>
 
+#include <cuda_runtime_api.h>
+
+#include <map>
+#include <mutex>
 #include <tuple>
 #include <vector>
 
@@ -44,9 +48,50 @@ inline torch::Tensor workspace(size_t bytes, const torch::Device &dev) {
   return torch::empty({(int64_t)bytes}, torch::TensorOptions().dtype(torch::kUInt8).device(dev));
 }
 
+// ---- one long-lived SpMM workspace per (device, stream) ---------------------------------
+// The SpMM kernels need arrival counters (zero on entry) and a partial-sum buffer.  The counters wrap back to zero inside
+// the kernel, so a region that is zeroed once stays usable forever by calls on the same stream (which the GPU runs one
+// after another): no memset and no allocator round trip per spmm() call - one kernel launch.  Streams under CUDA-graph
+// capture get a fresh workspace instead (memory handed out during capture belongs to the graph's private pool).
+struct StreamWorkspace {
+  torch::Tensor counters, partials;
+};
+std::mutex g_ws_mutex;
+std::map<std::pair<int, void *>, StreamWorkspace> g_ws;
+
+struct SpmmWs {
+  torch::Tensor counters, partials;
+  unsigned flags;
+};
+
+SpmmWs spmm_workspace(int64_t M, int64_t nnz, int64_t D, const torch::Device &dev) {
+  const size_t cb = gnn_csr_spmm_counter_bytes(M, nnz, D), pb = gnn_csr_spmm_partial_bytes(M, nnz, D);
+  auto stream = c10::cuda::getCurrentCUDAStream();
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream.stream(), &cap) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+  auto bytes = torch::TensorOptions().dtype(torch::kUInt8).device(dev);
+  if (cap != cudaStreamCaptureStatusNone)
+    return {torch::empty({(int64_t)cb}, bytes), torch::empty({(int64_t)pb}, bytes), 0u};
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  auto &ws = g_ws[{(int)dev.index(), (void *)stream.stream()}];
+  if (!ws.counters.defined() || (size_t)ws.counters.numel() < cb)
+    ws.counters = torch::zeros({(int64_t)std::max<size_t>(2 * cb, (size_t)1 << 20)}, bytes);      // zeroed on this stream, once
+  if (!ws.partials.defined() || (size_t)ws.partials.numel() < pb)
+    ws.partials = torch::empty({(int64_t)std::max<size_t>(pb + pb / 2, (size_t)8 << 20)}, bytes);
+  return {ws.counters, ws.partials, GNN_SPMM_COUNTERS_ZEROED};
+}
+
 // ---- CSR fast path -------------------------------------------------------
+inline const int32_t *rowidx_ptr(const c10::optional<torch::Tensor> &rowidx, int64_t nnz) {
+  if (!rowidx.has_value() || !rowidx.value().defined()) return nullptr;
+  const auto &t = rowidx.value();
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous() && t.scalar_type() == torch::kInt && t.numel() == nnz,
+              "rowidx must be a contiguous int32 CUDA tensor with one entry per nonzero");
+  return t.data_ptr<int32_t>();
+}
+
 torch::Tensor csr_spmm(const torch::Tensor &rowptr, const torch::Tensor &colidx, const torch::Tensor &vals, int64_t M,
-                       int64_t K, const torch::Tensor &dense) {
+                       int64_t K, const torch::Tensor &dense, const c10::optional<torch::Tensor> &rowidx) {
   CHECK_DENSE(rowptr); CHECK_DENSE(colidx); CHECK_DENSE(vals); CHECK_CUDA(dense);
   // rows may be padded (stride(0) >= D) as long as each row is contiguous: the gathered buffer is 16-byte-row aligned
   TORCH_CHECK(dense.dim() == 2 && (dense.stride(1) == 1 || dense.size(1) <= 1) && dense.stride(0) >= dense.size(1),
@@ -60,33 +105,68 @@ torch::Tensor csr_spmm(const torch::Tensor &rowptr, const torch::Tensor &colidx,
   c10::cuda::CUDAGuard g(dense.device());
   const int64_t nnz = vals.numel(), D = dense.size(1);
   auto out = torch::empty({M, D}, dense.options());
-  const size_t wsb = gnn_csr_spmm_workspace_bytes(M, nnz, D);
-  auto ws = workspace(wsb, dense.device());
-  check_rc(gnn_csr_spmm_f32(rowptr.data_ptr<int32_t>(), colidx.data_ptr<int32_t>(), vals.data_ptr<float>(), M, K, nnz, D,
-                            dense.data_ptr<float>(), dense.size(0) > 1 ? dense.stride(0) : D, out.data_ptr<float>(), D,
-                            ws.data_ptr(), wsb, cur_stream()),
+  auto ws = spmm_workspace(M, nnz, D, dense.device());
+  check_rc(gnn_csr_spmm_f32_ex(rowptr.data_ptr<int32_t>(), rowidx_ptr(rowidx, nnz), colidx.data_ptr<int32_t>(),
+                               vals.data_ptr<float>(), M, K, nnz, D, dense.data_ptr<float>(), dense.size(0) > 1 ? dense.stride(0) : D, out.data_ptr<float>(), D,
+                               reinterpret_cast<int32_t *>(ws.counters.data_ptr()), ws.partials.data_ptr(),
+                               (size_t)ws.partials.numel(), ws.flags, cur_stream()),
            "gnn_csr_spmm_f32");
   return out;
 }
 
 torch::Tensor gather_spmm(const torch::Tensor &rowptr, const torch::Tensor &colidx, const torch::Tensor &vals, int64_t M,
-                          int64_t K, int64_t D, const torch::Tensor &xrows) {
+                          int64_t K, int64_t D, const torch::Tensor &xrows, const c10::optional<torch::Tensor> &rowidx) {
   CHECK_DENSE(rowptr); CHECK_DENSE(colidx); CHECK_DENSE(vals); CHECK_DENSE(xrows);
   TORCH_CHECK(xrows.scalar_type() == torch::kLong && xrows.numel() == K, "xrows must be an int64 pointer table of K entries");
   c10::cuda::CUDAGuard g(vals.device());
   const int64_t nnz = vals.numel();
   auto out = torch::empty({M, D}, vals.options());
-  const size_t wsb = gnn_csr_spmm_workspace_bytes(M, nnz, D);
-  auto ws = workspace(wsb, vals.device());
-  check_rc(gnn_gather_spmm_f32(rowptr.data_ptr<int32_t>(), colidx.data_ptr<int32_t>(), vals.data_ptr<float>(), M, K, nnz, D,
-                               reinterpret_cast<const float *const *>(xrows.data_ptr<int64_t>()), out.data_ptr<float>(), D,
-                               ws.data_ptr(), wsb, cur_stream()),
+  auto ws = spmm_workspace(M, nnz, D, vals.device());
+  check_rc(gnn_gather_spmm_f32_ex(rowptr.data_ptr<int32_t>(), rowidx_ptr(rowidx, nnz), colidx.data_ptr<int32_t>(),
+                                  vals.data_ptr<float>(), M, K, nnz, D,
+                                  reinterpret_cast<const float *const *>(xrows.data_ptr<int64_t>()), out.data_ptr<float>(), D,
+                                  reinterpret_cast<int32_t *>(ws.counters.data_ptr()), ws.partials.data_ptr(),
+                                  (size_t)ws.partials.numel(), ws.flags, cur_stream()),
            "gnn_gather_spmm_f32");
   return out;
 }
 
-std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> csr_transpose(const torch::Tensor &rowptr, const torch::Tensor &colidx,
-                                                                       const torch::Tensor &vals, int64_t M, int64_t K) {
+// dX = A^T . G from A's own CSR (no transposed index; vector reductions into a zero-filled output)
+torch::Tensor csr_spmm_t(const torch::Tensor &rowptr, const torch::Tensor &colidx, const torch::Tensor &vals, int64_t M,
+                         int64_t K, const torch::Tensor &grad, const c10::optional<torch::Tensor> &rowidx) {
+  CHECK_DENSE(rowptr); CHECK_DENSE(colidx); CHECK_DENSE(vals); CHECK_CUDA(grad);
+  TORCH_CHECK(grad.dim() == 2 && (grad.stride(1) == 1 || grad.size(1) <= 1) && grad.stride(0) >= grad.size(1),
+              "grad_output must be contiguous");
+  TORCH_CHECK(rowptr.scalar_type() == torch::kInt && colidx.scalar_type() == torch::kInt, "CSR indices must be int32");
+  TORCH_CHECK(vals.scalar_type() == torch::kFloat && grad.scalar_type() == torch::kFloat, "values/grad must be float32");
+  TORCH_CHECK(grad.size(0) == M, "grad_output must be [", M, ", D], got ", grad.sizes());
+  c10::cuda::CUDAGuard g(grad.device());
+  const int64_t nnz = vals.numel(), D = grad.size(1);
+  auto out = torch::empty({K, D}, grad.options());
+  check_rc(gnn_csr_spmm_t_f32(rowptr.data_ptr<int32_t>(), rowidx_ptr(rowidx, nnz), colidx.data_ptr<int32_t>(),
+                              vals.data_ptr<float>(), M, K, nnz, D, grad.data_ptr<float>(), grad.size(0) > 1 ? grad.stride(0) : D, out.data_ptr<float>(), D, cur_stream()),
+           "gnn_csr_spmm_t_f32");
+  return out;
+}
+
+// L2->SM row-gather speed of light on a block's own column stream (measurement aid of bench.py): returns bytes gathered
+int64_t probe_row_gather(const torch::Tensor &X, const torch::Tensor &colidx, int64_t nv, int64_t warps_per_sm) {
+  CHECK_CUDA(X); CHECK_DENSE(colidx);
+  TORCH_CHECK(X.dim() == 2 && X.stride(1) == 1 && X.scalar_type() == torch::kFloat && colidx.scalar_type() == torch::kInt,
+              "X must be row-major float32, colidx int32");
+  c10::cuda::CUDAGuard g(X.device());
+  auto sink = torch::zeros({1}, X.options());
+  int64_t bytes = 0;
+  check_rc(gnn_probe_row_gather_f32(X.data_ptr<float>(), X.stride(0), X.size(1), colidx.data_ptr<int32_t>(), colidx.numel(),
+                                    (int)nv, (int)warps_per_sm, sink.data_ptr<float>(), &bytes, cur_stream()),
+           "gnn_probe_row_gather_f32");
+  return bytes;
+}
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> csr_transpose(const torch::Tensor &rowptr,
+                                                                                      const torch::Tensor &colidx,
+                                                                                      const torch::Tensor &vals, int64_t M,
+                                                                                      int64_t K) {
   CHECK_DENSE(rowptr); CHECK_DENSE(colidx); CHECK_DENSE(vals);
   c10::cuda::CUDAGuard g(vals.device());
   const int64_t nnz = vals.numel();
@@ -94,14 +174,14 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> csr_transpose(const torc
   auto t_rowptr = torch::empty({K + 1}, iopt);
   auto t_colidx = torch::empty({nnz}, iopt);
   auto t_vals = torch::empty({nnz}, vals.options());
-  const size_t wsb = gnn_csr_transpose_workspace_bytes(M, K, nnz);
-  TORCH_CHECK(wsb <= ((size_t)4 << 30), "gnn_csr_transpose: bitmap workspace of ", wsb, " bytes exceeds the 4 GiB limit");
+  auto t_rowidx = torch::empty({nnz}, iopt);
+  const size_t wsb = gnn_csr_transpose_workspace_bytes(M, K, nnz);      // bounded by the bitmap budget (row-blocked beyond it)
   auto ws = workspace(wsb, vals.device());
   check_rc(gnn_csr_transpose(rowptr.data_ptr<int32_t>(), colidx.data_ptr<int32_t>(), vals.data_ptr<float>(), M, K, nnz,
                              t_rowptr.data_ptr<int32_t>(), t_colidx.data_ptr<int32_t>(), t_vals.data_ptr<float>(),
-                             ws.data_ptr(), wsb, cur_stream()),
+                             t_rowidx.data_ptr<int32_t>(), ws.data_ptr(), wsb, cur_stream()),
            "gnn_csr_transpose");
-  return {t_rowptr, t_colidx, t_vals};
+  return {t_rowptr, t_colidx, t_vals, t_rowidx};
 }
 
 std::tuple<torch::Tensor, torch::Tensor> coo_to_csr(const torch::Tensor &sparseMat) {
@@ -124,7 +204,7 @@ torch::Tensor spmm_load_balance(const torch::Tensor &sparseMat, const torch::Ten
   CHECK_DENSE(denseMat);
   auto csr = coo_to_csr(sparseMat);
   auto vals = sparseMat._values().contiguous();
-  return csr_spmm(std::get<0>(csr), std::get<1>(csr), vals, sparseMat.size(0), sparseMat.size(1), denseMat);
+  return csr_spmm(std::get<0>(csr), std::get<1>(csr), vals, sparseMat.size(0), sparseMat.size(1), denseMat, c10::nullopt);
 }
 
 torch::Tensor spmm_naive(const torch::Tensor &sparseMat, const torch::Tensor &denseMat) {
@@ -132,9 +212,9 @@ torch::Tensor spmm_naive(const torch::Tensor &sparseMat, const torch::Tensor &de
   return spmm_load_balance(sparseMat, denseMat);
 }
 
-std::tuple<torch::Tensor, torch::Tensor> build_adj(const torch::Tensor &fullrowptr, const torch::Tensor &rowptr,
-                                                   const torch::Tensor &colidx, const torch::Tensor &normfact, int64_t nrows,
-                                                   int64_t ncols) {
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> build_adj(const torch::Tensor &fullrowptr, const torch::Tensor &rowptr,
+                                                                  const torch::Tensor &colidx, const torch::Tensor &normfact,
+                                                                  int64_t nrows, int64_t ncols) {
   CHECK_DENSE(fullrowptr);
   CHECK_DENSE(rowptr);
   CHECK_DENSE(colidx);
@@ -150,14 +230,16 @@ std::tuple<torch::Tensor, torch::Tensor> build_adj(const torch::Tensor &fullrowp
   auto indices = torch::empty({2, nnz}, colidx.options().dtype(torch::kLong));
   auto values = torch::empty({nnz}, normfact.options());
   auto col32 = torch::empty({nnz}, colidx.options().dtype(torch::kInt));
+  auto row32 = torch::empty({nnz}, colidx.options().dtype(torch::kInt));
   check_rc(gnn_build_adj(fullrowptr.data_ptr<int32_t>(), rowptr.data_ptr<int32_t>(), colidx.data_ptr(),
                          colidx.scalar_type() == torch::kShort ? 2 : 4, normfact.data_ptr<float>(), nrows, ncols, nnz,
-                         indices.data_ptr<int64_t>(), values.data_ptr<float>(), col32.data_ptr<int32_t>(), cur_stream()),
+                         indices.data_ptr<int64_t>(), values.data_ptr<float>(), col32.data_ptr<int32_t>(),
+                         row32.data_ptr<int32_t>(), cur_stream()),
            "gnn_build_adj");
   // rows ascending, columns ascending and unique inside a row: already coalesced (no sort, cuda_spmm.cu:825)
   auto coo = at::_sparse_coo_tensor_unsafe(indices, values, {nrows, ncols}, values.options().layout(torch::kSparse),
                                            /*is_coalesced=*/true);
-  return {coo, col32};
+  return {coo, col32, row32};
 }
 
 torch::Tensor create_coo_tensor(const torch::Tensor &fullrowptr, const torch::Tensor &rowptr, const torch::Tensor &colidx,
@@ -368,9 +450,20 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   // B200 path
   m.def("build_adj", &build_adj, "create_coo_tensor that also returns the int32 column ids (CSR for the kernels)", rel());
   m.def("coo_to_csr", &coo_to_csr, "coalesced COO -> (rowptr int32, colidx int32)", rel());
-  m.def("csr_spmm", &csr_spmm, "Y = A.X with A in CSR", rel());
+  m.def("csr_spmm", &csr_spmm, "Y = A.X with A in CSR (optional per-entry row ids)", py::arg("rowptr"), py::arg("colidx"),
+        py::arg("vals"), py::arg("M"), py::arg("K"), py::arg("dense"), py::arg("rowidx") = py::none(), rel());
   m.def("csr_transpose", &csr_transpose, "CSR of A^T, deterministic", rel());
-  m.def("gather_spmm", &gather_spmm, "Y = A.gather(xrows) without materialising the gathered rows", rel());
+  m.def("csr_spmm_t", &csr_spmm_t, "dX = A^T.G from A's own CSR (transpose-free, vector reductions)", py::arg("rowptr"),
+        py::arg("colidx"), py::arg("vals"), py::arg("M"), py::arg("K"), py::arg("grad"), py::arg("rowidx") = py::none(), rel());
+  m.def("probe_row_gather", &probe_row_gather, "row gather only (L2->SM roof probe); returns bytes gathered", rel());
+  m.def("set_transpose_budget", [](int64_t bytes) {
+    const int64_t prev = gnn_set_transpose_budget(bytes);
+    TORCH_CHECK(prev >= 0, "set_transpose_budget: ", gnn_error_string((int)prev));
+    return prev;
+  });
+  m.def("gather_spmm", &gather_spmm, "Y = A.gather(xrows) without materialising the gathered rows", py::arg("rowptr"),
+        py::arg("colidx"), py::arg("vals"), py::arg("M"), py::arg("K"), py::arg("D"), py::arg("xrows"),
+        py::arg("rowidx") = py::none(), rel());
   m.def("placement_remap", &placement_remap, "device placement remap -> (src_dev, slot, xrows, counts)", rel());
   m.def("gather_rows", &gather_rows, "out[j] = *xrows[j]", rel());
   m.def("gather_rows_src", &gather_rows_src, "gather only the rows of one source", rel());

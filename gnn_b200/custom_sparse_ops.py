@@ -13,7 +13,8 @@ CSR (row pointer, int32 column ids, values) as a Python attribute, so ``spmm``
 never rebuilds CSR from COO (the reference does on every call,
 cuda_spmm.cu:620-667), and backward multiplies by a cached CSR of A^T built once
 on the device instead of ``mat1.transpose(0,1).coalesce()`` per call
-(custom_sparse_ops.py:34).  Sparse tensors from elsewhere are converted on first
+(custom_sparse_ops.py:34) - or, for sparse layers, needs no transposed index at all
+(``BACKWARD``).  Sparse tensors from elsewhere are converted on first
 use.  There is no CPU fallback: CPU operands raise.
 """
 from __future__ import annotations
@@ -27,15 +28,27 @@ spmm_cpp = _native.extension()
 spmm_forward_time = 0.0
 spmm_backward_time = 0.0
 
+# How ``SparseDenseMM.backward`` computes dX = A^T.G (reference custom_sparse_ops.py:30-37):
+#   "index"    CSR of A^T built once per adjacency on the device, then the gather kernel (deterministic bits)
+#   "scatter"  transpose-free: vector reductions into a zero-filled dX straight from A's CSR (sum order not fixed,
+#              like the reference's atomicAdd kernel cuda_spmm.cu:205-209)
+#   "auto"     scatter for short-row layers (top LADIES layer, sparse graphs: the index build costs more than the
+#              product), index for the dense LADIES blocks (L2 reductions are ~2.3x slower than L2 reads there) -
+#              measured A/B in profiles/r2_backward_ab.md.  An adjacency whose A^T index already exists (prebuilt by
+#              the sampler / prefetcher, off the training stream) always uses it.
+BACKWARD = "auto"
+SCATTER_MEAN_ROW = 96          # "short-row": nnz < SCATTER_MEAN_ROW * nrows
+
 _ATTR = "_gnn_b200_adj"
 
 
 class Adjacency:
     """Device-resident CSR of one layer adjacency (+ lazily the CSR of its transpose)."""
-    __slots__ = ("rowptr", "colidx", "vals", "nrows", "ncols", "_t")
+    __slots__ = ("rowptr", "colidx", "vals", "rowidx", "nrows", "ncols", "_t")
 
-    def __init__(self, rowptr, colidx, vals, nrows, ncols):
+    def __init__(self, rowptr, colidx, vals, nrows, ncols, rowidx=None):
         self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
+        self.rowidx = rowidx                 # int32 row id per entry (build_adj / csr_transpose emit it) or None
         self.nrows, self.ncols = int(nrows), int(ncols)
         self._t = None
 
@@ -45,21 +58,27 @@ class Adjacency:
 
     def matmul(self, dense: torch.Tensor) -> torch.Tensor:
         """A . X   (forward, reference custom_sparse_ops.py:23)."""
-        return spmm_cpp.csr_spmm(self.rowptr, self.colidx, self.vals, self.nrows, self.ncols, dense)
+        return spmm_cpp.csr_spmm(self.rowptr, self.colidx, self.vals, self.nrows, self.ncols, dense, self.rowidx)
 
     def transpose(self) -> "Adjacency":
         if self._t is None:
-            t_rowptr, t_colidx, t_vals = spmm_cpp.csr_transpose(self.rowptr, self.colidx, self.vals, self.nrows, self.ncols)
-            self._t = Adjacency(t_rowptr, t_colidx, t_vals, self.ncols, self.nrows)
+            t_rowptr, t_colidx, t_vals, t_rowidx = spmm_cpp.csr_transpose(self.rowptr, self.colidx, self.vals, self.nrows, self.ncols)
+            self._t = Adjacency(t_rowptr, t_colidx, t_vals, self.ncols, self.nrows, t_rowidx)
         return self._t
 
-    def matmul_t(self, dense: torch.Tensor) -> torch.Tensor:
-        """A^T . G   (backward, reference custom_sparse_ops.py:34)."""
+    def short_rows(self) -> bool:
+        return self.nnz < SCATTER_MEAN_ROW * max(self.nrows, 1)
+
+    def matmul_t(self, dense: torch.Tensor, mode: str = None) -> torch.Tensor:
+        """A^T . G   (backward, reference custom_sparse_ops.py:34); ``mode`` overrides the module-level BACKWARD."""
+        mode = mode or BACKWARD
+        if mode == "scatter" or (mode == "auto" and self._t is None and self.short_rows()):
+            return spmm_cpp.csr_spmm_t(self.rowptr, self.colidx, self.vals, self.nrows, self.ncols, dense, self.rowidx)
         return self.transpose().matmul(dense)
 
     def gather_matmul(self, xrows: torch.Tensor, feat_dim: int) -> torch.Tensor:
         """A . gather(xrows) without materialising the gathered rows (main.py:129-134 + models.py:18)."""
-        return spmm_cpp.gather_spmm(self.rowptr, self.colidx, self.vals, self.nrows, self.ncols, int(feat_dim), xrows)
+        return spmm_cpp.gather_spmm(self.rowptr, self.colidx, self.vals, self.nrows, self.ncols, int(feat_dim), xrows, self.rowidx)
 
 
 def adjacency_of(mat1: torch.Tensor) -> Adjacency:
@@ -114,6 +133,6 @@ spmm = SparseDenseMM.apply
 def create_coo_tensor(fullrowptr, rowptr, colidx, normfact, nrows, ncols):
     """Drop-in for ``spmm_cpp.create_coo_tensor`` (reference spmm.cpp:44-50): returns the coalesced
     sparse COO tensor [nrows, ncols] (int64 indices, fp32 values) with its CSR attached."""
-    coo, col32 = spmm_cpp.build_adj(fullrowptr, rowptr, colidx, normfact, int(nrows), int(ncols))
-    setattr(coo, _ATTR, Adjacency(rowptr, col32, coo._values(), nrows, ncols))
+    coo, col32, row32 = spmm_cpp.build_adj(fullrowptr, rowptr, colidx, normfact, int(nrows), int(ncols))
+    setattr(coo, _ATTR, Adjacency(rowptr, col32, coo._values(), nrows, ncols, row32))
     return coo

@@ -1,13 +1,21 @@
-"""Placement tables consumed by the gather (producer side kept minimal).
+"""Placement tables consumed by the feature gather, and the locality-sampling node sets.
 
-The reference computes them offline in ``create_buffer`` (preprocess.py:311-407); that
-code is out of scope as a subsystem, but its OUTPUT FORMAT is the input of the hot
-path, so the default (non-PaGraph, non-naive) branch is restated here to be able to
-produce tables on a box that does not have the reference: access probability
-``1^T L[train,:] L^(layers-1)`` (preprocess.py:343-345), the top ``buffer*world`` nodes
-cached, every GPU starting from the same top-``buffer`` set, then the greedy
-alpha-swap (preprocess.py:355-383).  Checked against tables captured from the
-reference in tests/test_placement_golden.py.
+The reference computes both offline (``create_buffer``, preprocess.py:311-407, default branch; and
+``get_skewed_sampled_nodes``, preprocess.py:414-423).  Their OUTPUT FORMAT is the input of the hot path
+(sampler.py:150-158 reads ``device_id_of_nodes`` / ``idx_of_nodes_on_device``; sampler.py:119-121 reads the skew sets),
+so a box without the reference needs a producer.  This one is organised differently from the reference's
+per-candidate Python loop:
+
+* access probability ``1^T L[train,:] L^(layers-1)`` by CSR row-vector products on the bare structure arrays;
+* the alpha test ``prob[candidate] >= alpha * prob[replaced]`` does not depend on the running device loads, so the
+  point where the reference's loop breaks is found up front with one vector comparison;
+* the only sequential part - every ``world-1`` candidates the devices are re-ranked by accumulated probability - runs
+  once per ROUND (``buffer`` rounds instead of ``buffer * (world-1)`` candidate steps), recording for each round the
+  device order; the table updates (all ranks' views, the per-rank "my replaced copy now lives on the device that kept
+  it" entries, the buffer slots) are then applied as whole-array assignments.
+
+Tables are bit-identical to the reference's (tests/test_placement_golden.py, fixtures captured from the unmodified
+reference for alpha = 0 and 0.5), including its tie-breaking (same ``np.argsort`` calls on the same values).
 """
 from __future__ import annotations
 
@@ -20,50 +28,111 @@ import numpy as np
 @dataclasses.dataclass
 class Placement:
     device_id_of_nodes_group: List[np.ndarray]      # per rank: holder device id per node, -1 = host
-    idx_of_nodes_on_device_group: List[np.ndarray]  # per rank (aliased): slot inside the holder's buffer
+    idx_of_nodes_on_device_group: List[np.ndarray]  # per rank (one shared array, like the reference): slot inside the holder's buffer
     gpu_buffer_group: List[np.ndarray]              # per device: node id of every slot
     sample_prob: np.ndarray
+    accepted: int = 0                               # candidates placed before the alpha test failed
+
+
+def _csr_parts(lap_matrix):
+    """(indptr, indices, data) of a scipy CSR matrix or of a (indptr, indices, data) tuple."""
+    if isinstance(lap_matrix, tuple):
+        return lap_matrix
+    return lap_matrix.indptr, lap_matrix.indices, lap_matrix.data
+
+
+def _vec_times_csr(v: np.ndarray, indptr: np.ndarray, indices: np.ndarray, data, n_cols: int) -> np.ndarray:
+    """Row vector times CSR matrix: out[c] = sum_r v[r] * A[r, c] (float64)."""
+    w = np.repeat(np.asarray(v, dtype=np.float64), np.diff(indptr))
+    if data is not None:
+        w = w * data
+    return np.bincount(indices, weights=w, minlength=n_cols)
 
 
 def access_probability(lap_matrix, train_nodes, num_conv_layers: int) -> np.ndarray:
-    prob = np.ones(len(train_nodes)) * lap_matrix[train_nodes, :]      # preprocess.py:343
-    for _ in range(num_conv_layers - 1):                               # :344-345
-        prob = prob * lap_matrix
-    return np.asarray(prob).ravel()
+    """reference preprocess.py:343-345: ``ones(len(train)) * L[train, :]`` then ``* L`` per further layer.
+
+    Same float64 additions in the same order as scipy's row-vector x CSR product (entries visited row by row, the
+    rows of ``L[train, :]`` in ``train_nodes`` order), so the probabilities - and therefore the ranking, ties
+    included - are bit-identical to the reference's."""
+    indptr, indices, data = _csr_parts(lap_matrix)
+    n = indptr.size - 1
+    train = np.asarray(train_nodes, dtype=np.int64)
+    starts, lens = indptr[train], indptr[train + 1] - indptr[train]
+    offs = np.zeros(train.size + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    entry = np.repeat(starts - offs[:-1], lens) + np.arange(int(offs[-1]), dtype=np.int64)      # entries of L[train, :]
+    prob = np.bincount(indices[entry], weights=None if data is None else data[entry].astype(np.float64), minlength=n).astype(np.float64)
+    for _ in range(num_conv_layers - 1):
+        prob = _vec_times_csr(prob, indptr, indices, data, n)
+    return prob
 
 
 def create_placement(lap_matrix, train_nodes, num_nodes_per_dev: int, devices: Sequence[int],
-                     num_conv_layers: int, alpha: float = 0.0) -> Placement:
-    num_devs = len(devices)
-    n = lap_matrix.shape[1]
-    sample_prob = access_probability(lap_matrix, train_nodes, num_conv_layers)
-    buffered_nodes = np.argsort(-1 * sample_prob)[:num_nodes_per_dev * num_devs]          # :346-347
-    idx_of_nodes_on_device = np.arange(n)                                                  # :355
-    gpu_buffer_group, device_id_of_nodes_group = [], []
-    for i in range(num_devs):                                                              # :356-362
-        device_id_of_nodes = np.array([-1] * n)
-        gpu_buffer_group.append(buffered_nodes[:num_nodes_per_dev].copy())
-        first = buffered_nodes[:num_nodes_per_dev]
-        device_id_of_nodes[first] = devices[i]
-        device_id_of_nodes_group.append(device_id_of_nodes.copy())
-        idx_of_nodes_on_device[first] = np.arange(len(first))
-    idx_group = [idx_of_nodes_on_device] * num_devs                                        # :364 (aliased on purpose)
-    p_accum = np.array([0.0] * num_devs)
-    device_order = np.argsort(p_accum)
-    for i in range(len(buffered_nodes) - num_nodes_per_dev):                               # :367-383
-        if i % (num_devs - 1) == 0:
-            device_order = np.argsort(p_accum)
-        candidate = buffered_nodes[num_nodes_per_dev + i]
-        new_idx = num_nodes_per_dev - 1 - i // (num_devs - 1)
-        replaced = buffered_nodes[new_idx]
-        if sample_prob[candidate] >= alpha * sample_prob[replaced]:
-            cur = device_order[i % (num_devs - 1)]
-            p_accum[cur] += sample_prob[candidate]
-            for j in range(num_devs):
-                device_id_of_nodes_group[j][candidate] = devices[cur]
-                idx_group[j][candidate] = new_idx
-            device_id_of_nodes_group[cur][replaced] = devices[device_order[-1]]
-            gpu_buffer_group[cur][new_idx] = candidate
-        else:
-            break
-    return Placement(device_id_of_nodes_group, idx_group, gpu_buffer_group, sample_prob)
+                     num_conv_layers: int, alpha: float = 0.0, sample_prob: np.ndarray | None = None) -> Placement:
+    world = len(devices)
+    devs = np.asarray(devices)
+    indptr = _csr_parts(lap_matrix)[0]
+    n = indptr.size - 1
+    if sample_prob is None:
+        sample_prob = access_probability(lap_matrix, train_nodes, num_conv_layers)
+    ranked = np.argsort(-1 * sample_prob)[:num_nodes_per_dev * world]
+    top, cand = ranked[:num_nodes_per_dev], ranked[num_nodes_per_dev:]
+
+    # start: every GPU holds the same top set, every rank sees those nodes on itself
+    views = []
+    for d in range(world):
+        view = np.full(n, -1, dtype=np.int64)
+        view[top] = devs[d]
+        views.append(view)
+    slot_of = np.arange(n)
+    slot_of[top] = np.arange(top.size)
+    buffers = [top.copy() for _ in range(world)]
+
+    accepted = 0
+    if world > 1 and cand.size:
+        per_round = world - 1
+        new_slot = num_nodes_per_dev - 1 - np.arange(cand.size) // per_round     # slot each candidate would take
+        replaced = ranked[new_slot]                                               # ... and the node it evicts there
+        passes = sample_prob[cand] >= alpha * sample_prob[replaced]
+        accepted = int(cand.size if passes.all() else np.argmin(passes))          # the reference breaks at the first failure
+        rounds = -(-accepted // per_round)
+        # the sequential part: device ranking at the start of each round
+        load = np.zeros(world)
+        holder = np.empty(accepted, dtype=np.int64)      # device index that takes candidate i
+        keeper = np.empty(rounds, dtype=np.int64)        # device index that receives nothing in round r and keeps the evicted node
+        cand_prob = sample_prob[cand[:accepted]]
+        for r in range(rounds):
+            order = np.argsort(load)
+            lo, hi = r * per_round, min((r + 1) * per_round, accepted)
+            holder[lo:hi] = order[:hi - lo]
+            keeper[r] = order[-1]
+            load[order[:hi - lo]] += cand_prob[lo:hi]
+        acc_cand, acc_slot, acc_replaced = cand[:accepted], new_slot[:accepted], replaced[:accepted]
+        for view in views:
+            view[acc_cand] = devs[holder]
+        slot_of[acc_cand] = acc_slot
+        round_of = np.arange(accepted) // per_round
+        for d in range(world):
+            mine = holder == d
+            views[d][acc_replaced[mine]] = devs[keeper[round_of[mine]]]
+            buffers[d][acc_slot[mine]] = acc_cand[mine]
+    return Placement(views, [slot_of] * world, buffers, sample_prob, accepted)
+
+
+def locality_sampling_sets(indptr: np.ndarray, indices: np.ndarray, has_self_loops: bool,
+                           gpu_buffer_group: Sequence[np.ndarray], num_layers: int, top: int = 8192) -> List[np.ndarray]:
+    """Node sets whose sampling probability ``--locality_sampling`` scales up (reference preprocess.py:414-423 on
+    ``adjacency + I``): layer 0 = every node cached on some GPU; layer i = the ``top`` nodes with the most i-hop
+    paths from cached nodes.  Tie order follows the same ``np.argsort(-1 * v)`` call on the same float64 counts."""
+    n = indptr.size - 1
+    sets = [np.unique(np.concatenate([np.asarray(b) for b in gpu_buffer_group]))]
+    v = np.zeros(n, dtype=np.float64)
+    v[sets[0]] = 1
+    for _ in range(1, num_layers):
+        nxt = _vec_times_csr(v, indptr, indices, None, n)
+        if not has_self_loops:
+            nxt = nxt + v                                  # the "+ I" of preprocess.py call site main.py:257
+        v = nxt
+        sets.append(np.argsort(-1 * v)[:top])
+    return sets

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GNN_B200_ABI_VERSION 1
+#define GNN_B200_ABI_VERSION 2
 
 #define GNN_E_BADARG   (-1)   /* null pointer, negative size, unsupported width */
 #define GNN_E_WORKSPACE (-2)  /* workspace missing or too small */
@@ -64,15 +64,18 @@ int gnn_host_gather_ctas(void);
  *     out_vals[i] = (float)( (1.0 / (double)(fullrowptr[r+1]-fullrowptr[r]))
  *                            * (double)normfact[colidx[i]] )      (cuda_spmm.cu:800)
  *     out_colidx32[i] = colidx[i]                        (int32 copy for the SpMM kernels)
+ *     out_rowidx32[i] = r                                (row id per entry: lets the short-row SpMM kernels skip the
+ *                                                         row search, see gnn_csr_spmm_f32_ex)
  * colidx is int16 when colidx_bytes == 2 (what sampler.py:136 uploads; read as
  * signed 16-bit exactly like cuda_spmm.cu:792) or int32 when colidx_bytes == 4.
- * out_indices and out_colidx32 may each be NULL to skip that output.
+ * out_indices, out_colidx32 and out_rowidx32 may each be NULL to skip that output.
  * Rows are already sorted and (row,col) pairs unique, so the result is coalesced
  * without the reference's trailing .coalesce() (cuda_spmm.cu:825).
  * ------------------------------------------------------------------------- */
 int gnn_build_adj(const int32_t *fullrowptr, const int32_t *rowptr, const void *colidx, int colidx_bytes,
                   const float *normfact, int64_t M, int64_t K, int64_t nnz,
-                  int64_t *out_indices, float *out_vals, int32_t *out_colidx32, gnn_stream_t stream);
+                  int64_t *out_indices, float *out_vals, int32_t *out_colidx32, int32_t *out_rowidx32,
+                  gnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * gnn_coo_to_csr - coalesced COO (int64 [2,nnz], row-major sorted) -> CSR int32.
@@ -105,6 +108,40 @@ int gnn_csr_spmm_f32(const int32_t *rowptr, const int32_t *colidx, const float *
                      const float *X, int64_t ldx, float *Y, int64_t ldy,
                      void *workspace, size_t workspace_bytes, gnn_stream_t stream);
 
+/* Same product with the two workspace regions passed separately, for callers that keep ONE long-lived workspace per
+ * stream (spmm_ext.cpp does): `counters` (gnn_csr_spmm_counter_bytes) holds one arrival counter per (row, column slab)
+ * for rows whose nonzeros span several warp chunks, `partials` (gnn_csr_spmm_partial_bytes) their partial sums.
+ * The counters wrap back to zero inside the kernel, so a counter region that is all-zero on entry is all-zero again
+ * when the call has completed: pass GNN_SPMM_COUNTERS_ZEROED to skip the memset (one launch per SpMM instead of the
+ * reference's >= 8, cuda_spmm.cu:619-704).  Without the flag the contents of both regions are undefined on entry.
+ * The regions must not be shared by calls that may run concurrently (different streams).
+ * `rowidx` (optional, may be NULL): int32 row id of every stored entry, as gnn_build_adj / gnn_csr_transpose emit
+ * them.  Short-row blocks (top LADIES layer, sparse graphs) are latency-bound: with row ids a warp needs one round trip
+ * - (col, val, row) of its chunk - before its X loads go out, instead of a search over the row pointer. */
+#define GNN_SPMM_COUNTERS_ZEROED 1u
+size_t gnn_csr_spmm_counter_bytes(int64_t M, int64_t nnz, int64_t D);
+size_t gnn_csr_spmm_partial_bytes(int64_t M, int64_t nnz, int64_t D);
+
+int gnn_csr_spmm_f32_ex(const int32_t *rowptr, const int32_t *rowidx, const int32_t *colidx, const float *vals,
+                        int64_t M, int64_t K, int64_t nnz, int64_t D,
+                        const float *X, int64_t ldx, float *Y, int64_t ldy,
+                        int32_t *counters, void *partials, size_t partial_bytes, unsigned flags, gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * gnn_csr_spmm_t_f32 - transpose-free backward: dX[K,D] = A^T . G from A's own CSR.
+ *
+ * Replaces custom_sparse_ops.py:30-37 (transpose(0,1).coalesce() + the forward pipeline) without any transposed
+ * index: dX is zero-filled, then every stored entry (r, c, v) adds v * G[r, :] into dX[c, :] with vector reductions
+ * (red.global.add.v4.f32 when G, dX and both leading dimensions are 16-byte aligned, scalar reductions otherwise).
+ * The additions of one output row arrive in no fixed order: results are reproducible to rounding only, like the
+ * reference's atomicAdd kernel (cuda_spmm.cu:205-209).  Faster than gnn_csr_transpose + gnn_csr_spmm_f32 for sparse
+ * layers (the index build is four dependent launches), slower on dense LADIES blocks (profiles/ has the table).
+ * rowidx: optional row id per entry (see gnn_csr_spmm_f32_ex).  No workspace.
+ * ------------------------------------------------------------------------- */
+int gnn_csr_spmm_t_f32(const int32_t *rowptr, const int32_t *rowidx, const int32_t *colidx, const float *vals,
+                       int64_t M, int64_t K, int64_t nnz, int64_t D,
+                       const float *G, int64_t ldg, float *dX, int64_t lddx, gnn_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * gnn_gather_spmm_f32 - fused input-feature gather + SpMM for the deepest layer:
  *     Y[M,D] = A[M,K] . Xg,   Xg[j,:] = *(xrows[j])   (row j never materialised)
@@ -120,6 +157,10 @@ int gnn_gather_spmm_f32(const int32_t *rowptr, const int32_t *colidx, const floa
                         int64_t M, int64_t K, int64_t nnz, int64_t D,
                         const float *const *xrows, float *Y, int64_t ldy,
                         void *workspace, size_t workspace_bytes, gnn_stream_t stream);
+int gnn_gather_spmm_f32_ex(const int32_t *rowptr, const int32_t *rowidx, const int32_t *colidx, const float *vals,
+                           int64_t M, int64_t K, int64_t nnz, int64_t D,
+                           const float *const *xrows, float *Y, int64_t ldy,
+                           int32_t *counters, void *partials, size_t partial_bytes, unsigned flags, gnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * gnn_csr_transpose - CSR of A^T (entries of each output row in ascending source
@@ -130,13 +171,21 @@ int gnn_gather_spmm_f32(const int32_t *rowptr, const int32_t *colidx, const floa
  * The backward product dX = A^T.G is then gnn_csr_spmm_f32 on the result.
  * Deterministic: no atomics decide the order.
  *
- * workspace: gnn_csr_transpose_workspace_bytes(M, K, nnz) bytes.
+ * Precondition: (row, column) pairs are unique, i.e. the input is coalesced (what spmm.cpp:12-13 demands of every
+ * sparse operand); a duplicate pair would set the same bitmap bit twice and corrupt the positions after it.
+ *
+ * workspace: gnn_csr_transpose_workspace_bytes(M, K, nnz) bytes: two K-int arrays plus a column-major row bitmap
+ * of K * ceil(rows/32) * 8 bytes.  The bitmap never exceeds the budget (default 512 MiB): larger matrices
+ * (products / papers-scale samp_num, ~130 K x 130 K and up) are transposed in blocks of rows, block after block,
+ * with a per-column cursor - same result, more launches.  gnn_set_transpose_budget changes the budget
+ * (process-wide; 0 restores the default; returns the previous value); query the workspace size after setting it.
  * ------------------------------------------------------------------------- */
+int64_t gnn_set_transpose_budget(int64_t bytes);
 size_t gnn_csr_transpose_workspace_bytes(int64_t M, int64_t K, int64_t nnz);
 
 int gnn_csr_transpose(const int32_t *rowptr, const int32_t *colidx, const float *vals,
                       int64_t M, int64_t K, int64_t nnz,
-                      int32_t *t_rowptr, int32_t *t_colidx, float *t_vals,
+                      int32_t *t_rowptr, int32_t *t_colidx, float *t_vals, int32_t *t_rowidx /* optional: row id per entry of A^T */,
                       void *workspace, size_t workspace_bytes, gnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------
@@ -236,6 +285,19 @@ int gnn_elu_rownorm_fwd_f32(const float *x, int64_t ldx, int64_t M, int64_t C, c
 int gnn_elu_rownorm_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx, int64_t M, int64_t C,
                             const float *scale, const float *mean, const float *rstd, float *dx, int64_t lddx,
                             float *dscale, float *doffset, void *workspace, size_t workspace_bytes, gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * gnn_probe_row_gather_f32 - measurement aid (bench.py): the row gather of an SpMM and nothing else.
+ *
+ * Every warp walks a stretch of `colidx` (the block's own column stream) and loads the addressed rows of X
+ * (float4 per lane, nv = 1, 2 or 4 vectors per lane, several rows in flight), adding them up; no values, no row
+ * bookkeeping, no stores.  `warps_per_sm` resident warps per SM share the stream; *bytes_gathered (host pointer,
+ * written before return) = bytes the launch requests from L2.  Timing it on the benchmark's own blocks gives the
+ * L2->SM gather speed of light that bounds any row-wise fp32 SpMM on a dense LADIES block.
+ * X: [K, ldx] floats, 16-byte aligned rows, D >= 128*nv; sink: one float (never written in practice).
+ * ------------------------------------------------------------------------- */
+int gnn_probe_row_gather_f32(const float *X, int64_t ldx, int64_t D, const int32_t *colidx, int64_t nnz, int nv,
+                             int warps_per_sm, float *sink, int64_t *bytes_gathered, gnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Feature-shard memory that peers can map (one process per GPU).

@@ -22,15 +22,18 @@ def dev(a, dtype=None):
     return t.cuda()
 
 
-def build_adj(fullrowptr, rowptr, colidx, normfact, M, K, want_indices=True):
+def build_adj(fullrowptr, rowptr, colidx, normfact, M, K, want_indices=True, want_rows=False):
     lib = _native.cabi()
     nnz = int(colidx.numel())
     idx = torch.empty((2, nnz), dtype=torch.int64, device="cuda") if want_indices else None
     vals = torch.empty(nnz, dtype=torch.float32, device="cuda")
     col32 = torch.empty(nnz, dtype=torch.int32, device="cuda")
+    row32 = torch.full((nnz,), -7, dtype=torch.int32, device="cuda") if want_rows else None
     rc = lib.gnn_build_adj(_ptr(fullrowptr), _ptr(rowptr), _ptr(colidx), colidx.element_size(), _ptr(normfact), M, K, nnz,
-                           _ptr(idx), _ptr(vals), _ptr(col32), _stream())
+                           _ptr(idx), _ptr(vals), _ptr(col32), _ptr(row32), _stream())
     _native.check(rc, "gnn_build_adj")
+    if want_rows:
+        return idx, vals, col32, row32
     return idx, vals, col32
 
 
@@ -61,7 +64,7 @@ def gather_spmm(rowptr, colidx, vals, M, K, D, xrows):
     return Y
 
 
-def csr_transpose(rowptr, colidx, vals, M, K):
+def csr_transpose(rowptr, colidx, vals, M, K, want_rows=False):
     lib = _native.cabi()
     nnz = int(vals.numel())
     t_rowptr = torch.empty(K + 1, dtype=torch.int32, device="cuda")
@@ -69,9 +72,12 @@ def csr_transpose(rowptr, colidx, vals, M, K):
     t_vals = torch.empty(nnz, dtype=torch.float32, device="cuda")
     wsb = lib.gnn_csr_transpose_workspace_bytes(M, K, nnz)
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    t_rowidx = torch.full((nnz,), -7, dtype=torch.int32, device="cuda") if want_rows else None
     rc = lib.gnn_csr_transpose(_ptr(rowptr), _ptr(colidx), _ptr(vals), M, K, nnz, _ptr(t_rowptr), _ptr(t_colidx), _ptr(t_vals),
-                               _ptr(ws), wsb, _stream())
+                               _ptr(t_rowidx), _ptr(ws), wsb, _stream())
     _native.check(rc, "gnn_csr_transpose")
+    if want_rows:
+        return t_rowptr, t_colidx, t_vals, t_rowidx
     return t_rowptr, t_colidx, t_vals
 
 
@@ -113,3 +119,33 @@ def index_rows(X, idx):
     out = torch.empty((n, F), dtype=torch.float32, device="cuda")
     _native.check(lib.gnn_index_rows_f32(_ptr(X), X.stride(0), _ptr(idx), n, F, _ptr(out), F, _stream()), "gnn_index_rows_f32")
     return out
+
+
+def csr_spmm_ex(rowptr, colidx, vals, M, K, X, counters, partials, zeroed, ldx=None, rowidx=None):
+    """gnn_csr_spmm_f32_ex with caller-owned counter / partial regions (uint8 tensors)."""
+    lib = _native.cabi()
+    D = X.shape[1]
+    ldx = ldx if ldx is not None else X.stride(0)
+    nnz = int(vals.numel())
+    Y = torch.full((M, D), float("nan"), dtype=torch.float32, device="cuda")
+    rc = lib.gnn_csr_spmm_f32_ex(_ptr(rowptr), _ptr(rowidx), _ptr(colidx), _ptr(vals), M, K, nnz, D, _ptr(X), ldx, _ptr(Y), D,
+                                 _ptr(counters), _ptr(partials), int(partials.numel()), 1 if zeroed else 0, _stream())
+    _native.check(rc, "gnn_csr_spmm_f32_ex")
+    return Y
+
+
+def csr_spmm_t(rowptr, colidx, vals, M, K, G, lddx=None, rowidx=None):
+    """gnn_csr_spmm_t_f32: dX = A^T.G from A's CSR (transpose-free)."""
+    lib = _native.cabi()
+    D = G.shape[1]
+    nnz = int(vals.numel())
+    lddx = lddx or D
+    dX = torch.full((K, lddx), float("nan"), dtype=torch.float32, device="cuda")
+    rc = lib.gnn_csr_spmm_t_f32(_ptr(rowptr), _ptr(rowidx), _ptr(colidx), _ptr(vals), M, K, nnz, D, _ptr(G), G.stride(0) if M > 1 else D,
+                                _ptr(dX), lddx, _stream())
+    _native.check(rc, "gnn_csr_spmm_t_f32")
+    return dX
+
+
+def set_transpose_budget(nbytes):
+    return _native.cabi().gnn_set_transpose_budget(int(nbytes))

@@ -36,12 +36,22 @@ def test_header_symbols_exported(built):
 
 def test_abi_version_and_errors(built):
     lib = built.cabi()
-    assert lib.gnn_abi_version() == 1
+    assert lib.gnn_abi_version() == 2
     assert b"workspace" in lib.gnn_error_string(-2)
     assert lib.gnn_error_string(0) == b"success"
     # argument errors are reported before any CUDA call
-    assert lib.gnn_build_adj(None, None, None, 3, None, 4, 4, 4, None, None, None, None) == -1
+    assert lib.gnn_build_adj(None, None, None, 3, None, 4, 4, 4, None, None, None, None, None) == -1
     assert lib.gnn_csr_spmm_f32(None, None, None, -1, 1, 1, 1, None, 1, None, 1, None, 0, None) == -1
+    assert lib.gnn_csr_spmm_f32_ex(None, None, None, None, 1, 1, 1, 1, None, 1, None, 1, None, None, 0, 2, None) == -1   # unknown flag
+    assert lib.gnn_csr_spmm_t_f32(None, None, None, None, -1, 1, 1, 1, None, 1, None, 1, None) == -1
+    assert (lib.gnn_csr_spmm_counter_bytes(100, 1000, 64) + lib.gnn_csr_spmm_partial_bytes(100, 1000, 64)
+            == lib.gnn_csr_spmm_workspace_bytes(100, 1000, 64))
+    # transpose bitmap budget: process-wide knob, returns the previous value; the workspace never exceeds budget + tables
+    prev = lib.gnn_set_transpose_budget(1 << 20)
+    assert prev == 512 << 20
+    assert lib.gnn_csr_transpose_workspace_bytes(200000, 150000, 10) <= (1 << 20) + 150000 * 8 + 150000 * 8 + 4096
+    assert lib.gnn_set_transpose_budget(0) == 1 << 20
+    assert lib.gnn_set_transpose_budget(-5) == -1
     assert lib.gnn_csr_spmm_workspace_bytes(100, 1000, 64) >= 2 * (1000 // 64) * 64 * 4
     assert lib.gnn_csr_transpose_workspace_bytes(64, 10, 5) >= 10 * 2 * 4
     # planner hint: returns the previous value, rejects negatives, no CUDA call involved

@@ -126,19 +126,22 @@ def test_cuda_graph_capture_and_stream_semantics(cso, mb):
     adj = cso.adjacency_of(a)
     x = torch.randn(layer.ncols, 128, device="cuda")
     go = torch.randn(layer.nrows, 128, device="cuda")
-    y_ref, dx_ref = adj.matmul(x), adj.matmul_t(go)
+    y_ref, dx_ref = adj.matmul(x), adj.matmul_t(go, mode="index")
     adj._t = None
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         y = adj.matmul(x)
-        dx = adj.matmul_t(go)          # includes the A^T build
+        dx = adj.matmul_t(go, mode="index")          # includes the A^T build
+        adj._t = None
+        dxs = adj.matmul_t(go, mode="scatter")       # transpose-free: zero fill + reductions, capturable too
     for _ in range(3):
         x.normal_()
         go.normal_()
         graph.replay()
         torch.cuda.synchronize()
-        assert torch.equal(y, adj.matmul(x)) and torch.equal(dx, adj.matmul_t(go))
+        assert torch.equal(y, adj.matmul(x)) and torch.equal(dx, adj.matmul_t(go, mode="index"))
+        assert torch.allclose(dxs, dx, rtol=1e-4, atol=1e-5)
     assert y_ref.shape == y.shape and dx_ref.shape == dx.shape
 
 

@@ -60,10 +60,11 @@ def _layer_csr(layer):
 @pytest.mark.parametrize("name", ["cora_gcn", "tiny_sage3", "tiny_order0"])
 def test_build_adj_bit_exact(cu, golden_dir, name):
     for L in _golden_layers(golden_dir, name):
-        idx, vals, col32 = cu.build_adj(cu.dev(L["fullrowptr"]), cu.dev(L["rowptr"]), cu.dev(L["colidx"]), cu.dev(L["normfact"]),
-                                        L["nrows"], L["ncols"])
+        idx, vals, col32, row32 = cu.build_adj(cu.dev(L["fullrowptr"]), cu.dev(L["rowptr"]), cu.dev(L["colidx"]), cu.dev(L["normfact"]),
+                                               L["nrows"], L["ncols"], want_rows=True)
         rows, cols, ovals = oracle.build_adj(L["fullrowptr"], L["rowptr"], L["colidx"], L["normfact"], L["nrows"])
         assert np.array_equal(idx[0].cpu().numpy(), rows)
+        assert np.array_equal(row32.cpu().numpy(), rows.astype(np.int32))
         assert np.array_equal(idx[1].cpu().numpy(), cols)
         assert np.array_equal(col32.cpu().numpy(), cols.astype(np.int32))
         got = vals.cpu().numpy()
@@ -320,7 +321,7 @@ def test_error_codes_and_workspace_contract(cu):
     torch.cuda.synchronize()
     assert Y.tolist() == [[3.0] * 8, [3.0] * 8]
     assert lib.gnn_csr_spmm_f32(P(rowptr), P(col), P(vals), 2, 2, 3, 1 << 25, P(X), 1 << 25, P(Y), 1 << 25, P(ws), need, st) == -3   # D limit
-    assert lib.gnn_build_adj(P(rowptr), P(rowptr), P(col), 8, P(vals), 2, 2, 3, None, P(vals), None, st) == -1       # colidx width
+    assert lib.gnn_build_adj(P(rowptr), P(rowptr), P(col), 8, P(vals), 2, 2, 3, None, P(vals), None, None, st) == -1       # colidx width
 
 
 def test_int32_columns_beyond_int16_range(cu):
@@ -356,7 +357,7 @@ def test_concurrent_threads_and_streams(cu, small_mb):
     G = torch.randn(layer.nrows, 100, device="cuda")
     a0 = cso.create_coo_tensor(*args, layer.nrows, layer.ncols)
     y0 = cso.adjacency_of(a0).matmul(X)
-    d0 = cso.adjacency_of(a0).matmul_t(G)
+    d0 = cso.adjacency_of(a0).matmul_t(G, mode="index")
     torch.cuda.synchronize()
     results, errors = {}, []
 
@@ -367,9 +368,11 @@ def test_concurrent_threads_and_streams(cu, small_mb):
                 for _ in range(5):
                     a = cso.create_coo_tensor(*args, layer.nrows, layer.ncols)
                     adj = cso.adjacency_of(a)
-                    y, d = adj.matmul(X), adj.matmul_t(G)
+                    ds = adj.matmul_t(G, mode="scatter")          # transpose-free: same value up to summation order
+                    y, d = adj.matmul(X), adj.matmul_t(G, mode="index")
                 s.synchronize()
-            results[tid] = (torch.equal(y, y0), torch.equal(d, d0), torch.equal(a._values(), a0._values()))
+            results[tid] = (torch.equal(y, y0), torch.equal(d, d0), torch.equal(a._values(), a0._values()),
+                            torch.allclose(ds, d0, rtol=1e-4, atol=1e-5))
         except Exception as exc:  # noqa: BLE001
             errors.append(exc)
 

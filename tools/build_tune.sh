@@ -4,5 +4,5 @@
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p tools/_build
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC -Iinclude -DGNN_TUNE \
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC -Xlinker -Bsymbolic -Iinclude -DGNN_TUNE \
      -Ignn_b200/csrc -o tools/_build/libgnn_b200_tune.so gnn_b200/csrc/gnn_kernels.cu
