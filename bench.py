@@ -38,9 +38,9 @@ sys.path.insert(0, REPO)
 
 ORDERS = [1, 1, 1]
 NHID = 512
-# Measured on this pool's B200 (profiles/gather_roof_r1.txt): a kernel that only performs the SpMM's row gather
-# (same column stream, float4 loads, no FMA/stores) tops out at ~20 TB/s of L2->SM traffic.
-L2_GATHER_ROOF_BPS = 20.0e12
+# The L2->SM row-gather roof is MEASURED in every run (measure_gather_roof: the production library's probe kernel on the
+# dominant block's own column stream); this constant is only the fallback when the probe cannot run.
+L2_GATHER_ROOF_FALLBACK_BPS = 18.0e12
 
 
 # ----------------------------------------------------------------------------- workload
@@ -87,6 +87,116 @@ def block_stats(mb, widths):
                     "row_nnz_mean": round(float(rl.mean()), 1), "row_nnz_max": int(rl.max()),
                     "density": round(layer.nnz / (layer.nrows * layer.ncols), 5)})
     return out
+
+
+def make_config(shape, g, mbs, widths, samp, batch):
+    """`config` of the JSON line - identical keys in the product arm and in the reference arm."""
+    return {"workload": f"{shape.name}-shaped {'GCN' if shape.self_loops else 'GraphSAGE'} LADIES samp_num {samp} batch {batch}"
+                        + (" (BASELINE configs[1])" if shape.name == "reddit" else ""),
+            "graph": {"nodes": g.num_nodes, "directed_nnz": g.nnz, "feat_dim": shape.feat_dim, "alpha": shape.alpha,
+                      "max_degree": int(g.degrees().max())},
+            "blocks": block_stats(mbs[0], widths), "minibatches_rotated": len(mbs),
+            "l2": "flushed between steps (384 MiB write + 384 MiB read) and inputs rotate over >L2 working sets",
+            "sharding": "each rank its own minibatches, no data-path collective in `value`",
+            "bwd_includes": "everything a backward needs from a fresh adjacency: the CSR-of-A^T build (dense blocks) or the "
+                            "zero fill of the transpose-free path (short-row blocks)"}
+
+
+# ----------------------------------------------------------------------------- parity gate
+GATE_TOL = 1e-5
+GATE_ROWS = 1024
+
+
+def _row_sample(rowptr, cols, vals, rows):
+    """Sub-CSR of the given rows (host numpy)."""
+    lens = (rowptr[rows + 1] - rowptr[rows]).astype(np.int64)
+    sub = np.zeros(rows.size + 1, dtype=np.int32)
+    np.cumsum(lens, out=sub[1:])
+    take = np.repeat(rowptr[rows].astype(np.int64) - sub[:-1], lens) + np.arange(int(sub[-1]), dtype=np.int64)
+    return sub, cols[take], vals[take]
+
+
+def parity_gate(mb, widths, dev_mb, store, device, log):
+    """Before anything is timed: the operands of the TIMED minibatch 0 through the product path vs the CPU oracle.
+
+    * adjacency values of every layer bit-equal to oracle.build_adj (reference cuda_spmm.cu:787-803);
+    * every timed op (fwd of each layer, bwd of layers >= 1) on GATE_ROWS evenly spaced output rows vs the oracle's
+      fp64-accumulated product (reference custom_sparse_ops.py:16-37), worst-row relative L2 <= 1e-5;
+    * the gathered input features of the minibatch bit-equal to feats[input_nodes] (reference main.py:129-134).
+    The oracle is the checker here, never the thing measured."""
+    import torch
+    import oracle
+    adjs, xs, gs = dev_mb
+    checks, ok = [], True
+    host = []
+    for li, (layer, D) in enumerate(zip(mb.layers, widths)):
+        _, cols, vals = oracle.build_adj(layer.fullrowptr, layer.rowptr, layer.colidx32, layer.normfact, layer.nrows)
+        cols = cols.astype(np.int32)
+        same = bool(np.array_equal(adjs[li].vals.cpu().numpy().view(np.uint32), vals.view(np.uint32)))
+        checks.append({"op": f"adj{li}", "values_bit_exact": same})
+        ok &= same
+        host.append((cols, vals))
+    for li, (layer, D) in enumerate(zip(mb.layers, widths)):
+        cols, vals = host[li]
+        X = xs[li].cpu().numpy()
+        rows = np.unique(np.linspace(0, layer.nrows - 1, min(GATE_ROWS, layer.nrows)).astype(np.int64))
+        sub = _row_sample(layer.rowptr, cols, vals, rows)
+        ref = oracle.spmm_f64acc(sub[0], sub[1], sub[2], rows.size, np.ascontiguousarray(X))
+        got = adjs[li].matmul(xs[li])[torch.from_numpy(rows).to(device)].cpu().numpy()
+        err = oracle.rel_err(got, ref)[0]
+        checks.append({"op": f"fwd{li}", "rows_checked": int(rows.size), "worst_row_rel_err": float(f"{err:.3e}")})
+        ok &= err <= GATE_TOL
+        if li == 0:
+            continue
+        t_rowptr, t_col, perm = oracle.csr_transpose(layer.rowptr, cols, layer.nrows, layer.ncols)
+        crow = np.unique(np.linspace(0, layer.ncols - 1, min(GATE_ROWS, layer.ncols)).astype(np.int64))
+        subt = _row_sample(t_rowptr, t_col, vals[perm], crow)
+        G = gs[li].cpu().numpy()
+        reft = oracle.spmm_f64acc(subt[0], subt[1], subt[2], crow.size, np.ascontiguousarray(G))
+        adjs[li]._t = None
+        gott = adjs[li].matmul_t(gs[li])[torch.from_numpy(crow).to(device)].cpu().numpy()
+        adjs[li]._t = None
+        errt = oracle.rel_err(gott, reft)[0]
+        checks.append({"op": f"bwd{li}", "rows_checked": int(crow.size), "worst_row_rel_err": float(f"{errt:.3e}")})
+        ok &= errt <= GATE_TOL
+    if store is not None:
+        nodes = torch.from_numpy(mb.input_nodes).to(device)
+        x0 = store.gather(nodes).cpu().numpy()
+        want = store.host_rows(mb.input_nodes)
+        same = bool(np.array_equal(x0.view(np.uint32), want.view(np.uint32)))
+        _, _, _, counts = store.remap(nodes)
+        c = counts.cpu().numpy()
+        checks.append({"op": "gather", "rows": int(nodes.numel()), "bit_exact": same,
+                       "rows_by_source": {"gpu_shards": [int(v) for v in c[:store.world]], "host": int(c[store.world])}})
+        ok &= same
+    log("parity gate: " + json.dumps(checks))
+    return {"passed": bool(ok), "tolerance": GATE_TOL, "checks": checks,
+            "checker": "oracle/ (CPU restatement of the reference, fp64 accumulation), on the operands of timed minibatch 0"}
+
+
+def measure_gather_roof(ext, X, colidx, flush_l2):
+    """L2->SM row-gather speed of light on THIS GPU, on the dominant block's own column stream (the production
+    library's probe kernel: loads only, no FMA, no stores).  Best of a few layouts; TB/s."""
+    import torch
+    best, detail = 0.0, {}
+    Xp = X if (X.stride(0) % 4 == 0 and X.data_ptr() % 16 == 0) else X.contiguous()
+    for nv, wps in [(4, 32), (4, 16), (2, 32), (1, 32), (1, 64)]:
+        if Xp.shape[1] < 128 * nv:
+            continue
+        ts = []
+        for rep in range(4):
+            flush_l2()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            nbytes = ext.probe_row_gather(Xp, colidx, nv, wps)
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                ts.append(e0.elapsed_time(e1))
+        tbps = nbytes / (float(np.median(ts)) * 1e-3) / 1e12
+        detail[f"nv{nv}_w{wps}"] = round(tbps, 2)
+        best = max(best, tbps)
+    return best, detail
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -223,7 +333,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true")
-    ap.add_argument("--ref-gpu", action="store_true", help="also time the reference's CUDA kernels from oracle/_ref")
+    ap.add_argument("--ref-gpu", action="store_true", help="(default on) time the reference's CUDA kernels from oracle/_ref")
+    ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip BASELINE configs[3]/[4] (products GCN + locality, papers sweep)")
+    ap.add_argument("--papers-scale", type=int, default=16, help="papers100M-shaped graph at 1/scale of the nodes and edges")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
@@ -290,6 +403,24 @@ def main():
         dev_mbs.append((adjs, xs, gs))
     step_bytes = [sum(algorithmic_bytes(l.nnz, l.nrows, l.ncols, D) * (1 if li == 0 else 2)
                       for li, (l, D) in enumerate(zip(mb.layers, widths))) for mb in mbs]
+
+    # ---- placement-partitioned feature store (needed by the gate's gather check, e2e and train)
+    store = None
+    if not (args.no_e2e and args.no_train):
+        store = build_store(args, gmod, shape, g, device, rank, world, log)
+
+    # ---- parity gate on the operands of timed minibatch 0, on every rank, BEFORE anything is timed
+    gate = parity_gate(mbs[0], widths, dev_mbs[0], store, device, log)
+    gate_ok = torch.tensor([1.0 if gate["passed"] else 0.0], device=device)
+    if world > 1:
+        dist.all_reduce(gate_ok, op=dist.ReduceOp.MIN)
+    if gate_ok.item() < 1.0:
+        if rank == 0 or not gate["passed"]:
+            print(f"[bench r{rank}] PARITY GATE FAILED - no number is reported: {json.dumps(gate)}", file=sys.stderr, flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return 3
+    gate["ranks_passed"] = world
 
     flush_buf = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=device)   # 3x L2
     flush_src = torch.zeros(96 * 1024 * 1024, dtype=torch.int32, device=device)   # 384 MiB, read-only
@@ -401,6 +532,14 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     sm_clk_ghz = (clk["sm_mhz"] if clk and clk["sm_mhz"] > 0 else 1965.0) / 1e3
+    # L2->SM gather speed of light, measured now, on the largest forward block of timed minibatch 0
+    big = max(range(nl), key=lambda li: mbs[0].layers[li].nnz * widths[li])
+    try:
+        gather_roof_tbps, gather_roof_detail = measure_gather_roof(ext, dev_mbs[0][1][big], dev_mbs[0][0][big].colidx, flush_l2)
+        gather_roof_src = "measured in this run (gnn_probe_row_gather_f32 on the block's own column stream, cold L2)"
+    except Exception as exc:                             # the headline must not die with the probe
+        gather_roof_tbps, gather_roof_detail = L2_GATHER_ROOF_FALLBACK_BPS / 1e12, {"error": str(exc)[:200]}
+        gather_roof_src = "fallback constant"
     ops = []
     for k, name in enumerate(op_names):
         li = int(name[3:])
@@ -409,11 +548,12 @@ def main():
         nnzD = np.array([mbs[s % len(mbs)].layers[li].nnz * widths[li] for s in range(args.steps)], dtype=np.float64)
         ms = op_ms[:, k]
         t_hbm = bytes_k.mean() / (hbm_peak * 1e9)
-        t_l2 = 4 * nnzD.mean() / L2_GATHER_ROOF_BPS                            # gather bytes / measured pure-gather roof
+        t_l2 = 4 * nnzD.mean() / (gather_roof_tbps * 1e12)                     # gather bytes / measured pure-gather roof
         t_fma = nnzD.mean() / (148 * 128 * sm_clk_ghz * 1e9)
         ops.append({"op": name, "ms": round(float(ms.mean()), 4), "ms_median": round(float(np.median(ms)), 4),
                     "ms_max": round(float(ms.max()), 4), "share": round(float(ms.sum() / op_ms.sum()), 4),
                     "algorithmic_GBps": round(float(bytes_k.sum() / (ms.sum() * 1e-3) / 1e9), 1),
+                    "frac_of_hbm_roof": round(float(bytes_k.sum() / (ms.sum() * 1e-3) / 1e9 / hbm_peak), 4),
                     "bytes": int(bytes_k.mean()), "gather_GB": round(float(4 * nnzD.mean() / 1e9), 3),
                     "gflop": round(float(2 * nnzD.mean() / 1e9), 3),
                     "t_bound_us": {"hbm": round(t_hbm * 1e6, 1), "l2_gather": round(t_l2 * 1e6, 1), "fma": round(t_fma * 1e6, 1)},
@@ -423,8 +563,11 @@ def main():
                 "peak": hbm_peak, "unit": "GB/s", "frac": round(dom["algorithmic_GBps"] / hbm_peak, 4), "traffic": None,
                 "peak_source": peak_src, "binding_roof": max(dom["t_bound_us"], key=dom["t_bound_us"].get),
                 "frac_of_binding_roof": dom["frac_of_t_bound"],
-                "binding_roof_note": "l2_gather = 4*nnz*D bytes requested from L2 / 20 TB/s, the measured speed of light of a "
-                                     "pure row-gather kernel on this GPU (profiles/gather_roof_r1.txt)"}
+                "l2_gather_roof_measured_TBps": round(gather_roof_tbps, 2), "l2_gather_roof_layouts_TBps": gather_roof_detail,
+                "l2_gather_roof_source": gather_roof_src,
+                "binding_roof_note": "a row-wise fp32 SpMM on a dense LADIES block re-reads every X row nnz/K (~100-160) times "
+                                     "from L2; l2_gather = 4*nnz*D bytes / the gather-only speed of light measured above "
+                                     "(SURVEY.md 8(d): HBM is not the binding roof of these blocks; it is for the short-row ones)"}
     prof = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
@@ -433,27 +576,25 @@ def main():
             pass
 
     # ---- end-to-end through the public API with host inputs
-    e2e, train, store = None, None, None
-    if not (args.no_e2e and args.no_train):
-        store = build_store(args, gmod, shape, g, device, rank, world, log)
+    e2e, train = None, None
     if not args.no_e2e:
         e2e = run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
 
     # ---- training minibatches/s (full step incl. NCCL allreduce), secondary metric of BASELINE.json
-    if not args.no_train and shape.self_loops:
-        train = {"skipped": "the training harness restates the GraphSAGE model only; GCN shapes report the SpMM path"}
-    elif not args.no_train:
+    if not args.no_train:
         from gnn_b200 import harness
         # reference-shaped model first (the reference's own models.py would run exactly these torch ops), then the
-        # same model with the fused ELU+row-norm epilogue of gnn_b200/models.py
+        # same model with the fused ELU+row-norm epilogue of gnn_b200/models.py and the
+        # flat-gradient clip + exchange
         train = harness.bench_train(args, cso, store, shape, g, mbs, ORDERS, NHID, device, rank, world, log)
         # sampler threads per GPU: the reference's default --pool_num is 4 (main.py:77); with the host cores to spare
         # (>= 2 per thread and rank) the second live number uses 8, since 4 threads x 26 ms per minibatch is sampler-bound
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
         pool_wide = 8 if cores // max(world, 1) >= 16 else 4
         for key, fn, kw in [("fused_epilogue_model", harness.bench_train, dict(fused=True)),
+                            ("fused_epilogue_flat_gradients", harness.bench_train, dict(fused=True, flat_grads=True)),
                             ("live_sampler", harness.bench_train_live, dict(fused=False, pool_num=4)),
-                            ("live_sampler_fused_epilogue", harness.bench_train_live, dict(fused=True, pool_num=pool_wide))]:
+                            ("live_sampler_fused_epilogue", harness.bench_train_live, dict(fused=True, pool_num=pool_wide, flat_grads=True))]:
             try:
                 if fn is harness.bench_train:
                     train[key] = fn(args, cso, store, shape, g, mbs, ORDERS, NHID, device, rank, world, log, **kw)
@@ -463,10 +604,30 @@ def main():
                 train[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if store is not None:
         store.close()
+        store = None
 
+    # ---- the kernel to beat: the reference's own CUDA extension (compiled unmodified into oracle/_ref) on the same
+    # blocks, same GPU, same clock (CUDA events, cold L2)
     ref_gpu = None
-    if args.ref_gpu and rank == 0:
-        ref_gpu = run_ref_gpu(mbs, widths, device, log)
+    if not args.no_ref_gpu and rank == 0:
+        try:
+            ref_gpu = run_ref_gpu(mbs, widths, device, flush_l2, step_bytes[0], total_ms_max / args.steps, log)
+        except Exception as exc:
+            ref_gpu = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+    # ---- BASELINE configs[3] and [4]: bounded runs of the other named workloads, every rank its own minibatches
+    other = None
+    if not args.no_other_workloads and args.workload == "reddit":
+        del dev_mbs, flush_src
+        torch.cuda.empty_cache()
+        other = {}
+        for key, fn in [("products_gcn_locality", run_products_locality), ("papers_width_sweep", run_papers_sweep)]:
+            try:
+                other[key] = fn(args, cso, gmod, device, rank, world, flush_buf, log)
+            except Exception as exc:
+                import traceback
+                log(traceback.format_exc())
+                other[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -477,20 +638,13 @@ def main():
             "metric": "LADIES-layer SpMM HBM GB/s (fwd+bwd)", "value": round(value, 2), "unit": "GB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms_max / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{shape.name}-shaped {'GCN' if shape.self_loops else 'GraphSAGE'} LADIES samp_num {samp} batch {batch}"
-                                   + (" (BASELINE configs[1])" if shape.name == "reddit" else ""),
-                       "graph": {"nodes": g.num_nodes, "directed_nnz": g.nnz, "feat_dim": shape.feat_dim, "alpha": shape.alpha,
-                                 "max_degree": int(g.degrees().max())},
-                       "blocks": block_stats(mbs[0], widths), "minibatches_rotated": len(mbs),
-                       "l2": "flushed between steps (384 MiB write + 384 MiB read) and inputs rotate over >L2 working sets",
-                       "sharding": "each rank its own minibatches, no data-path collective in `value`",
-                       "bwd_includes": "CSR-of-A^T build (gnn_csr_transpose) every step"},
+            "config": make_config(shape, g, mbs, widths, samp, batch),
+            "parity_gate": gate,
             "wall_ms_per_step_incl_flush": round(wall / args.steps * 1e3, 4),
             "gpu_launches": int(launches), "clocks": clk, "ops": ops, "warm_l2": warm_l2, "roofline": roofline,
             "e2e": e2e, "train": train, "cpu_baseline": cpu_baseline,
+            "reference_cuda_kernels_same_gpu": ref_gpu, "other_workloads": other,
         }
-        if ref_gpu is not None:
-            line["reference_cuda_kernels_same_gpu"] = ref_gpu
         emit(line)
     if world > 1:
         dist.barrier()
@@ -689,8 +843,11 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
     return out
 
 
-def run_ref_gpu(mbs, widths, device, log):
-    """The reference's own CUDA kernels (oracle/_ref, built unmodified) on the same blocks and GPU: the kernel to beat."""
+def run_ref_gpu(mbs, widths, device, flush_l2, step_bytes, our_ms_per_step, log):
+    """The reference's own CUDA kernels (oracle/_ref, built unmodified by oracle/build_ref.py) on the blocks of timed
+    minibatch 0, on this GPU, clocked like `value`: CUDA events around each op, L2 flushed before each op, median of 3.
+    Forward = spmm_load_balance (spmm.cpp:23-27); backward = mat1.transpose(0,1).coalesce() + spmm_load_balance, exactly
+    what custom_sparse_ops.py:30-37 executes.  Used as a yardstick only."""
     import torch
     from oracle import build_ref
     mod = build_ref.load_ref()
@@ -698,7 +855,7 @@ def run_ref_gpu(mbs, widths, device, log):
         return {"unavailable": "oracle/_ref/spmm_ref.so not in this snapshot"}
     mb = mbs[0]
     res = {}
-    tot_ms, tot_bytes = 0.0, 0.0
+    tot_ms = 0.0
     for li, (layer, D) in enumerate(zip(mb.layers, widths)):
         a = mod.create_coo_tensor(torch.from_numpy(layer.fullrowptr).to(device), torch.from_numpy(layer.rowptr).to(device),
                                   torch.from_numpy(layer.colidx).to(device), torch.from_numpy(layer.normfact).to(device),
@@ -708,18 +865,231 @@ def run_ref_gpu(mbs, widths, device, log):
         for name, fn in [("fwd", lambda: mod.spmm_load_balance(a, x))] + (
                 [("bwd", lambda: mod.spmm_load_balance(a.transpose(0, 1).coalesce(), gq.contiguous()))] if li > 0 else []):
             fn()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
+            ts = []
             for _ in range(3):
+                flush_l2()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
                 fn()
-            torch.cuda.synchronize()
-            ms = (time.perf_counter() - t0) / 3 * 1e3
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = float(np.median(ts))
             res[f"{name}{li}_ms"] = round(ms, 3)
             tot_ms += ms
-            tot_bytes += algorithmic_bytes(layer.nnz, layer.nrows, layer.ncols, D)
-    res["algorithmic_GBps"] = round(tot_bytes / (tot_ms * 1e-3) / 1e9, 1)
-    res["note"] = "spmm_load_balance (+ transpose().coalesce() in bwd), wall clock around device syncs, warm L2"
+    res["ms_per_step"] = round(tot_ms, 3)
+    res["algorithmic_GBps"] = round(step_bytes / (tot_ms * 1e-3) / 1e9, 1)
+    res["ours_speedup"] = round(tot_ms / our_ms_per_step, 2)
+    res["note"] = ("reference spmm_load_balance (+ transpose().coalesce() in bwd) compiled unmodified for sm_100a; CUDA events, "
+                   "cold L2 per op, median of 3, minibatch 0 (rank 0)")
     return res
+
+
+# ----------------------------------------------------------------------------- BASELINE configs[3] / [4]
+def _timed_us(fn, flush_buf, reps=3):
+    import torch
+    ts = []
+    for r in range(reps + 1):
+        flush_buf.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if r:
+            ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)) * 1e3
+
+
+def _graph_rank0_first(name, rank, world, log):
+    """Rank 0 generates (and caches) the graph, the others load the cache."""
+    import torch.distributed as dist
+    from gnn_b200 import graphgen
+    shape = graphgen.SHAPES[name]
+    cache_root = os.path.join(REPO, ".cache") if os.path.isdir(os.path.join(REPO, ".cache")) else None
+    if world > 1 and rank != 0:
+        dist.barrier()
+    t0 = time.time()
+    g = graphgen.generate_cached(shape, seed=0, root=cache_root)
+    log(f"graph {shape.name}: {g.num_nodes} nodes, {g.nnz} directed nnz ({time.time() - t0:.1f}s)")
+    if world > 1 and rank == 0:
+        dist.barrier()
+    return shape, g
+
+
+def _spmm_block_sweep(cso, mb, widths_per_layer, device, flush_buf, check_rows=512):
+    """fwd + bwd of every layer block at the given widths: CUDA-event us (cold L2), algorithmic bytes, oracle parity on a
+    row sample.  Returns (rows, total_bytes, total_us, worst_err)."""
+    import torch
+    import oracle
+    rows_out, tot_b, tot_us, worst = [], 0.0, 0.0, 0.0
+    for li, layer in enumerate(mb.layers):
+        a = cso.create_coo_tensor(torch.from_numpy(layer.fullrowptr).to(device), torch.from_numpy(layer.rowptr).to(device),
+                                  torch.from_numpy(layer.colidx32 if layer.ncols > 32767 else layer.colidx).to(device),
+                                  torch.from_numpy(layer.normfact).to(device), layer.nrows, layer.ncols)
+        adj = cso.adjacency_of(a)
+        _, cols, vals = oracle.build_adj(layer.fullrowptr, layer.rowptr, layer.colidx32, layer.normfact, layer.nrows)
+        cols = cols.astype(np.int32)
+        rsel = np.unique(np.linspace(0, layer.nrows - 1, min(check_rows, layer.nrows)).astype(np.int64))
+        sub = _row_sample(layer.rowptr, cols, vals, rsel)
+        for D in widths_per_layer[li]:
+            from gnn_b200 import gather as gmod
+            x = torch.randn(layer.ncols, gmod.padded_ld(D), device=device)[:, :D]
+            go = torch.randn(layer.nrows, D, device=device)
+            B = algorithmic_bytes(layer.nnz, layer.nrows, layer.ncols, D)
+            y = adj.matmul(x)
+            err = oracle.rel_err(y[torch.from_numpy(rsel).to(device)].cpu().numpy(),
+                                 oracle.spmm_f64acc(sub[0], sub[1], sub[2], rsel.size, np.ascontiguousarray(x.cpu().numpy())))[0]
+            worst = max(worst, err)
+            t_f = _timed_us(lambda: adj.matmul(x), flush_buf)
+
+            def bwd():
+                adj._t = None                     # a fresh adjacency per minibatch: whatever the backward needs is inside
+                adj.matmul_t(go)
+            t_b = _timed_us(bwd, flush_buf) if li > 0 else None
+            rows_out.append({"layer": li, "M": layer.nrows, "K": layer.ncols, "nnz": layer.nnz, "D": D, "fwd_us": round(t_f, 1),
+                             "bwd_us": (round(t_b, 1) if t_b is not None else None),
+                             "fwd_GBps": round(B / t_f / 1e3, 1), "bwd_GBps": (round(B / t_b / 1e3, 1) if t_b else None),
+                             "fwd_rel_err": float(f"{err:.2e}")})
+            tot_b += B * (2 if li > 0 else 1)
+            tot_us += t_f + (t_b or 0.0)
+    return rows_out, tot_b, tot_us, worst
+
+
+def _allreduce_sum_max(vals_sum, vals_max, device, world):
+    import torch
+    import torch.distributed as dist
+    if world <= 1:
+        return vals_sum, vals_max
+    a = torch.tensor(vals_sum, device=device, dtype=torch.float64)
+    b = torch.tensor(vals_max, device=device, dtype=torch.float64)
+    dist.all_reduce(a, op=dist.ReduceOp.SUM)
+    dist.all_reduce(b, op=dist.ReduceOp.MAX)
+    return a.tolist(), b.tolist()
+
+
+def run_products_locality(args, cso, gmod, device, rank, world, flush_buf, log):
+    """BASELINE configs[3]: 3-layer GCN with --locality_sampling on the ogbn-products-shaped graph, features placed by
+    the placement model (buffer 0.1 per GPU, alpha 0), every rank its own minibatches.  Reports the SpMM path (fwd+bwd
+    GB/s with oracle parity), where the input rows come from with and without locality sampling (reference
+    sampler.py:119-121 + preprocess.py:414-423), and GCN training minibatches/s with the device sampler in the loop."""
+    import torch
+    import torch.distributed as dist
+    from gnn_b200 import graphgen, harness, placement, sampler
+    shape, g = _graph_rank0_first("products", rank, world, log)
+    orders, nhid, samp, batch, scale_factor = [1, 1, 1], 512, 8192, 512, 2.0
+    devices = list(range(world))
+    buffer_rows = int(args.buffer_size * g.num_nodes)
+    t0 = time.time()
+    lap = (g.indptr, g.indices, np.repeat(1.0 / np.maximum(g.degrees(), 1), g.degrees()))
+    prob = placement.access_probability(lap, g.train_nodes, sum(orders))
+    if world > 1:
+        pl = placement.create_placement(lap, g.train_nodes, buffer_rows, devices, sum(orders), alpha=0.0, sample_prob=prob)
+        did, idx, bufs = pl.device_id_of_nodes_group[rank], pl.idx_of_nodes_on_device_group[rank], pl.gpu_buffer_group
+    else:
+        top = np.argsort(-1 * prob)[:buffer_rows]
+        did = np.full(g.num_nodes, -1, dtype=np.int64)
+        did[top] = 0
+        idx = np.arange(g.num_nodes, dtype=np.int64)
+        idx[top] = np.arange(top.size)
+        bufs = [top]
+    skew = placement.locality_sampling_sets(g.indptr, g.indices, shape.self_loops, bufs, len(orders))
+    log(f"products: placement + locality sets ({time.time() - t0:.1f}s)")
+    feats = torch.from_numpy(graphgen.features(shape, seed=1))
+    store = gmod.FeatureStore(feats, bufs, did, idx, devices, rank, device, group=(dist.group.WORLD if world > 1 else None))
+    rng = np.random.Generator(np.random.PCG64(4000 + rank))
+    chunk = (g.train_nodes.size + world - 1) // world
+    own = g.train_nodes[rank * chunk: min((rank + 1) * chunk, g.train_nodes.size)]
+    out = {"config": f"products-shaped 3-layer GCN (nhid {nhid}), LADIES samp_num {samp} batch {batch}, buffer_size {args.buffer_size}, "
+                     f"alpha 0, locality_sampling scale_factor {scale_factor} (BASELINE configs[3])",
+           "graph": {"nodes": g.num_nodes, "directed_nnz": g.nnz, "feat_dim": shape.feat_dim}}
+    widths = [[shape.feat_dim], [nhid], [nhid]]
+    src = {}
+    for tag, sf in [("uniform", 1.0), ("locality", scale_factor)]:
+        mbs = [sampler.ladies_sample(7000 + 10 * rank + i, own[rng.permutation(own.size)[:batch]], [samp] * 5, g.num_nodes, g.indptr,
+                                     g.indices, orders, skewed_sampling_nodes=skew, scale_factor=sf) for i in range(2)]
+        counts = np.zeros(world + 2)
+        for mb in mbs:
+            _, _, _, c = store.remap(torch.from_numpy(mb.input_nodes).to(device))
+            counts += c.cpu().numpy()
+        counts /= len(mbs)
+        local, host = counts[rank], counts[world]
+        peer = counts[:world].sum() - local
+        rows, tot_b, tot_us, worst = _spmm_block_sweep(cso, mbs[0], widths, device, flush_buf)
+        x0 = store.gather(torch.from_numpy(mbs[0].input_nodes).to(device)).cpu().numpy()
+        gather_ok = bool(np.array_equal(x0.view(np.uint32), store.host_rows(mbs[0].input_nodes).view(np.uint32)))
+        (b_all, us_sum), (us_max, err_max) = _allreduce_sum_max([tot_b, tot_us], [tot_us, worst], device, world)
+        src[tag] = {"input_rows_per_minibatch": {"local": int(local), "peer": int(peer), "host": int(host)},
+                    "spmm_fwd_bwd_GBps_all_ranks": round(b_all / us_max / 1e3, 1), "spmm_us_per_minibatch_max_rank": round(us_max, 1),
+                    "blocks": rows if rank == 0 else None, "worst_row_rel_err": float(f"{err_max:.2e}"),
+                    "parity_ok": bool(err_max <= GATE_TOL and gather_ok), "gather_bit_exact": gather_ok}
+    out["sampling"] = src
+    # GCN training with the device sampler in the loop, locality sampling on
+    try:
+        targs = argparse.Namespace(steps=min(args.steps, 12))
+        out["train_gcn_live_locality"] = harness.bench_train_live(targs, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log,
+                                                                   pool_num=4, fused=True, flat_grads=True, skewed_sampling_nodes=skew,
+                                                                   scale_factor=scale_factor)
+    except Exception as exc:
+        out["train_gcn_live_locality"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    store.close()
+    return out
+
+
+def run_papers_sweep(args, cso, gmod, device, rank, world, flush_buf, log):
+    """BASELINE configs[4]: ogbn-papers100M-shaped graph (at 1/--papers-scale of the nodes and edges - stated in the
+    output; degree statistics kept), features in pinned host memory only (no GPU cache: every input row crosses PCIe),
+    SpMM width sweep 16..1024 on each rank's own LADIES blocks, oracle parity at every width."""
+    import torch
+    import torch.distributed as dist
+    from gnn_b200 import graphgen, sampler
+    name = "papers16" if args.papers_scale == 16 else None
+    if name is None:
+        base = graphgen.SHAPES["papers16"]
+        f = 16.0 / args.papers_scale
+        graphgen.SHAPES[f"papers{args.papers_scale}"] = graphgen.GraphShape(f"papers{args.papers_scale}", int(base.num_nodes * f),
+                                                                             int(base.num_undirected_edges * f), base.feat_dim,
+                                                                             base.num_classes, base.max_degree, base.alpha, base.self_loops)
+        name = f"papers{args.papers_scale}"
+    shape, g = _graph_rank0_first(name, rank, world, log)
+    orders, samp, batch = [1, 1, 1], 8192, 512
+    rng = np.random.Generator(np.random.PCG64(9000 + rank))
+    chunk = (g.train_nodes.size + world - 1) // world
+    own = g.train_nodes[rank * chunk: min((rank + 1) * chunk, g.train_nodes.size)]
+    mb = sampler.ladies_sample(8000 + rank, own[rng.permutation(own.size)[:batch]], [samp] * 5, g.num_nodes, g.indptr, g.indices, orders)
+    sweep = [16, 32, 64, 128, 256, 512, 1024]
+    rows, tot_b, tot_us, worst = _spmm_block_sweep(cso, mb, [sweep] * len(mb.layers), device, flush_buf)
+    # host-resident features: the whole table pinned + mapped, no GPU shard; gather of one minibatch's input rows
+    t0 = time.time()
+    feats = torch.from_numpy(graphgen.features(shape, seed=1))
+    did = np.full(g.num_nodes, -1, dtype=np.int64)
+    store = gmod.FeatureStore(feats, [np.empty(0, dtype=np.int64) for _ in range(world)], did, np.arange(g.num_nodes, dtype=np.int64),
+                              list(range(world)), rank, device, group=(dist.group.WORLD if world > 1 else None))
+    log(f"papers: host table {tuple(feats.shape)} pinned ({time.time() - t0:.1f}s)")
+    nodes = torch.from_numpy(mb.input_nodes).to(device)
+    x0 = store.gather(nodes)
+    gather_ok = bool(np.array_equal(x0.cpu().numpy().view(np.uint32), store.host_rows(mb.input_nodes).view(np.uint32)))
+    src_dev, _, xrows, _ = store.remap(nodes)
+    buf = torch.empty((nodes.numel(), store.ld), device=device)
+    t_g = _timed_us(lambda: store.ext.gather_rows_src(xrows, src_dev, -1, store.feat_dim, buf), flush_buf)
+    gbytes = nodes.numel() * store.feat_dim * 4
+    store.close()
+    per_width = []
+    for D in sweep:
+        rs = [r for r in rows if r["D"] == D]
+        b = sum(algorithmic_bytes(r["nnz"], r["M"], r["K"], D) * (2 if r["bwd_us"] is not None else 1) for r in rs)
+        us = sum(r["fwd_us"] + (r["bwd_us"] or 0.0) for r in rs)
+        (b_all,), (us_max,) = _allreduce_sum_max([b], [us], device, world)
+        per_width.append({"D": D, "fwd_bwd_GBps_all_ranks": round(b_all / us_max / 1e3, 1), "us_per_minibatch_max_rank": round(us_max, 1)})
+    (_,), (err_max, tg_max) = _allreduce_sum_max([0.0], [worst, t_g], device, world)
+    return {"config": f"papers100M-shaped graph at 1/{args.papers_scale} scale ({g.num_nodes} nodes, {g.nnz} directed nnz, mean degree "
+                      f"{g.nnz / g.num_nodes:.1f}), 128-d features in pinned host memory, LADIES samp_num {samp} batch {batch}, width sweep "
+                      "(BASELINE configs[4])",
+            "width_sweep": per_width, "blocks_rank0": rows if rank == 0 else None,
+            "worst_row_rel_err": float(f"{err_max:.2e}"), "parity_ok": bool(err_max <= GATE_TOL and gather_ok),
+            "host_gather": {"rows": int(nodes.numel()), "bytes": int(gbytes), "us_max_rank": round(tg_max, 1),
+                            "GBps_per_gpu": round(gbytes / tg_max / 1e3, 1), "bit_exact": gather_ok,
+                            "note": "every input row of the minibatch read zero-copy from the pinned host table over PCIe"}}
 
 
 def run_reference(args, log):
@@ -731,8 +1101,7 @@ def run_reference(args, log):
     line = {"impl": "reference", "metric": "LADIES-layer SpMM HBM GB/s (fwd+bwd)", "value": round(cpu["value"], 4), "unit": "GB/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(float(np.mean(times)) * 1e3, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{shape.name}-shaped GraphSAGE LADIES samp_num {samp} batch {batch} (BASELINE configs[1])",
-                       "blocks": block_stats(mbs[0], widths)},
+            "config": make_config(shape, g, mbs, widths, samp, batch),
             "cpu_baseline": cpu, "gpu_launches": 0,
             "e2e": {"value": round(cpu["value"], 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)

@@ -66,7 +66,7 @@ def cabi() -> ctypes.CDLL:
                 "gnn_probe_row_gather_f32": (ctypes.c_int, [vp, i64, i64, vp, i64, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(i64), vp]),
                 "gnn_csr_transpose_workspace_bytes": (sz, [i64, i64, i64]),
                 "gnn_csr_transpose": (ctypes.c_int, [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, sz, vp]),
-                "gnn_placement_remap": (ctypes.c_int, [vp, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp]),
+                "gnn_placement_remap": (ctypes.c_int, [vp, i64, vp, vp, vp, i64, vp, i64, i64, vp, vp, vp, vp, vp]),
                 "gnn_gather_rows_f32": (ctypes.c_int, [vp, i64, i64, vp, i64, vp]),
                 "gnn_gather_rows_src_f32": (ctypes.c_int, [vp, vp, i32, i64, i64, vp, i64, vp]),
                 "gnn_index_rows_f32": (ctypes.c_int, [vp, i64, vp, i64, i64, vp, i64, vp]),

@@ -36,31 +36,41 @@ __device__ __forceinline__ int row_of_nnz(const int *__restrict__ rowptr, int lo
   return lo;
 }
 
-// Row-pointer window of a chunk.  win[k] = rowptr[min(r_lo + k, M)] for k in [0, 32*J]; `win` is this warp's own
-// shared-memory array of 32*J + 1 ints.
+// Row-pointer window of a chunk [s, e).  win[k] = rowptr[min(r_lo + k, M)] for k in [0, 32*J]; `win` is this warp's
+// own shared-memory array of 32*J + 1 ints.
 template <int J>
 struct ChunkRows {
   int r_lo;          // row of entry s
   const int *win;
 
-  // all 32 lanes must call; ends with __syncwarp()
-  __device__ __forceinline__ void load(const int *__restrict__ rowptr, int M, int s, int lane, int *win_smem) {
+  int span;          // window entries win[1..span] are the only ones that can be <= an entry of the chunk
+
+  // all 32 lanes must call; ends with __syncwarp().  e = end of the chunk (exclusive).
+  __device__ __forceinline__ void load(const int *__restrict__ rowptr, int M, int s, int e, int lane, int *win_smem) {
     r_lo = warp_first_row(rowptr, M, s, lane);
+    int first = 0;
 #pragma unroll
-    for (int j = 0; j < J; ++j) win_smem[32 * j + lane] = __ldg(rowptr + min(r_lo + 32 * j + lane, M));
+    for (int j = 0; j < J; ++j) {
+      const int v = __ldg(rowptr + min(r_lo + 32 * j + lane, M));
+      win_smem[32 * j + lane] = v;
+      if (j == 0) first = v;
+    }
     if (lane == 0) win_smem[32 * J] = __ldg(rowptr + min(r_lo + 32 * J, M));
+    // dense rows: the chunk touches 1-3 rows, so the per-entry search only needs the first few window entries.
+    // lane l holds win[l]; the first l >= 1 with win[l] >= e bounds every search of this chunk.
+    const unsigned beyond = __ballot_sync(kFull, lane >= 1 && first >= e);
+    span = beyond ? __ffs(beyond) - 2 : 32 * J;        // win[1..span] < e
     __syncwarp();
     win = win_smem;
   }
 
-  // row of entry i (s <= i < nnz): r_lo + #{k in [1, 32J] : win[k] <= i}; beyond the window (a chunk that crosses more
+  // row of entry i (s <= i < e): r_lo + #{k in [1, span] : win[k] <= i}; beyond the window (a chunk that crosses more
   // than 32J row starts, i.e. runs of empty rows) falls back to the global search
   __device__ __forceinline__ int row_of(const int *__restrict__ rowptr, int M, int i) const {
-    int lo = 0, hi = 32 * J;
-#pragma unroll
-    for (int it = 0; it < 6 + (J > 1) + (J > 2) + (J > 4); ++it) {      // log2(32J) + 1 halvings empty the range
+    int lo = 0, hi = span;
+    while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if (lo < hi) { if (win[mid + 1] <= i) lo = mid + 1; else hi = mid; }
+      if (win[mid + 1] <= i) lo = mid + 1; else hi = mid;
     }
     if (lo == 32 * J) return row_of_nnz(rowptr, r_lo + 32 * J, M - 1, i);
     return r_lo + lo;

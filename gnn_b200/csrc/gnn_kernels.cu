@@ -326,8 +326,8 @@ inline int spmm_chunk(int64_t nnz, int64_t D) {
 // bandwidth, are the run time; the row-split kernel (longer register-resident row segments, fewer shared-memory
 // trips per nonzero) for the dense LADIES blocks.  A function of (M, nnz, D) only: the workspace query must agree.
 constexpr int64_t kFlatMaxNnz = 4 << 20;
-constexpr int64_t kFlatMeanRow = 96;
-constexpr int64_t kFlatTargetItems = 8192;
+constexpr int64_t kFlatMeanRow = 24;           // measured crossover (profiles/r2_kernel_ab.md): below ~24 entries per row
+constexpr int64_t kFlatTargetItems = 8192;     // (scatter backward) warp items wanted before chunks grow
 
 inline bool flat_wanted(int64_t M, int64_t nnz, int64_t D) {
   (void)D;
@@ -337,15 +337,14 @@ inline bool flat_wanted(int64_t M, int64_t nnz, int64_t D) {
   return nnz <= kFlatMaxNnz && nnz < kFlatMeanRow * std::max<int64_t>(M, 1);
 }
 
-// flat chunk: 128 entries per warp item, halved (down to 32) while the grid would stay under ~2 waves of warps
+// flat chunk (entries per warp item): 64; 128 for wide rows (two vectors per lane halve the passes over the index
+// stream); 32 when the whole problem is a fraction of a wave anyway
 inline int flat_chunk(int64_t nnz, int64_t D) {
 #ifdef GNN_TUNE
   if (getenv("GNN_TUNE_FC")) return atoi(getenv("GNN_TUNE_FC"));
 #endif
-  const int64_t slabs = cdiv(D, 128);
-  int c = kFlatMaxC;
-  while (c > 32 && cdiv(nnz, c) * slabs < kFlatTargetItems) c >>= 1;
-  return c;
+  if (cdiv(nnz, 64) * cdiv(D, 128) < 1024) return 32;
+  return D >= 512 ? 128 : 64;
 }
 
 struct SpmmPlan { int kind, vec, nv, lpr, nslabs, C, nchunks, Dp, u; };   // kind: 0 row-split, 1 flat
@@ -364,10 +363,8 @@ inline SpmmPlan make_plan(int64_t M, int64_t nnz, int64_t D, int vec) {
     pl.C = flat_chunk(nnz, D);
     pl.nchunks = (int)cdiv(nnz, pl.C);
     const int64_t n = cdiv(nvec, 32);              // vector columns per lane
-    pl.nv = 1;
-    for (int nv : {4, 2})                          // wider slabs (fewer passes over the index stream) once the grid is large
-      if (nv <= n && (int64_t)pl.nchunks * cdiv(n, nv) >= 2 * kFlatTargetItems) { pl.nv = nv; break; }
-    pl.u = pl.nv == 1 ? 16 : (pl.nv == 2 ? 8 : 4);
+    pl.nv = (pl.C == 128 && n >= 2) ? 2 : 1;
+    pl.u = pl.nv == 1 ? (D < 256 ? 16 : 8) : 8;
 #ifdef GNN_TUNE
     if (getenv("GNN_TUNE_FNV")) pl.nv = atoi(getenv("GNN_TUNE_FNV"));
     if (getenv("GNN_TUNE_FU")) pl.u = atoi(getenv("GNN_TUNE_FU"));
@@ -643,7 +640,7 @@ build_adj_kernel(const int *__restrict__ fullrowptr, const int *__restrict__ row
     c[j] = i < e ? (int)colidx[i] : 0;
   }
   ChunkRows<J> cr;
-  cr.load(rowptr, M, s, lane, win_s[warp]);
+  cr.load(rowptr, M, s, e, lane, win_s[warp]);
 #pragma unroll
   for (int j = 0; j < J; ++j) nf[j] = __ldg(normfact + c[j]);
   int r_prev = -1;
@@ -722,7 +719,7 @@ transpose_pass_kernel(uint2 *__restrict__ cells, int M, int nnz, int words_per_c
     if (FILL) v[j] = i < e ? __ldg(vals + i) : 0.f;
   }
   ChunkRows<J> cr;
-  cr.load(rowptr, M, s, lane, win_s[warp]);
+  cr.load(rowptr, M, s, e, lane, win_s[warp]);
   if (cr.r_lo >= row1) return;                     // the whole chunk lies after this row block (warp-uniform)
 #pragma unroll
   for (int j = 0; j < J; ++j) {
@@ -1132,7 +1129,7 @@ int elu_rownorm_bwd_launch(const float *dy, int64_t lddy, const float *x, int64_
 __global__ void placement_remap_kernel(const int64_t *__restrict__ input_nodes, int64_t n0,
                                        const int64_t *__restrict__ dev_of, const int64_t *__restrict__ idx_of,
                                        const int64_t *__restrict__ devices, int world, const float *const *__restrict__ bases,
-                                       int64_t ld_src, int *__restrict__ src_dev, int64_t *__restrict__ slot,
+                                       int64_t ld_src, int64_t ld_host, int *__restrict__ src_dev, int64_t *__restrict__ slot,
                                        const float **__restrict__ xrows, unsigned long long *__restrict__ counts) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n0) return;
@@ -1148,7 +1145,12 @@ __global__ void placement_remap_kernel(const int64_t *__restrict__ input_nodes, 
   }
   src_dev[j] = s;
   slot[j] = sl;
-  if (xrows) xrows[j] = (s == -2 || !bases) ? nullptr : bases[s < 0 ? world : s] + sl * ld_src;
+  if (xrows) {
+    // a source whose base pointer is NULL (no mapped host table, a shard that was not opened) yields a NULL row
+    // pointer, which the gather kernels skip - never an address computed from NULL
+    const float *base = (s == -2 || !bases) ? nullptr : bases[s < 0 ? world : s];
+    xrows[j] = base ? base + sl * (s < 0 ? ld_host : ld_src) : nullptr;
+  }
   if (counts) atomicAdd(counts + (s == -2 ? world + 1 : (s < 0 ? world : s)), 1ull);
 }
 
@@ -1463,8 +1465,8 @@ int gnn_csr_transpose(const int32_t *rowptr, const int32_t *colidx, const float 
 
 int gnn_placement_remap(const int64_t *input_nodes, int64_t n0, const int64_t *device_id_of_nodes,
                         const int64_t *idx_of_nodes_on_device, const int64_t *devices, int64_t world,
-                        const float *const *bases, int64_t ld_src, int32_t *src_dev, int64_t *slot, const float **xrows,
-                        int64_t *counts, gnn_stream_t stream) {
+                        const float *const *bases, int64_t ld_src, int64_t ld_host, int32_t *src_dev, int64_t *slot,
+                        const float **xrows, int64_t *counts, gnn_stream_t stream) {
   if (n0 < 0 || world < 0 || world > 1024) return GNN_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (counts) GNN_CUDA(cudaMemsetAsync(counts, 0, (size_t)(world + 2) * sizeof(int64_t), st));
@@ -1474,7 +1476,7 @@ int gnn_placement_remap(const int64_t *input_nodes, int64_t n0, const int64_t *d
   if (xrows && !bases) return GNN_E_BADARG;
   placement_remap_kernel<<<(unsigned)cdiv(n0, 256), 256, 0, st>>>(input_nodes, n0, device_id_of_nodes,
                                                                  idx_of_nodes_on_device, devices, (int)world, bases, ld_src,
-                                                                 src_dev, slot, xrows, (unsigned long long *)counts);
+                                                                 ld_host, src_dev, slot, xrows, (unsigned long long *)counts);
   GNN_LAUNCH_CHECK();
   return 0;
 }

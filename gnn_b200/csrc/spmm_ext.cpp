@@ -163,10 +163,8 @@ int64_t probe_row_gather(const torch::Tensor &X, const torch::Tensor &colidx, in
   return bytes;
 }
 
-std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> csr_transpose(const torch::Tensor &rowptr,
-                                                                                      const torch::Tensor &colidx,
-                                                                                      const torch::Tensor &vals, int64_t M,
-                                                                                      int64_t K) {
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, c10::optional<torch::Tensor>> csr_transpose(
+    const torch::Tensor &rowptr, const torch::Tensor &colidx, const torch::Tensor &vals, int64_t M, int64_t K) {
   CHECK_DENSE(rowptr); CHECK_DENSE(colidx); CHECK_DENSE(vals);
   c10::cuda::CUDAGuard g(vals.device());
   const int64_t nnz = vals.numel();
@@ -174,14 +172,16 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> csr_trans
   auto t_rowptr = torch::empty({K + 1}, iopt);
   auto t_colidx = torch::empty({nnz}, iopt);
   auto t_vals = torch::empty({nnz}, vals.options());
-  auto t_rowidx = torch::empty({nnz}, iopt);
+  // row ids of A^T's entries only where a short-row kernel will read them (one more scattered store per entry otherwise)
+  const bool want_rows = nnz < 96 * std::max<int64_t>(K, 1);
+  auto t_rowidx = want_rows ? torch::empty({nnz}, iopt) : torch::Tensor();
   const size_t wsb = gnn_csr_transpose_workspace_bytes(M, K, nnz);      // bounded by the bitmap budget (row-blocked beyond it)
   auto ws = workspace(wsb, vals.device());
   check_rc(gnn_csr_transpose(rowptr.data_ptr<int32_t>(), colidx.data_ptr<int32_t>(), vals.data_ptr<float>(), M, K, nnz,
                              t_rowptr.data_ptr<int32_t>(), t_colidx.data_ptr<int32_t>(), t_vals.data_ptr<float>(),
-                             t_rowidx.data_ptr<int32_t>(), ws.data_ptr(), wsb, cur_stream()),
+                             want_rows ? t_rowidx.data_ptr<int32_t>() : nullptr, ws.data_ptr(), wsb, cur_stream()),
            "gnn_csr_transpose");
-  return {t_rowptr, t_colidx, t_vals, t_rowidx};
+  return {t_rowptr, t_colidx, t_vals, want_rows ? c10::optional<torch::Tensor>(t_rowidx) : c10::nullopt};
 }
 
 std::tuple<torch::Tensor, torch::Tensor> coo_to_csr(const torch::Tensor &sparseMat) {
@@ -212,9 +212,11 @@ torch::Tensor spmm_naive(const torch::Tensor &sparseMat, const torch::Tensor &de
   return spmm_load_balance(sparseMat, denseMat);
 }
 
-std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> build_adj(const torch::Tensor &fullrowptr, const torch::Tensor &rowptr,
-                                                                  const torch::Tensor &colidx, const torch::Tensor &normfact,
-                                                                  int64_t nrows, int64_t ncols) {
+std::tuple<torch::Tensor, torch::Tensor, c10::optional<torch::Tensor>> build_adj(const torch::Tensor &fullrowptr,
+                                                                                 const torch::Tensor &rowptr,
+                                                                                 const torch::Tensor &colidx,
+                                                                                 const torch::Tensor &normfact, int64_t nrows,
+                                                                                 int64_t ncols) {
   CHECK_DENSE(fullrowptr);
   CHECK_DENSE(rowptr);
   CHECK_DENSE(colidx);
@@ -230,16 +232,18 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> build_adj(const torch::T
   auto indices = torch::empty({2, nnz}, colidx.options().dtype(torch::kLong));
   auto values = torch::empty({nnz}, normfact.options());
   auto col32 = torch::empty({nnz}, colidx.options().dtype(torch::kInt));
-  auto row32 = torch::empty({nnz}, colidx.options().dtype(torch::kInt));
+  // per-entry row ids for the short-row kernels (flat SpMM, scatter backward); dense LADIES blocks never read them
+  const bool want_rows = nnz < 96 * std::max<int64_t>(nrows, 1);
+  auto row32 = want_rows ? torch::empty({nnz}, colidx.options().dtype(torch::kInt)) : torch::Tensor();
   check_rc(gnn_build_adj(fullrowptr.data_ptr<int32_t>(), rowptr.data_ptr<int32_t>(), colidx.data_ptr(),
                          colidx.scalar_type() == torch::kShort ? 2 : 4, normfact.data_ptr<float>(), nrows, ncols, nnz,
                          indices.data_ptr<int64_t>(), values.data_ptr<float>(), col32.data_ptr<int32_t>(),
-                         row32.data_ptr<int32_t>(), cur_stream()),
+                         want_rows ? row32.data_ptr<int32_t>() : nullptr, cur_stream()),
            "gnn_build_adj");
   // rows ascending, columns ascending and unique inside a row: already coalesced (no sort, cuda_spmm.cu:825)
   auto coo = at::_sparse_coo_tensor_unsafe(indices, values, {nrows, ncols}, values.options().layout(torch::kSparse),
                                            /*is_coalesced=*/true);
-  return {coo, col32, row32};
+  return {coo, col32, want_rows ? c10::optional<torch::Tensor>(row32) : c10::nullopt};
 }
 
 torch::Tensor create_coo_tensor(const torch::Tensor &fullrowptr, const torch::Tensor &rowptr, const torch::Tensor &colidx,
@@ -250,7 +254,7 @@ torch::Tensor create_coo_tensor(const torch::Tensor &fullrowptr, const torch::Te
 // ---- gather path ----------------------------------------------------------
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> placement_remap(
     const torch::Tensor &input_nodes, const torch::Tensor &device_id_of_nodes, const torch::Tensor &idx_of_nodes_on_device,
-    const torch::Tensor &devices, const torch::Tensor &bases, int64_t ld_src) {
+    const torch::Tensor &devices, const torch::Tensor &bases, int64_t ld_src, int64_t ld_host) {
   CHECK_DENSE(input_nodes); CHECK_DENSE(device_id_of_nodes); CHECK_DENSE(idx_of_nodes_on_device); CHECK_DENSE(devices);
   CHECK_DENSE(bases);
   TORCH_CHECK(input_nodes.scalar_type() == torch::kLong && device_id_of_nodes.scalar_type() == torch::kLong &&
@@ -266,7 +270,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> placement
   auto counts = torch::empty({world + 2}, input_nodes.options());
   check_rc(gnn_placement_remap(input_nodes.data_ptr<int64_t>(), n0, device_id_of_nodes.data_ptr<int64_t>(),
                                idx_of_nodes_on_device.data_ptr<int64_t>(), devices.data_ptr<int64_t>(), world,
-                               reinterpret_cast<const float *const *>(bases.data_ptr<int64_t>()), ld_src,
+                               reinterpret_cast<const float *const *>(bases.data_ptr<int64_t>()), ld_src, ld_host,
                                src_dev.data_ptr<int32_t>(), slot.data_ptr<int64_t>(),
                                reinterpret_cast<const float **>(xrows.data_ptr<int64_t>()), counts.data_ptr<int64_t>(),
                                cur_stream()),

@@ -104,7 +104,7 @@ spmm_flat_kernel(const SpmmParams p, const XSrc<GATHER> xs) {
     cr.r_lo = 0;
     cr.win = nullptr;
   } else {
-    cr.load(p.rowptr, p.M, s, lane, win_s[warp]);
+    cr.load(p.rowptr, p.M, s, e, lane, win_s[warp]);
 #pragma unroll
     for (int j = 0; j < kFlatMaxC / 32; ++j) {
       const int k = 32 * j + lane;

@@ -65,7 +65,7 @@ spmm_scatter_t_kernel(const ScatterParams p) {
   }
   if constexpr (!ROWIDS) {
     ChunkRows<kFlatMaxC / 32> cr;
-    cr.load(p.rowptr, p.M, s, lane, win_s[warp]);
+    cr.load(p.rowptr, p.M, s, e, lane, win_s[warp]);
 #pragma unroll
     for (int j = 0; j < kFlatMaxC / 32; ++j) {
       const int k = 32 * j + lane;

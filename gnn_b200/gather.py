@@ -33,11 +33,15 @@ def padded_ld(feat_dim: int) -> int:
 class FeatureStore:
     def __init__(self, feat_data: torch.Tensor, gpu_buffer_nodes: Sequence[np.ndarray], device_id_of_nodes: np.ndarray,
                  idx_of_nodes_on_device: np.ndarray, devices: Sequence[int], rank: int, device: torch.device,
-                 group=None, map_host: bool = True):
+                 group=None, map_host: bool = True, pad_host: bool = True):
         """feat_data: CPU float32 [N, F] (the reference's ``feat_data``); gpu_buffer_nodes[i]: node id of every
         slot of GPU i's buffer (``gpu_buffer_group``); device_id_of_nodes / idx_of_nodes_on_device: THIS rank's
         view of the placement tables; devices: device ids as they appear in the tables; ``group``: a
-        torch.distributed process group when there is one process per GPU (None = single process)."""
+        torch.distributed process group when there is one process per GPU (None = single process).
+        ``pad_host=False`` registers ``feat_data`` as it is (leading dimension F) instead of copying it into a table
+        with 128-byte-aligned rows: no second copy of a papers100M-sized table in host RAM, at the price of narrower
+        loads on the (PCIe-bound) host rows.  ``map_host=False``: no host table at all - a minibatch that needs an
+        uncached node then raises instead of reading through a NULL base."""
         self.ext = _native.extension()
         self.rank, self.world = int(rank), len(devices)
         self.device = torch.device(device)
@@ -47,10 +51,13 @@ class FeatureStore:
 
         # ---- host table: padded, pinned, mapped (zero-copy reads of uncached rows, main.py:134)
         self.host = None
+        self._feat = feat_data                  # the caller's table (not copied): reference rows for checks
+        self.ld_host = self.ld
         host_alias = 0
         if map_host:
-            if feat_data.shape[1] == self.ld and feat_data.is_contiguous():
+            if (feat_data.shape[1] == self.ld or not pad_host) and feat_data.is_contiguous():
                 self.host = feat_data
+                self.ld_host = int(feat_data.shape[1])
             else:
                 self.host = torch.zeros((feat_data.shape[0], self.ld), dtype=torch.float32)
                 self.host[:, :self.feat_dim] = feat_data
@@ -63,7 +70,7 @@ class FeatureStore:
         if multi_process:
             import torch.distributed as dist
             nodes = np.asarray(gpu_buffer_nodes[self.rank])
-            shard, handle = self.ext.shard_alloc(len(nodes), self.ld, dev_index)
+            shard, handle = self.ext.shard_alloc(max(len(nodes), 1), self.ld, dev_index)      # an empty buffer still maps
             self._fill(shard, feat_data, nodes)
             self.shards[self.rank] = shard
             handles = [None] * self.world
@@ -72,7 +79,7 @@ class FeatureStore:
             dist.barrier(group=group)
             for i, (h, rows) in enumerate(handles):
                 if i != self.rank:
-                    self.shards[i] = self.ext.shard_open(h, rows, self.ld, dev_index)
+                    self.shards[i] = self.ext.shard_open(h, max(rows, 1), self.ld, dev_index)
         else:
             # single process: every buffer lives on this device (world == 1, or a test emulating more ranks)
             for i in range(self.world):
@@ -97,12 +104,24 @@ class FeatureStore:
     # ------------------------------------------------------------------
     def remap(self, input_nodes: torch.Tensor):
         """Device placement remap (reference sampler.py:150-158): -> (src_dev i32, slot i64, xrows i64, counts i64)."""
-        return self.ext.placement_remap(input_nodes, self.device_id_of_nodes, self.idx_of_nodes_on_device, self.devices,
-                                        self.bases, self.ld)
+        out = self.ext.placement_remap(input_nodes, self.device_id_of_nodes, self.idx_of_nodes_on_device, self.devices,
+                                       self.bases, self.ld, self.ld_host)
+        return out
+
+    def host_rows(self, nodes) -> np.ndarray:
+        """``feat_data[nodes]`` from the caller's own table (what the reference's gather must reproduce bit for bit)."""
+        return self._feat[torch.as_tensor(np.asarray(nodes), dtype=torch.int64)].numpy()
+
+    def check_all_resident(self, counts: torch.Tensor) -> None:
+        """With ``map_host=False`` a node that no GPU caches has nowhere to come from: fail loudly."""
+        if self.host is None and int(counts[self.world].item()) > 0:
+            raise RuntimeError(f"{int(counts[self.world].item())} input nodes are not cached on any GPU and the store has no host table")
 
     def gather(self, input_nodes: torch.Tensor) -> torch.Tensor:
         """input_feat_data of main.py:129-134 as a [n0, F] view of a 16-byte-row-aligned buffer."""
-        _, _, xrows, _ = self.remap(input_nodes)
+        _, _, xrows, counts = self.remap(input_nodes)
+        if self.host is None:
+            self.check_all_resident(counts)
         return self.ext.gather_rows(xrows, self.feat_dim, self.ld)
 
     def begin_co_running(self):

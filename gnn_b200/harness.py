@@ -5,9 +5,8 @@ keep working unchanged on top of ``custom_sparse_ops`` (SURVEY.md section 2.1 ro
 box does not have /root/reference, so the few dense pieces a training step needs are restated
 here with the same math, only to drive the hot path in its real calling pattern:
 
-  * GraphSAGE layer: ``spmm(adj, x)`` then ``cat[linearB(x[sampled_nodes]), linearW(feat)]``, ELU,
-    per-row standardisation with learnable scale/offset   (reference models.py:6-25, 27-44)
-  * head: L2-normalise, dropout, linear                     (models.py:86-97)
+  * the model shells of gnn_b200/models.py (parameter names = the reference's, pinned to goldens of the unmodified
+    reference modules): GraphSAGE / GCN layers around ``spmm(adj, x)``, head = L2-normalise, dropout, linear
   * loss: BCE-with-logits weighted 1/batch, summed          (utils.py:129-140, sigmoid_loss default)
   * step: gather -> forward -> loss -> backward -> clip_grad_norm_(5) -> gradient exchange -> Adam
     (main.py:129-170); the exchange is ONE NCCL allreduce(SUM) of the flattened gradient - the
@@ -22,49 +21,6 @@ import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
-
-
-class SageLayer(nn.Module):
-    def __init__(self, n_in, n_out, order, spmm, fused=False):
-        super().__init__()
-        self.fused = fused
-        self.linearW = nn.Linear(n_in, n_out)
-        self.linearB = nn.Linear(n_in, n_out)
-        self.offset = nn.Parameter(torch.zeros((1 + order) * n_out))
-        self.scale = nn.Parameter(torch.ones((1 + order) * n_out))
-        self.order = order
-        self.spmm = spmm
-
-    def forward(self, x, adj, sampled_nodes):
-        if self.order > 0:
-            feat = self.spmm(adj, x)
-            feat = torch.cat([self.linearB(x[sampled_nodes]), self.linearW(feat)], 1)
-        else:
-            feat = self.linearW(x)
-        if self.fused:                       # one kernel per direction instead of ~10 / ~20 (gnn_b200/models.py)
-            from .models import elu_rownorm
-            return elu_rownorm(feat, self.scale, self.offset)
-        out = F.elu(feat)
-        mean = out.mean(dim=1, keepdim=True)
-        var = out.var(dim=1, unbiased=False, keepdim=True) + 1e-9
-        return (out - mean) * self.scale * torch.rsqrt(var) + self.offset
-
-
-class SageNet(nn.Module):
-    def __init__(self, nfeat, nhid, orders, num_classes, spmm, dropout=0.1, fused=False):
-        super().__init__()
-        self.layers = nn.ModuleList([SageLayer(nfeat, nhid, orders[0], spmm, fused)])
-        for i in range(len(orders) - 1):
-            self.layers.append(SageLayer((1 + orders[i]) * nhid, nhid, orders[i + 1], spmm, fused))
-        self.dropout = nn.Dropout(dropout)
-        self.head = nn.Linear((1 + orders[-1]) * nhid, num_classes)
-
-    def forward(self, feat, adjs, sampled_nodes):
-        x = feat
-        for layer, adj, sn in zip(self.layers, adjs, sampled_nodes):
-            x = self.dropout(layer(x, adj, sn))
-        x = F.normalize(x, p=2, dim=1)
-        return self.head(self.dropout(x))
 
 
 def bce_loss(preds, labels):
@@ -88,14 +44,59 @@ def exchange_gradients(params, world):
     return flat.numel() * 4
 
 
-def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, world, log, fused=False):
+class FlatGradients:
+    """All parameter gradients as views of ONE buffer.
+
+    The reference clips every replica's gradient to norm 5 (main.py:146), then sums the replicas (main.py:149-168:
+    threads + barrier + per-parameter peer copies).  With the gradients living in one flat buffer from the start,
+    zeroing is one memset, the clip is one norm + one in-place scale over the buffer (instead of a per-parameter norm,
+    a stack and a per-parameter multiply), and the exchange is one NCCL allreduce(SUM) straight on the buffer with no
+    flatten / copy-back.  ``buckets`` > 1 splits the allreduce so that the optimizer can start on the first bucket while
+    the next one is still in flight (not used by default: 11 MB over NVSwitch is latency-bound)."""
+
+    def __init__(self, params, world: int, max_norm: float = 5.0, comm_stream=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.world, self.max_norm = world, max_norm
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.params[0].device)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+        self.bytes = total * 4
+
+    def zero(self):
+        self.flat.zero_()
+
+    def clip_and_exchange(self):
+        """clip_grad_norm_(params, max_norm) followed by the gradient sum over ranks; returns bytes exchanged."""
+        norm = torch.linalg.vector_norm(self.flat)
+        self.flat.mul_(torch.clamp(self.max_norm / (norm + 1e-6), max=1.0))      # same coefficient as clip_grad_norm_
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            return self.bytes
+        return 0
+
+
+def make_model(cso, shape, orders, nhid, device, fused):
+    """Replica of the reference's model for this shape: GraphSAGE (main.py default) or GCN for the +I shapes."""
+    from . import models
+    torch.manual_seed(1234)                      # same initial replica on every rank (reference main.py:91-97 builds one per thread)
+    kind = "gcn" if shape.self_loops else "graphsage"
+    return models.build_model(kind, shape.feat_dim, nhid, orders, shape.num_classes, dropout=0.1, fused=fused,
+                              spmm=cso.spmm).to(device), kind
+
+
+def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, world, log, fused=False, flat_grads=False):
     """Full training steps over the rotated pre-sampled minibatches (sampling excluded, as stated in the line)."""
     import torch.distributed as dist
     from . import graphgen
-    torch.manual_seed(1234)                      # same initial replica on every rank (reference main.py:91-97 builds one per thread)
-    model = SageNet(shape.feat_dim, nhid, orders, shape.num_classes, cso.spmm, fused=fused).to(device)
+    model, kind = make_model(cso, shape, orders, nhid, device, fused)
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=0.01)
+    flat = FlatGradients(params, world) if flat_grads else None
+    opt = torch.optim.Adam(params, lr=0.01, fused=bool(flat_grads))
     labels_all = graphgen.labels(shape, seed=3)
     prepared = []
     for mb in mbs:
@@ -118,7 +119,10 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
         adjs, sn, y, nodes = prepared[i % len(prepared)]
         for a in adjs:
             cso.adjacency_of(a)._t = None        # a fresh adjacency every minibatch: backward rebuilds its A^T index
-        opt.zero_grad(set_to_none=False)
+        if flat is not None:
+            flat.zero()
+        else:
+            opt.zero_grad(set_to_none=False)
         if i in pending:
             x0, ev = pending.pop(i)
             torch.cuda.current_stream().wait_event(ev)
@@ -130,8 +134,11 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
         out = model(x0, adjs, sn)
         loss = bce_loss(out, y)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(params, 5)
-        comm_bytes = exchange_gradients(params, world)
+        if flat is not None:
+            comm_bytes = flat.clip_and_exchange()
+        else:
+            torch.nn.utils.clip_grad_norm_(params, 5)
+            comm_bytes = exchange_gradients(params, world)
         opt.step()
         return loss
 
@@ -170,13 +177,13 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
     return {"minibatches_per_s": round(world * steps / max(ms * 1e-3, wall), 2), "unit": "minibatches/s", "steps": steps,
             "ms_per_step_device": round(ms / steps, 3), "ms_per_step_wall": round(wall / steps * 1e3, 3),
             "allreduce_bytes_per_step": int(comm_bytes), "parameters": int(nparams), "final_loss": round(last, 4),
-            "fused_epilogue": bool(fused),
-            "note": "gather (next minibatch prefetched on a side stream) + GraphSAGE fwd + BCE loss + bwd + clip + NCCL "
+            "fused_epilogue": bool(fused), "flat_gradients": bool(flat_grads), "model": kind,
+            "note": f"gather (next minibatch prefetched on a side stream) + {kind} fwd + BCE loss + bwd + clip + NCCL "
                     "allreduce(sum) + Adam on pre-sampled minibatches (host LADIES sampling and adjacency upload excluded)"}
 
 
 def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log, pool_num=4, fused=False,
-                     prebuild_transpose=True):
+                     prebuild_transpose=True, flat_grads=False, skewed_sampling_nodes=None, scale_factor=1.0):
     """Training with the sampler IN the loop (BASELINE's second minibatches/s number): ``pool_num`` sampler threads
     (reference main.py:77 uses a ThreadPoolExecutor of --pool_num=4 per GPU) run the device LADIES sampler
     (gnn_b200/gpu_sampler.py: numpy draw on the host, array passes on the GPU) and the feature gather on their own
@@ -186,10 +193,10 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
     from concurrent.futures import ThreadPoolExecutor
     import torch.distributed as dist
     from . import gpu_sampler, graphgen, pipeline
-    torch.manual_seed(1234)
-    model = SageNet(shape.feat_dim, nhid, orders, shape.num_classes, cso.spmm, fused=fused).to(device)
+    model, kind = make_model(cso, shape, orders, nhid, device, fused)
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=0.01)
+    flat = FlatGradients(params, world) if flat_grads else None
+    opt = torch.optim.Adam(params, lr=0.01, fused=bool(flat_grads))
     labels_all = graphgen.labels(shape, seed=3)
     dg = gpu_sampler.DeviceGraph(g.indptr, g.indices, device)
     tls = threading.local()
@@ -215,7 +222,8 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         with torch.cuda.stream(tls.stream):
             mb = gpu_sampler.ladies_sample_device(5000 + 1000 * rank + i, batches[i], [samp] * 5, dg, orders,
                                                   create_coo_tensor=cso.create_coo_tensor, scratch=tls.scratch,
-                                                  prebuild_transpose=prebuild_transpose)
+                                                  prebuild_transpose=prebuild_transpose,
+                                                  skewed_sampling_nodes=skewed_sampling_nodes, scale_factor=scale_factor)
             nodes = torch.from_numpy(mb.input_nodes).to(device)
             x0 = store.gather(nodes)
             sn = [torch.from_numpy(np.ascontiguousarray(s_, dtype=np.int64)).to(device) for s_ in mb.sampled_nodes]
@@ -242,12 +250,18 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         refill()
         mb, x0, sn, y = pending.popleft().result()
         refill()
-        opt.zero_grad(set_to_none=False)
+        if flat is not None:
+            flat.zero()
+        else:
+            opt.zero_grad(set_to_none=False)
         out = model(x0, mb.adjs, sn)
         loss = bce_loss(out, y)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(params, 5)
-        exchange_gradients(params, world)
+        if flat is not None:
+            flat.clip_and_exchange()
+        else:
+            torch.nn.utils.clip_grad_norm_(params, 5)
+            exchange_gradients(params, world)
         opt.step()
         return loss
 
@@ -276,6 +290,6 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         wall = float(t.item())
     return {"minibatches_per_s": round(world * steps / wall, 2), "unit": "minibatches/s", "steps": steps,
             "ms_per_step_wall": round(wall / steps * 1e3, 3), "sampler_threads": pool_num, "warmup_steps": warm, "final_loss": round(last, 4),
-            "fused_epilogue": bool(fused),
+            "fused_epilogue": bool(fused), "flat_gradients": bool(flat_grads), "model": kind, "scale_factor": float(scale_factor),
             "note": "live LADIES sampling: numpy draw on the host + device array passes (bit-identical sampled sets), "
                     "gather in the sampler threads, then the same training step; wall clock incl. sampling"}

@@ -198,8 +198,10 @@ int gnn_csr_transpose(const int32_t *rowptr, const int32_t *colidx, const float 
  *     dev == devices[i]  -> src_dev[j] =  i, slot[j] = idx_of_nodes_on_device[input_nodes[j]]
  *     otherwise          -> src_dev[j] = -2, slot[j] = -1
  * and, when xrows != NULL,
- *     xrows[j] = bases[i] + slot[j]*ld_src     (bases[world] is the host table)
- * or NULL for src_dev -2.  The tables are the per-rank views produced by
+ *     xrows[j] = bases[i] + slot[j]*ld_src     (GPU shards; leading dimension ld_src)
+ *     xrows[j] = bases[world] + slot[j]*ld_host (host table; its own leading dimension, so an unpadded table can be
+ *                                                registered as it is instead of being copied into a padded one)
+ * or NULL for src_dev -2 and for a source whose base pointer is NULL (gather kernels skip NULL rows).  The tables are the per-rank views produced by
  * create_buffer (preprocess.py:311-407), resident on the device as int64.
  * counts (optional, int64 [world+2], zeroed by this call) receives the number of
  * rows per source: counts[i] for GPU i, counts[world] host, counts[world+1] invalid.
@@ -207,7 +209,7 @@ int gnn_csr_transpose(const int32_t *rowptr, const int32_t *colidx, const float 
 int gnn_placement_remap(const int64_t *input_nodes, int64_t n0,
                         const int64_t *device_id_of_nodes, const int64_t *idx_of_nodes_on_device,
                         const int64_t *devices, int64_t world,
-                        const float *const *bases, int64_t ld_src,
+                        const float *const *bases, int64_t ld_src, int64_t ld_host,
                         int32_t *src_dev, int64_t *slot, const float **xrows, int64_t *counts,
                         gnn_stream_t stream);
 

@@ -90,7 +90,7 @@ def coo_to_csr(indices, M):
     return rowptr, col32
 
 
-def placement_remap(input_nodes, dev_of, idx_of, devices, bases, ld_src):
+def placement_remap(input_nodes, dev_of, idx_of, devices, bases, ld_src, ld_host=None):
     lib = _native.cabi()
     n0 = int(input_nodes.numel())
     world = int(devices.numel())
@@ -99,7 +99,7 @@ def placement_remap(input_nodes, dev_of, idx_of, devices, bases, ld_src):
     xrows = torch.empty(n0, dtype=torch.int64, device="cuda")
     counts = torch.empty(world + 2, dtype=torch.int64, device="cuda")
     rc = lib.gnn_placement_remap(_ptr(input_nodes), n0, _ptr(dev_of), _ptr(idx_of), _ptr(devices), world, _ptr(bases), ld_src,
-                                 _ptr(src), _ptr(slot), _ptr(xrows), _ptr(counts), _stream())
+                                 ld_host if ld_host is not None else ld_src, _ptr(src), _ptr(slot), _ptr(xrows), _ptr(counts), _stream())
     _native.check(rc, "gnn_placement_remap")
     return src, slot, xrows, counts
 

@@ -43,6 +43,22 @@ def _worker(rank, world, port, out_dir):
     ok = ok and np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32))
     ok = ok and np.array_equal(ref, feats[mb.input_nodes])           # the gather reproduces the full table's rows
     n_peer = int(sum((o_src == i).sum() for i in range(world) if i != rank))
+    # fused gather + first-layer SpMM with the shards on DIFFERENT devices (local rows read in place, peer rows over
+    # NVLink and host rows over PCIe staged once): same bits as gather-then-SpMM, and within 1e-5 of the fp64 oracle
+    import custom_sparse_ops as cso
+    layer = mb.layers[0]
+    a = cso.create_coo_tensor(torch.from_numpy(layer.fullrowptr).to(device), torch.from_numpy(layer.rowptr).to(device),
+                              torch.from_numpy(layer.colidx).to(device), torch.from_numpy(layer.normfact).to(device), layer.nrows, layer.ncols)
+    adj = cso.adjacency_of(a)
+    y_fused = store.gather_spmm(adj, nodes)
+    y_staged = adj.matmul(out)
+    _, cols, vals = oracle.build_adj(layer.fullrowptr, layer.rowptr, layer.colidx32, layer.normfact, layer.nrows)
+    y_ref = oracle.spmm_f64acc(layer.rowptr, cols.astype(np.int32), vals, layer.nrows, np.ascontiguousarray(ref))
+    ok = ok and bool(torch.equal(y_fused, y_staged)) and oracle.rel_err(y_fused.cpu().numpy(), y_ref)[0] <= 1e-5
+    # prefetch on the store's side stream returns the same rows
+    buf, ev = store.prefetch(nodes)
+    torch.cuda.current_stream().wait_event(ev)
+    ok = ok and bool(torch.equal(buf, out))
     # gradient exchange: SUM over ranks
     p = torch.nn.Parameter(torch.zeros(1000, device=device))
     p.grad = torch.full_like(p, float(rank + 1))

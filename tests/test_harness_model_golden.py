@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 import oracle
-from gnn_b200 import graphgen, harness, sampler
+from gnn_b200 import graphgen, harness, models, sampler
 
 
 def test_sagenet_matches_reference_models(golden_dir):
@@ -20,14 +20,10 @@ def test_sagenet_matches_reference_models(golden_dir):
     for l in mb.layers:
         r, c, v = oracle.build_adj(l.fullrowptr, l.rowptr, l.colidx, l.normfact, l.nrows)
         adjs.append(torch.sparse_coo_tensor(torch.from_numpy(np.stack([r, c])), torch.from_numpy(v), (l.nrows, l.ncols)).coalesce())
-    net = harness.SageNet(shape.feat_dim, 16, [1, 1, 1], shape.num_classes, lambda a, x: torch.sparse.mm(a, x), dropout=0.0)
-    name_map = {}
-    for i in range(3):
-        for p in ["offset", "scale", "linearW.weight", "linearW.bias", "linearB.weight", "linearB.bias"]:
-            name_map[f"layers.{i}.{p}"] = f"encoder.gcs.{i}.{p}"
-    name_map["head.weight"], name_map["head.bias"] = "linear.weight", "linear.bias"
-    sd = {k: torch.from_numpy(z["w_" + v]) for k, v in name_map.items()}
-    net.load_state_dict(sd)
+    net = models.build_model("graphsage", shape.feat_dim, 16, [1, 1, 1], shape.num_classes, dropout=0.0,
+                             spmm=lambda a, x: torch.sparse.mm(a, x))
+    name_map = {k: k for k in net.state_dict()}                    # parameter names ARE the reference's
+    net.load_state_dict({k: torch.from_numpy(z["w_" + k]) for k in name_map})
     net.train()
     sn = [torch.from_numpy(np.asarray(s, dtype=np.int64)) for s in mb.sampled_nodes]
     out = net(torch.from_numpy(feats[mb.input_nodes]), adjs, sn)
