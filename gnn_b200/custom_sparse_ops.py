@@ -66,6 +66,14 @@ class Adjacency:
             self._t = Adjacency(t_rowptr, t_colidx, t_vals, self.ncols, self.nrows, t_rowidx)
         return self._t
 
+    def device_tensors(self):
+        """Every device tensor this adjacency (and its cached transpose) keeps alive - what a consumer on ANOTHER stream
+        must ``record_stream`` (the caching allocator hands a freed block back to the producing stream at once)."""
+        ts = [t for t in (self.rowptr, self.colidx, self.vals, self.rowidx) if t is not None]
+        if self._t is not None:
+            ts += self._t.device_tensors()
+        return ts
+
     def short_rows(self) -> bool:
         return self.nnz < SCATTER_MEAN_ROW * max(self.nrows, 1)
 

@@ -178,9 +178,6 @@ def record_stream(mb: DeviceMinibatch, stream) -> None:
     for layer, adj in zip(mb.layers, mb.adjs):
         if layer is None:
             continue
-        a = adjacency_of(adj)
-        ts = [layer.fullrowptr, layer.rowptr, layer.colidx, layer.normfact, adj._indices(), adj._values(), a.colidx]
-        if a._t is not None:
-            ts += [a._t.rowptr, a._t.colidx, a._t.vals]
+        ts = [layer.fullrowptr, layer.rowptr, layer.colidx, layer.normfact, adj._indices(), adj._values()] + adjacency_of(adj).device_tensors()
         for t in ts:
             t.record_stream(stream)

@@ -139,10 +139,7 @@ class DevicePrefetcher:
         tensors = [x0, counts]
         for a in adjs:
             if a is not None:
-                adj = adjacency_of(a)
-                tensors += [a._indices(), a._values(), adj.rowptr, adj.colidx]
-                if adj._t is not None:
-                    tensors += [adj._t.rowptr, adj._t.colidx, adj._t.vals]
+                tensors += [a._indices(), a._values()] + adjacency_of(a).device_tensors()
         for t in tensors:
             t.record_stream(cur)
         return adjs, x0, counts
