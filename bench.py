@@ -808,9 +808,7 @@ def run_e2e(args, cso, store, mbs, widths, step_bytes, device, rank, world, log)
             if rep == 1:
                 ev[0].record()
             if sid is None:
-                for i in range(world):
-                    if i != rank:
-                        store.ext.gather_rows_src(xrows, src_dev, i, store.feat_dim, outbuf)
+                store.ext.gather_rows_src(xrows, src_dev, -100000 - rank, store.feat_dim, outbuf)     # GNN_SRC_PEERS(rank): one launch
             else:
                 store.ext.gather_rows_src(xrows, src_dev, sid, store.feat_dim, outbuf)
         ev[1].record()

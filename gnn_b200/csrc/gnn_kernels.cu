@@ -1096,6 +1096,36 @@ __global__ void column_partials_reduce_kernel(const float *__restrict__ part_sca
 
 constexpr int kEpiCtas = 296;        // 2 per SM: row loop is grid-strided, partial buffers stay small
 
+#include "epilogue_vec.cuh"
+
+inline bool aligned16(const void *p, int64_t ld) { return ((reinterpret_cast<uintptr_t>(p) | (uintptr_t)(ld * 4)) & 15) == 0; }
+
+template <int PER4>
+int elu_rownorm_fwd_vec_launch(const float *x, int64_t ldx, int64_t M, int64_t C, const float *scale, const float *offset,
+                               float *y, int64_t ldy, float *mean, float *rstd, cudaStream_t st) {
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(M, 8), 148 * 8);
+  elu_rownorm_fwd_vec_kernel<PER4><<<grid, 256, 0, st>>>(x, ldx, (int)M, (int)C, scale, offset, y, ldy, mean, rstd);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int PER4>
+int elu_rownorm_bwd_vec_launch(const float *dy, int64_t lddy, const float *x, int64_t ldx, int64_t M, int64_t C,
+                               const float *scale, const float *mean, const float *rstd, float *dx, int64_t lddx,
+                               float *dscale, float *doffset, float *ws, cudaStream_t st) {
+  const int wpb = 8;
+  const size_t smem = (size_t)2 * wpb * C * sizeof(float);               // <= 64 KB for C <= 1024 (two CTAs per SM)
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(M, wpb), kEpiCtas);
+  if (smem > 48 * 1024)
+    GNN_CUDA(cudaFuncSetAttribute(elu_rownorm_bwd_vec_kernel<PER4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  float *ps = ws, *po = ws + (size_t)kEpiCtas * C;
+  elu_rownorm_bwd_vec_kernel<PER4><<<grid, wpb * 32, smem, st>>>(dy, lddy, x, ldx, (int)M, (int)C, scale, mean, rstd, dx, lddx, ps, po);
+  GNN_LAUNCH_CHECK();
+  column_partials_reduce_kernel<<<(unsigned)cdiv(C, 256), 256, 0, st>>>(ps, po, (int)grid, (int)C, dscale, doffset);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int PER>
 int elu_rownorm_fwd_launch(const float *x, int64_t ldx, int64_t M, int64_t C, const float *scale, const float *offset,
                                   float *y, int64_t ldy, float *mean, float *rstd, cudaStream_t st) {
@@ -1166,7 +1196,8 @@ gather_rows_kernel(const float *const *__restrict__ xrows, const int *__restrict
     if (FILTER) {
       const int sd = src_dev[j];
       const bool take = only_src == GNN_SRC_DEVICES ? sd >= 0
-                        : (only_src <= GNN_SRC_NOT(0) ? (sd != GNN_SRC_NOT(only_src) && sd != -2) : sd == only_src);
+                        : (only_src <= GNN_SRC_PEERS(0) ? (sd >= 0 && sd != -(only_src + 100000))
+                        : (only_src <= GNN_SRC_NOT(0) ? (sd != GNN_SRC_NOT(only_src) && sd != -2) : sd == only_src));
       if (!take) continue;
     }
     const float *src = INDEX ? X + idx[j] * ldx : xrows[j];
@@ -1594,6 +1625,13 @@ int gnn_elu_rownorm_fwd_f32(const float *x, int64_t ldx, int64_t M, int64_t C, c
   if (!x || !scale || !offset || !y || !mean || !rstd || ldx < C || ldy < C) return GNN_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int per = (int)cdiv(C, 32);
+  if (C % 4 == 0 && C <= 1024 && aligned16(x, ldx) && aligned16(y, ldy) && aligned16(scale, 4) && aligned16(offset, 4)) {
+    const int per4 = (int)cdiv(C, 128);
+    if (per4 <= 1) return elu_rownorm_fwd_vec_launch<1>(x, ldx, M, C, scale, offset, y, ldy, mean, rstd, st);
+    if (per4 <= 2) return elu_rownorm_fwd_vec_launch<2>(x, ldx, M, C, scale, offset, y, ldy, mean, rstd, st);
+    if (per4 <= 4) return elu_rownorm_fwd_vec_launch<4>(x, ldx, M, C, scale, offset, y, ldy, mean, rstd, st);
+    return elu_rownorm_fwd_vec_launch<8>(x, ldx, M, C, scale, offset, y, ldy, mean, rstd, st);
+  }
   if (per <= 4) return elu_rownorm_fwd_launch<4>(x, ldx, M, C, scale, offset, y, ldy, mean, rstd, st);
   if (per <= 8) return elu_rownorm_fwd_launch<8>(x, ldx, M, C, scale, offset, y, ldy, mean, rstd, st);
   if (per <= 16) return elu_rownorm_fwd_launch<16>(x, ldx, M, C, scale, offset, y, ldy, mean, rstd, st);
@@ -1618,6 +1656,13 @@ int gnn_elu_rownorm_bwd_f32(const float *dy, int64_t lddy, const float *x, int64
   if (!workspace || workspace_bytes < gnn_elu_rownorm_workspace_bytes(C)) return GNN_E_WORKSPACE;
   float *ws = reinterpret_cast<float *>(workspace);
   const int per = (int)cdiv(C, 32);
+  if (C % 4 == 0 && C <= 1024 && aligned16(x, ldx) && aligned16(dy, lddy) && aligned16(dx, lddx) && aligned16(scale, 4)) {
+    const int per4 = (int)cdiv(C, 128);
+    if (per4 <= 1) return elu_rownorm_bwd_vec_launch<1>(dy, lddy, x, ldx, M, C, scale, mean, rstd, dx, lddx, dscale, doffset, ws, st);
+    if (per4 <= 2) return elu_rownorm_bwd_vec_launch<2>(dy, lddy, x, ldx, M, C, scale, mean, rstd, dx, lddx, dscale, doffset, ws, st);
+    if (per4 <= 4) return elu_rownorm_bwd_vec_launch<4>(dy, lddy, x, ldx, M, C, scale, mean, rstd, dx, lddx, dscale, doffset, ws, st);
+    return elu_rownorm_bwd_vec_launch<8>(dy, lddy, x, ldx, M, C, scale, mean, rstd, dx, lddx, dscale, doffset, ws, st);
+  }
   if (per <= 4) return elu_rownorm_bwd_launch<4>(dy, lddy, x, ldx, M, C, scale, mean, rstd, dx, lddx, dscale, doffset, ws, st);
   if (per <= 8) return elu_rownorm_bwd_launch<8>(dy, lddy, x, ldx, M, C, scale, mean, rstd, dx, lddx, dscale, doffset, ws, st);
   if (per <= 16) return elu_rownorm_bwd_launch<16>(dy, lddy, x, ldx, M, C, scale, mean, rstd, dx, lddx, dscale, doffset, ws, st);

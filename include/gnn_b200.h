@@ -233,6 +233,8 @@ int gnn_gather_rows_f32(const float *const *xrows, int64_t n0, int64_t F,
 /* GNN_SRC_NOT(i): every valid row NOT held by source i (e.g. everything that is not in the local shard);
  * the macro is its own inverse: GNN_SRC_NOT(GNN_SRC_NOT(i)) == i. */
 #define GNN_SRC_NOT(i) (-200 - (i))
+/* GNN_SRC_PEERS(i): every row held by a GPU other than i (one launch pulls all peer shards over NVLink). */
+#define GNN_SRC_PEERS(i) (-100000 - (i))
 int gnn_gather_rows_src_f32(const float *const *xrows, const int32_t *src_dev, int32_t only_src,
                             int64_t n0, int64_t F, float *out, int64_t ld_out, gnn_stream_t stream);
 
