@@ -26,6 +26,10 @@ KEYS = [
     ("l1tex__throughput.avg.pct_of_peak_sustained_active", "L1 %"),
     ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
     ("lts__t_sectors_srcunit_tex_op_read.sum", "L2->L1 sectors"),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2->SM bytes"),
+    ("derived__lts__lts2xbar_bytes.sum.per_second", "L2->xbar rate"),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed", "SM ingest % of peak"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 data pipe %"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
@@ -48,8 +52,12 @@ def main():
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, body = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
-    out = [f"# ncu --set full, round {tag}: captured launches of `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-train`",
-           "", "Cold-cache, serialised replays: read shares and ratios, not absolute times.", "",
+    out = [f"# ncu --set full, round {tag}: captured launches of `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-train "
+           "--no-other-workloads --no-ref-gpu --skip-gate` (one timed step: fwd0, fwd1, fwd2, A^T build + bwd1, scatter bwd2)",
+           "", "Cold-cache, serialised replays: read shares and ratios, not absolute times.  `L2->xbar rate` is against ncu's own",
+           "`derived__lts__lts2xbar_bytes.sum.peak_sustained` = 11,776 B/clk (184 L2 slices x 64 B) = 23.1 TB/s at 1.96 GHz: the dense SpMM",
+           "launches run at 18.2-18.7 TB/s = 79-81 % of it (the gather-only probe kernel: 19.2-19.6 TB/s = 83-85 %), while the SM side",
+           "(`SM ingest`) is only half used - the L2 output ports, not HBM (4-7 %) and not the SMs, bind these kernels.", "",
            "| # | kernel | grid | " + " | ".join(n for _, n in KEYS) + " |", "|---|---|---|" + "---|" * len(KEYS)]
     traffic = {}
     spmm_seen = 0
@@ -63,7 +71,7 @@ def main():
             f = num(v)
             cells.append(f"{f:.4g} {u}".strip() if f is not None else v)
         out.append(f"| {i} | `{name}` | {r[idx['Grid Size']]} | " + " | ".join(cells) + " |")
-        if name.startswith("spmm_rowsplit") and spmm_seen < len(op_order):
+        if (name.startswith("spmm_rowsplit") or name.startswith("spmm_scatter") or name.startswith("spmm_flat")) and spmm_seen < len(op_order):
             rd, wr = num(r[idx["dram__bytes_read.sum"]]), num(r[idx["dram__bytes_write.sum"]])
             scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
             b = rd * scale.get(units[idx["dram__bytes_read.sum"]], 1.0) + wr * scale.get(units[idx["dram__bytes_write.sum"]], 1.0)
