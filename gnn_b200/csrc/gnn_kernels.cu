@@ -266,35 +266,11 @@ spmm_rowsplit_kernel(const SpmmParams p, const XSrc<GATHER> xs) {
     if (c_first == c_last) {
       store_row<VEC, NV, LPR>(yrow, y_vec_ok, lane, col0, p.D, acc);
     } else {
-      // partial of (row r, chunk): slot 2*chunk + (row starts strictly inside this chunk)
+      // partial of (row r, chunk): slot 2*chunk + (row starts strictly inside this chunk); the last chunk to arrive adds
+      // the partials in ascending chunk order (spmm_flat.cuh: finish_spanning_row)
       float *slot = p.partials + ((int64_t)2 * chunk + (row_start > chunk * p.C ? 1 : 0)) * p.Dp;
       store_row<VEC, NV, LPR>(slot, true, lane, col0, p.D, acc);
-      __threadfence();
-      __syncwarp();
-      int last = 0;
-      // atomicInc wraps to 0 on the last arrival: counters that are zero on entry are zero again on exit
-      if (lane == 0)
-        last = (atomicInc(reinterpret_cast<unsigned *>(p.counters) + (int64_t)r * p.nslabs + slab, (unsigned)(c_last - c_first)) ==
-                (unsigned)(c_last - c_first));
-      last = __shfl_sync(kFull, last, 0);
-      if (last) {
-        __threadfence();
-#pragma unroll
-        for (int n = 0; n < NV; ++n) vzero<VEC>(acc[n]);
-        if (lane < LPR) {
-          for (int ch = c_first; ch <= c_last; ++ch) {
-            const float *ps = p.partials + ((int64_t)2 * ch + (row_start > ch * p.C ? 1 : 0)) * p.Dp;
-#pragma unroll
-            for (int n = 0; n < NV; ++n) {
-              const int col = col0 + n * LPR * VEC;
-#pragma unroll
-              for (int q = 0; q < VEC; ++q)
-                if (col + q < p.D) acc[n][q] += __ldcg(ps + col + q);
-            }
-          }
-        }
-        store_row<VEC, NV, LPR>(yrow, y_vec_ok, lane, col0, p.D, acc);
-      }
+      finish_spanning_row<VEC, NV, LPR>(p, r, slab, lane, col0, row_start, c_first, c_last, p.C, yrow, y_vec_ok);
     }
     s = seg_end;
     if (seg_end == row_end) {
@@ -753,13 +729,14 @@ transpose_pass_kernel(uint2 *__restrict__ cells, int M, int nnz, int words_per_c
   }
 }
 
-// exclusive scan of in[0..n) into out[0..n], out[n] = total, by ONE CTA of 1024 threads.  Tiles of 32 K elements:
+// exclusive scan of in[0..n) into out[0..n], out[n] = total, by ONE CTA of WARPS warps.  Tiles of 1024 * WARPS elements:
 // warp w owns 1024 consecutive ones as 32 coalesced rows of 32 (all loads issued together), shuffle scans per row
 // with a running carry, then one 32-entry scan over the warp totals.
-__device__ __forceinline__ void block_exclusive_scan_1024(const int *__restrict__ in, int n, int *__restrict__ out, int *sm33) {
+template <int WARPS>
+__device__ __forceinline__ void block_exclusive_scan(const int *__restrict__ in, int n, int *__restrict__ out, int *sm33) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int carry = 0;
-  for (int base = 0; base < n; base += 32768) {
+  for (int base = 0; base < n; base += 1024 * WARPS) {
     const int seg = base + warp * 1024 + lane;
     int v[32];
 #pragma unroll
@@ -779,7 +756,7 @@ __device__ __forceinline__ void block_exclusive_scan_1024(const int *__restrict_
     if (lane == 0) sm33[warp] = run;
     __syncthreads();
     if (warp == 0) {
-      int w = sm33[lane];
+      int w = lane < WARPS ? sm33[lane] : 0;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const int y = __shfl_up_sync(kFull, w, off);
@@ -789,7 +766,7 @@ __device__ __forceinline__ void block_exclusive_scan_1024(const int *__restrict_
     }
     __syncthreads();
     const int offset = carry + (warp ? sm33[warp - 1] : 0);
-    carry += sm33[31];
+    carry += sm33[WARPS - 1];
 #pragma unroll
     for (int it = 0; it < 32; ++it)
       if (seg + it * 32 < n) out[seg + it * 32] = v[it] + offset;
@@ -802,7 +779,7 @@ __device__ __forceinline__ void block_exclusive_scan_1024(const int *__restrict_
 //   cursor != NULL (multi-block mode): first cursor[c] += counts[c] (the previous block's count), then counts[c] = this block's.
 //   t_rowptr != NULL (single-block mode): the CTA that finishes last turns the counts into the row pointer of A^T
 //   (saves a launch; `done` is a zeroed word in the workspace).
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 bitmap_prefix_kernel(uint2 *__restrict__ cells, int K, int words_per_col, int *__restrict__ counts, int *__restrict__ cursor,
                      int advance, int *__restrict__ t_rowptr, unsigned *__restrict__ done) {
   __shared__ int sm33[33];
@@ -833,7 +810,7 @@ bitmap_prefix_kernel(uint2 *__restrict__ cells, int K, int words_per_col, int *_
     __syncthreads();
     if (!sm33[32]) return;
     __threadfence();
-    block_exclusive_scan_1024(counts, K, t_rowptr, sm33);
+    block_exclusive_scan<8>(counts, K, t_rowptr, sm33);
   }
 }
 
@@ -1456,14 +1433,14 @@ int gnn_csr_transpose(const int32_t *rowptr, const int32_t *colidx, const float 
   uint2 *cells = reinterpret_cast<uint2 *>(ws + L.off_cells);
   const size_t cell_bytes = (size_t)K * L.wpc * sizeof(uint2);
   const unsigned pass_grid = (unsigned)cdiv(cdiv(nnz, kTrChunk), 8);
-  const unsigned prefix_grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(K, 32), 148 * 2));
+  const unsigned prefix_grid = warp_grid(K, 8);          // one warp per column, 256-thread CTAs
   if (L.nblocks == 1) {
     // `done` sits right in front of the cells: one memset zeroes both
     GNN_CUDA(cudaMemsetAsync(done, 0, (L.off_cells - L.off_done) + cell_bytes, st));
     transpose_pass_kernel<false><<<pass_grid, 256, 0, st>>>(cells, (int)M, (int)nnz, L.wpc, 0, (int)M, rowptr, colidx, vals,
                                                            nullptr, t_colidx, t_vals, nullptr);
     GNN_LAUNCH_CHECK();
-    bitmap_prefix_kernel<<<prefix_grid, 1024, 0, st>>>(cells, (int)K, L.wpc, counts, nullptr, 0, t_rowptr, done);
+    bitmap_prefix_kernel<<<prefix_grid, 256, 0, st>>>(cells, (int)K, L.wpc, counts, nullptr, 0, t_rowptr, done);
     GNN_LAUNCH_CHECK();
     transpose_pass_kernel<true><<<pass_grid, 256, 0, st>>>(cells, (int)M, (int)nnz, L.wpc, 0, (int)M, rowptr, colidx, vals,
                                                           t_rowptr, t_colidx, t_vals, t_rowidx);
@@ -1485,7 +1462,7 @@ int gnn_csr_transpose(const int32_t *rowptr, const int32_t *colidx, const float 
     transpose_pass_kernel<false><<<pass_grid, 256, 0, st>>>(cells, (int)M, (int)nnz, L.wpc, row0, row1, rowptr, colidx, vals,
                                                            nullptr, t_colidx, t_vals, nullptr);
     GNN_LAUNCH_CHECK();
-    bitmap_prefix_kernel<<<prefix_grid, 1024, 0, st>>>(cells, (int)K, L.wpc, counts, cursor, blk > 0 ? 1 : 0, nullptr, done);
+    bitmap_prefix_kernel<<<prefix_grid, 256, 0, st>>>(cells, (int)K, L.wpc, counts, cursor, blk > 0 ? 1 : 0, nullptr, done);
     GNN_LAUNCH_CHECK();
     transpose_pass_kernel<true><<<pass_grid, 256, 0, st>>>(cells, (int)M, (int)nnz, L.wpc, row0, row1, rowptr, colidx, vals,
                                                           cursor, t_colidx, t_vals, t_rowidx);

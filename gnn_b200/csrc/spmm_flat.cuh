@@ -22,10 +22,15 @@ constexpr int kFlatMaxC = 128;
 // Finish a row that spans several chunks: this warp's partial is already stored in its slot.  The last warp to
 // arrive adds the partials in ascending chunk order and stores the row.  atomicInc wraps to 0 on the last arrival, so
 // a counter array that is zero on entry is zero again when the kernel has finished (see GNN_SPMM_COUNTERS_ZEROED).
+//
+// A hub row of a sparse block spans dozens of chunks (1,468 entries = 46 chunks of 32): adding its partials one
+// dependent L2 load at a time was a 25 us tail on a 30 us kernel.  The loads are independent - only the ADDITIONS have
+// a fixed order - so B partials are fetched together (128-bit ld.cg: partials bypass L1, which is why the last arriver
+// needs no acquire fence of its own) and then added in order.
 template <int VEC, int NV, int LPR>
 __device__ __noinline__ void finish_spanning_row(const SpmmParams &p, int r, int slab, int lane, int col0, int row_start,
                                                  int c_first, int c_last, int C, float *yrow, bool y_vec_ok) {
-  __threadfence();
+  __threadfence();                                   // release: this warp's partial is visible before its arrival
   __syncwarp();
   int last = 0;
   if (lane == 0)
@@ -33,19 +38,37 @@ __device__ __noinline__ void finish_spanning_row(const SpmmParams &p, int r, int
             (unsigned)(c_last - c_first));
   last = __shfl_sync(kFull, last, 0);
   if (!last) return;
-  __threadfence();
+  constexpr int B = NV * VEC >= 12 ? 2 : (NV * VEC >= 8 ? 4 : 8);      // partials in flight per lane (register budget of the caller)
   float acc[NV][VEC];
 #pragma unroll
   for (int n = 0; n < NV; ++n) vzero<VEC>(acc[n]);
   if (lane < LPR) {
-    for (int ch = c_first; ch <= c_last; ++ch) {
-      const float *ps = p.partials + ((int64_t)2 * ch + (row_start > ch * C ? 1 : 0)) * p.Dp;
+    for (int ch0 = c_first; ch0 <= c_last; ch0 += B) {
+      float t[B][NV][VEC];
 #pragma unroll
-      for (int n = 0; n < NV; ++n) {
-        const int col = col0 + n * LPR * VEC;
+      for (int j = 0; j < B; ++j) {
+        const int ch = min(ch0 + j, c_last);
+        const float *ps = p.partials + ((int64_t)2 * ch + (row_start > ch * C ? 1 : 0)) * p.Dp;
 #pragma unroll
-        for (int q = 0; q < VEC; ++q)
-          if (col + q < p.D) acc[n][q] += __ldcg(ps + col + q);
+        for (int n = 0; n < NV; ++n) {
+          const int col = col0 + n * LPR * VEC;
+          if (VEC == 4 && col + 4 <= p.Dp) {         // slots are Dp (multiple of 4) wide and 16-byte aligned
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(ps + col));
+            t[j][n][0] = v.x; t[j][n][1 % VEC] = v.y; t[j][n][2 % VEC] = v.z; t[j][n][3 % VEC] = v.w;
+          } else {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) t[j][n][q] = col + q < p.D ? __ldcg(ps + col + q) : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        if (ch0 + j <= c_last) {
+#pragma unroll
+          for (int n = 0; n < NV; ++n)
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) acc[n][q] += t[j][n][q];
+        }
       }
     }
   }

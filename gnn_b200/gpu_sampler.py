@@ -136,7 +136,8 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
         nz = nz_dev.cpu().numpy()
         pi_nz = scratch.counts[nz_dev].cpu().numpy().astype(np.int64)                       # :117 on the support
         if scale_factor > 1:                                                                # :119-121
-            pi_nz = pi_nz.astype(np.float64)
+            # integer counts stay integer (the reference assigns the scaled values into scipy's int64 count array, which
+            # truncates them), so the normaliser below is an exact integer sum on the support as on the full array
             sel = np.isin(nz, skewed_sampling_nodes[len(orders1) - d - 1])
             pi_nz[sel] = pi_nz[sel] * scale_factor
         p_nz = pi_nz / np.sum(pi_nz)                                                        # :124 (same quotients)
@@ -147,11 +148,13 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
         p_after = np.where(nz[pos] == after_nodes, p_nz[pos], 0.0)                          # p[after_nodes]
         after_dev = torch.from_numpy(after_nodes.astype(np.int64, copy=False)).to(dev)
         ext.lookup_set(scratch.lookup, after_dev, True)
-        rowptr = ext.column_slice_count(ucols, fullrowptr, scratch.lookup)                    # :133,135
-        nnz = int(rowptr[-1].item())
-        use16 = int16_ids and after_nodes.size <= 32768
-        colidx = ext.column_slice_fill(ucols, fullrowptr, scratch.lookup, rowptr, nnz, use16)  # :136
-        ext.lookup_set(scratch.lookup, after_dev, False)
+        try:
+            rowptr = ext.column_slice_count(ucols, fullrowptr, scratch.lookup)                # :133,135
+            nnz = int(rowptr[-1].item())
+            use16 = int16_ids and after_nodes.size <= 32768
+            colidx = ext.column_slice_fill(ucols, fullrowptr, scratch.lookup, rowptr, nnz, use16)  # :136
+        finally:
+            ext.lookup_set(scratch.lookup, after_dev, False)      # the table must be all -1 for the next minibatch, whatever happened
         normfact = 1 / np.clip(s_num * p_after, 1e-10, 1).astype(np.float32)                # :137
         nf_dev = torch.from_numpy(normfact).to(dev)
         layer = DeviceLayer(fullrowptr, rowptr, colidx, nf_dev, int(previous_nodes.size), int(after_nodes.size))

@@ -128,7 +128,8 @@ def ladies_sample(seed: int, batch_nodes, samp_num_list: Sequence[int], num_node
         fullrowptr, u_cols, lens = row_slice(indptr, indices, previous_nodes)      # :113-114
         pi = np.bincount(u_cols, minlength=num_nodes)                              # :117
         if scale_factor > 1:                                                       # :119-121
-            pi = pi.astype(np.float64)
+            # `pi` is an INTEGER array in the reference too (scipy's ord=0 column norm counts nonzeros as int64), so the
+            # scaled counts are truncated toward zero by the assignment - 3 * 1.5 -> 4.  Kept: sampled sets stay identical.
             sel = skewed_sampling_nodes[len(orders1) - d - 1]
             pi[sel] = pi[sel] * scale_factor
         p = pi / np.sum(pi)                                                        # :124

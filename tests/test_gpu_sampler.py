@@ -68,3 +68,24 @@ def test_device_sampler_matches_reference_golden(gs, golden_dir):
                 assert np.array_equal(getattr(a, k).cpu().numpy(), z[lp + k]), k
             assert np.array_equal(got.sampled_nodes[li], z[lp + "sampled_nodes"])
         assert got.input_nodes.size == int(z[f"s{si}_n0"])
+
+
+@pytest.mark.parametrize("tag", ["gcn", "sage"])
+def test_device_sampler_locality_sampling_matches_reference(gs, golden_dir, tag):
+    """--locality_sampling on the device sampler: scale factors 2, 1.5 and 16 (the reference truncates the scaled integer
+    counts, sampler.py:119-121 on scipy's int64 column norm) against arrays captured from the unmodified reference."""
+    z = np.load(os.path.join(golden_dir, "locality_small.npz"))
+    shape = graphgen.SHAPES[str(z[tag + "_shape"])]
+    g = graphgen.generate(shape, seed=0)
+    dg = gs.DeviceGraph(g.indptr, g.indices, "cuda")
+    orders = [int(o) for o in z[tag + "_orders"]]
+    sets = [z[f"{tag}_set{i}"] for i in range(len(orders))]
+    for ci in range(3):
+        c = f"{tag}_c{ci}_"
+        got = gs.ladies_sample_device(int(z[c + "seed"]), z[c + "batch_nodes"], [int(z[tag + "_samp_num"])] * 5, dg, orders,
+                                      skewed_sampling_nodes=sets, scale_factor=float(z[c + "scale_factor"]))
+        assert got.input_nodes.size == int(z[c + "n0"])
+        for li, a in enumerate(got.layers):
+            for k in ["fullrowptr", "rowptr", "colidx", "normfact"]:
+                assert np.array_equal(getattr(a, k).cpu().numpy(), z[c + f"l{li}_{k}"]), (tag, ci, li, k)
+            assert np.array_equal(got.sampled_nodes[li], z[c + f"l{li}_sampled_nodes"])
