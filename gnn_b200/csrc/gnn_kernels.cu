@@ -313,14 +313,15 @@ inline bool flat_wanted(int64_t M, int64_t nnz, int64_t D) {
   return nnz <= kFlatMaxNnz && nnz < kFlatMeanRow * std::max<int64_t>(M, 1);
 }
 
-// flat chunk (entries per warp item): 64; 128 for wide rows (two vectors per lane halve the passes over the index
-// stream); 32 when the whole problem is a fraction of a wave anyway
+// flat chunk (entries per warp item): 64; 128 for the widest rows; 32 when the whole problem is a fraction of a wave
+// anyway (profiles/r2_kernel_ab.md)
+inline bool flat_tiny(int64_t nnz, int64_t D) { return cdiv(nnz, 64) * cdiv(D, 128) < 2048; }
 inline int flat_chunk(int64_t nnz, int64_t D) {
 #ifdef GNN_TUNE
   if (getenv("GNN_TUNE_FC")) return atoi(getenv("GNN_TUNE_FC"));
 #endif
-  if (cdiv(nnz, 64) * cdiv(D, 128) < 1024) return 32;
-  return D >= 512 ? 128 : 64;
+  if (flat_tiny(nnz, D)) return 32;
+  return D >= 1024 ? 128 : 64;
 }
 
 struct SpmmPlan { int kind, vec, nv, lpr, nslabs, C, nchunks, Dp, u; };   // kind: 0 row-split, 1 flat
@@ -339,8 +340,10 @@ inline SpmmPlan make_plan(int64_t M, int64_t nnz, int64_t D, int vec) {
     pl.C = flat_chunk(nnz, D);
     pl.nchunks = (int)cdiv(nnz, pl.C);
     const int64_t n = cdiv(nvec, 32);              // vector columns per lane
-    pl.nv = (pl.C == 128 && n >= 2) ? 2 : 1;
-    pl.u = pl.nv == 1 ? (D < 256 ? 16 : 8) : 8;
+    // vectors per lane: wide rows walk the index stream fewer times (D >= 512: 4, D >= 256: 2); tiny problems keep the
+    // most warps (1)
+    pl.nv = flat_tiny(nnz, D) ? 1 : (D >= 512 && n >= 4 ? 4 : (D >= 256 && n >= 2 ? 2 : 1));
+    pl.u = pl.nv == 1 ? 16 : (pl.nv == 2 ? 8 : 4);
 #ifdef GNN_TUNE
     if (getenv("GNN_TUNE_FNV")) pl.nv = atoi(getenv("GNN_TUNE_FNV"));
     if (getenv("GNN_TUNE_FU")) pl.u = atoi(getenv("GNN_TUNE_FU"));
