@@ -89,14 +89,16 @@ def legacy_choice_on_support(rs: np.random.RandomState, p_nz: np.ndarray, size: 
             p[found[0:n_uniq]] = 0
         cdf = np.cumsum(p)
         cdf /= cdf[-1]
-        new = cdf.searchsorted(x, side="right")
-        # == `_, unique_indices = np.unique(new, return_index=True); unique_indices.sort()`: first occurrences, in draw order
-        order = np.argsort(new, kind="stable")
-        snew = new[order]
-        first = np.empty(snew.size, dtype=bool)
-        first[0] = True
-        np.not_equal(snew[1:], snew[:-1], out=first[1:])
-        unique_indices = np.sort(order[first])
+        # searchsorted with SORTED needles walks the cdf once instead of 8 K random binary searches over 200 K entries;
+        # the positions found are the same, so the draw is unchanged
+        xo = np.argsort(x, kind="stable")
+        snew = cdf.searchsorted(x[xo], side="right")              # non-decreasing, like x[xo]
+        new = np.empty(x.size, dtype=np.int64)
+        new[xo] = snew
+        # == `_, unique_indices = np.unique(new, return_index=True); unique_indices.sort()`: the FIRST draw of every
+        # distinct value, in draw order = the smallest original index inside each run of equal values of the sorted array
+        starts = np.flatnonzero(np.concatenate(([True], snew[1:] != snew[:-1])))
+        unique_indices = np.sort(np.minimum.reduceat(xo, starts))
         new = new.take(unique_indices)
         found[n_uniq:n_uniq + new.size] = new
         n_uniq += new.size

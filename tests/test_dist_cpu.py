@@ -32,6 +32,27 @@ def _worker(rank, world, port, out_dir):
     expect = sum(r + 1 for r in range(world))
     ok = all(torch.allclose(p.grad, torch.full_like(p, float(expect) * (i + 1))) for i, p in enumerate(params) if p.grad is not None)
     ok = ok and params[1].grad is None and nbytes == 4 * sum(p.numel() for i, p in enumerate(params) if i != 1)
+    # FlatGradients: clip every replica to norm 5 (main.py:146), THEN sum the replicas (main.py:149-168) - on one flat
+    # buffer the parameters' .grad are views of; must equal clip_grad_norm_ + exchange_gradients on a twin model
+    torch.manual_seed(1)
+    twin_a = torch.nn.Sequential(torch.nn.Linear(7, 9), torch.nn.ELU(), torch.nn.Linear(9, 4))
+    twin_b = torch.nn.Sequential(torch.nn.Linear(7, 9), torch.nn.ELU(), torch.nn.Linear(9, 4))
+    twin_b.load_state_dict(twin_a.state_dict())
+    pa, pb = list(twin_a.parameters()), list(twin_b.parameters())
+    flat = harness.FlatGradients(pb, world, max_norm=5.0)
+    for step in range(2):
+        x = torch.randn(6, 7, generator=torch.Generator().manual_seed(10 * rank + step)) * (40.0 if step == 0 else 0.01)
+        for q in pa:
+            q.grad = None
+        twin_a(x).square().sum().backward()
+        torch.nn.utils.clip_grad_norm_(pa, 5)
+        harness.exchange_gradients(pa, world)
+        flat.zero()
+        twin_b(x).square().sum().backward()
+        nb = flat.clip_and_exchange()
+        ok = ok and nb == 4 * sum(q.numel() for q in pb)
+        ok = ok and all(q.grad.data_ptr() == flat.flat[o:].data_ptr() for q, o in zip(pb, np.cumsum([0] + [q.numel() for q in pb[:-1]])))
+        ok = ok and all(torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-7) for a, b in zip(pa, pb))
     batches = sampler.rank_batches(1001, 64, rank, world, iter_num=3)
     np.save(os.path.join(out_dir, f"b{rank}.npy"), np.concatenate(batches))
     np.save(os.path.join(out_dir, f"n{rank}.npy"), np.array([len(batches), int(ok)]))

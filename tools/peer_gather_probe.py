@@ -24,8 +24,13 @@ ext = cso.spmm_cpp
 d0, d1 = torch.device("cuda", 0), torch.device("cuda", 1)
 ld = gmod.padded_ld(F)
 shard = torch.randn(262144, ld, device=d1)
-torch.zeros(1, device=d1).to(d0)                       # makes torch enable peer access 0 <-> 1
+torch.zeros(1, device=d1).to(d0)
 torch.cuda.set_device(0)
+import ctypes
+rt = ctypes.CDLL("libcudart.so.12")                    # already loaded by torch; kernels on cuda:0 may then dereference cuda:1 memory
+rc = rt.cudaDeviceEnablePeerAccess(ctypes.c_int(1), ctypes.c_uint(0))
+assert rc in (0, 704), f"cudaDeviceEnablePeerAccess -> {rc}"        # 704 = already enabled
+rt.cudaGetLastError()
 gen = torch.Generator(device=d0).manual_seed(1)
 slots = torch.randint(0, shard.shape[0], (rows,), device=d0, generator=gen)
 ptrs = shard.data_ptr() + slots * (ld * 4)
