@@ -595,8 +595,12 @@ def main():
         pool_wide = 8 if cores // max(world, 1) >= 16 else 4
         for key, fn, kw in [("fused_epilogue_model", harness.bench_train, dict(fused=True)),
                             ("fused_epilogue_flat_gradients", harness.bench_train, dict(fused=True, flat_grads=True)),
+                            # + the layers' dense linears (and the gather / concat around them) on tcgen05 in 3xTF32
+                            ("tensor_core_linears", harness.bench_train, dict(fused=True, flat_grads=True, tc=True)),
                             ("live_sampler", harness.bench_train_live, dict(fused=False, pool_num=4)),
-                            ("live_sampler_fused_epilogue", harness.bench_train_live, dict(fused=True, pool_num=pool_wide, flat_grads=True))]:
+                            ("live_sampler_fused_epilogue", harness.bench_train_live, dict(fused=True, pool_num=pool_wide, flat_grads=True)),
+                            ("live_sampler_tensor_core_linears", harness.bench_train_live,
+                             dict(fused=True, pool_num=pool_wide, flat_grads=True, tc=True))]:
             try:
                 if fn is harness.bench_train:
                     train[key] = fn(args, cso, store, shape, g, mbs, ORDERS, NHID, device, rank, world, log, **kw)

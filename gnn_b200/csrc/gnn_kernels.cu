@@ -10,11 +10,13 @@
 // nnz-balanced chunking with a fixed-order fix-up instead of atomics.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 
 #include "gnn_b200.h"
@@ -1218,6 +1220,7 @@ inline unsigned warp_grid(int64_t n_warps, int wpb) {
 #ifdef GNN_TUNE
 #include "experiments_device.cuh"   // gather-roof microbenchmark, hub-cache prototype (tools/ only)
 #endif
+#include "linear_tc.cuh"            // tcgen05 3xTF32 dense linears of a layer
 
 }  // namespace
 
@@ -1241,6 +1244,7 @@ const char *gnn_error_string(int code) {
     case GNN_E_BADARG: return "gnn_b200: bad argument (null pointer, negative size, unsupported width)";
     case GNN_E_WORKSPACE: return "gnn_b200: workspace missing or too small";
     case GNN_E_RANGE: return "gnn_b200: size exceeds the limits of this path";
+    case GNN_E_DRIVER: return "gnn_b200: cuTensorMapEncodeTiled unavailable or rejected the weight descriptor";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "gnn_b200: unknown error";
   }
 }
@@ -1698,6 +1702,130 @@ int gnn_host_register(void *host_ptr, size_t bytes, void **dev_alias) {
 int gnn_host_unregister(void *host_ptr) {
   if (!host_ptr) return GNN_E_BADARG;
   GNN_CUDA(cudaHostUnregister(host_ptr));
+  return 0;
+}
+
+// ---- dense linears of a layer on tcgen05, 3xTF32 (linear_tc.cuh) -------------------------------------------------
+size_t gnn_linear_split_elems(int64_t rows, int64_t cols) {
+  if (rows < 0 || cols < 0) return 0;
+  return (size_t)2 * (size_t)rows * (size_t)((cols + 31) / 32 * 32);
+}
+
+int gnn_linear_split_weights_f32(const float *W, int64_t ldw, int64_t N, int64_t K, float *w_nk, float *w_kn,
+                                 gnn_stream_t stream) {
+  if (!W || !w_nk || N <= 0 || K <= 0 || ldw < K) return GNN_E_BADARG;
+  if (N > INT32_MAX / 2 || K > INT32_MAX / 2) return GNN_E_RANGE;
+  const int Kp = tc::round_up((int)K, 32), Np = tc::round_up((int)N, 32);
+  const int64_t total = N * Kp + (w_kn ? K * Np : 0);
+  const int grid = (int)std::min<int64_t>(cdiv(total, 256), 148 * 8);
+  tc::split_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, ldw, (int)N, (int)K, Kp, Np, w_nk, w_kn);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+int gnn_linear_tf32x3_f32(const float *A, int64_t lda, const int64_t *a_rows, int64_t M, int64_t K, const float *w_split,
+                          int64_t N, const float *bias, float *C, int64_t ldc, gnn_stream_t stream) {
+  if (M < 0 || N <= 0 || K <= 0 || lda < 0 || ldc < N) return GNN_E_BADARG;
+  if (M == 0) return 0;
+  if (!A || !w_split || !C) return GNN_E_BADARG;
+  if (M > INT32_MAX / 2 || N > INT32_MAX / 2 || K > INT32_MAX / 2) return GNN_E_RANGE;
+  if (((uintptr_t)w_split & 15u) != 0) return GNN_E_BADARG;
+  tc::EncodeTiledFn encode = tc::encode_tiled_fn();
+  if (!encode) return GNN_E_DRIVER;
+  // a runtime call first: it makes the device's primary context current on this thread (autograd worker threads reach
+  // this function without one, and the driver-API encode below then fails with CUDA_ERROR_INVALID_CONTEXT)
+  auto kern = tc::linear_tc_kernel<tc::MODE_NT>;
+  GNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kTcSmemBytes));
+  const int Kp = tc::round_up((int)K, 32), BN = tc::tile_width((int)N);
+  CUtensorMap maps[2];
+  for (int pl = 0; pl < 2; ++pl) {
+    const cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)N};
+    const cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::kBK, (cuuint32_t)BN};
+    const cuuint32_t estr[2] = {1, 1};
+    void *g = (void *)(w_split + (size_t)pl * (size_t)N * (size_t)Kp);
+    CUresult r = encode(&maps[pl], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT) {
+      (void)cudaFree(nullptr);
+      r = encode(&maps[pl], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) {
+      if (getenv("GNN_TC_DEBUG"))
+        fprintf(stderr, "cuTensorMapEncodeTiled -> %d (plane %d, ptr %p, dims %llu x %llu, stride %llu, box %u x %u)\n", (int)r, pl, g,
+                (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)strides[0], box[0], box[1]);
+      return GNN_E_DRIVER;
+    }
+  }
+  tc::TcParams p{};
+  p.A = A; p.lda = lda; p.a_rows = a_rows;
+  p.bias = bias; p.C = C; p.ldc = ldc;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.BN = BN;
+  p.idesc = tc::make_idesc(BN, false);
+  p.desc_lbo = 16; p.desc_sbo = 1024; p.desc_kstep = 32;
+  p.a_vec = tc::aligned16(A, lda); p.c_vec = tc::aligned16(C, ldc);
+  const dim3 grid((unsigned)cdiv(M, tc::kBM), (unsigned)cdiv(N, BN));
+  kern<<<grid, tc::kTcThreads, tc::kTcSmemBytes, (cudaStream_t)stream>>>(p, maps[0], maps[1]);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
+static void wgrad_plan(int64_t M, int64_t N, int64_t K, int &BN, int &splits, int &kbps, int64_t &ldp) {
+  BN = tc::tile_width((int)K);
+  const int64_t tiles = cdiv(N, tc::kBM) * cdiv(K, BN), total_kb = std::max<int64_t>(cdiv(M, tc::kBK), 1);
+  int64_t want = std::max<int64_t>(1, tc::sm_count() / tiles);
+  want = std::min<int64_t>(want, std::max<int64_t>(1, total_kb / 4));      // at least 4 k-blocks per CTA
+  // at most 24 k-blocks (768 rows) per CTA: the tensor core truncates on every accumulation (linear_tc.cuh), 96 steps
+  // keep that bias below 2e-6; the partial sums of the splits are added in fp32 with rounding
+  want = std::max<int64_t>(want, cdiv(total_kb, 24));
+  kbps = (int)cdiv(total_kb, want);
+  splits = (int)cdiv(total_kb, kbps);
+  ldp = (K + 3) / 4 * 4;
+}
+
+size_t gnn_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  if (M < 0 || N <= 0 || K <= 0) return 0;
+  int BN, splits, kbps; int64_t ldp;
+  wgrad_plan(M, N, K, BN, splits, kbps, ldp);
+  return (size_t)splits * (size_t)N * (size_t)ldp * 4 + 16;
+}
+
+int gnn_linear_wgrad_tf32x3_f32(const float *dY, int64_t lddy, const float *X, int64_t ldx, const int64_t *x_rows, int64_t M,
+                                int64_t N, int64_t K, float *dW, int64_t lddw, void *workspace, size_t workspace_bytes,
+                                gnn_stream_t stream) {
+  if (M < 0 || N <= 0 || K <= 0 || lddy < N || lddw < K || !dW) return GNN_E_BADARG;
+  if (M > INT32_MAX / 2 || N > INT32_MAX / 2 || K > INT32_MAX / 2) return GNN_E_RANGE;
+  if (M == 0) {
+    GNN_CUDA(cudaMemset2DAsync(dW, (size_t)lddw * 4, 0, (size_t)K * 4, (size_t)N, (cudaStream_t)stream));
+    return 0;
+  }
+  if (!dY || !X) return GNN_E_BADARG;
+  int BN, splits, kbps; int64_t ldp;
+  wgrad_plan(M, N, K, BN, splits, kbps, ldp);
+  if (!workspace || workspace_bytes < gnn_linear_wgrad_workspace_bytes(M, N, K)) return GNN_E_WORKSPACE;
+  float *ws = reinterpret_cast<float *>(((uintptr_t)workspace + 15u) & ~(uintptr_t)15u);
+  tc::TcParams p{};
+  p.A = dY; p.lda = lddy; p.B = X; p.ldb = ldx; p.b_rows = x_rows;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.BN = BN; p.kb_per_split = kbps;
+  p.idesc = tc::make_idesc(BN, true);
+  p.desc_lbo = tc::dbg_env("GNN_TC_TN_LBO", tc::kPanelBytes); p.desc_sbo = tc::dbg_env("GNN_TC_TN_SBO", 512);
+  p.desc_kstep = tc::dbg_env("GNN_TC_TN_KSTEP", 1024);
+  p.a_vec = tc::aligned16(dY, lddy); p.b_vec = tc::aligned16(X, ldx);
+  const bool direct = splits == 1;
+  p.C = direct ? dW : ws; p.ldc = direct ? lddw : ldp; p.c_split_stride = N * ldp;
+  p.c_vec = tc::aligned16(p.C, p.ldc);
+  auto kern = tc::linear_tc_kernel<tc::MODE_TN>;
+  GNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kTcSmemBytes));
+  const dim3 grid((unsigned)cdiv(N, tc::kBM), (unsigned)cdiv(K, BN), (unsigned)splits);
+  CUtensorMap dummy{};
+  kern<<<grid, tc::kTcThreads, tc::kTcSmemBytes, (cudaStream_t)stream>>>(p, dummy, dummy);
+  GNN_LAUNCH_CHECK();
+  if (!direct) {
+    const int rgrid = (int)std::min<int64_t>(cdiv(N * K, 256), 148 * 8);
+    tc::reduce_splits_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(ws, N * ldp, splits, (int)N, (int)K, ldp, dW, lddw);
+    GNN_LAUNCH_CHECK();
+  }
   return 0;
 }
 

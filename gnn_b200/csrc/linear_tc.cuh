@@ -1,0 +1,442 @@
+// linear_tc.cuh - the dense half of a GraphSAGE / GCN layer on the 5th-generation tensor cores.
+//
+// Reference: models.py:18-19  `cat[linearB(x[sampled_nodes]), linearW(spmm(adj, x))]`, models.py:60 `linear(feat)`, and
+// their autograd backward (dX = dY.W, dW = dY^T.X).  The reference runs them as fp32 cuBLAS SIMT GEMMs plus an index
+// kernel and a concat; after the SpMM work of rounds 1-2 they were the largest part of a training step.
+//
+// Arithmetic: fp32 in, fp32 out, "3xTF32" inside: every operand element a is split into hi = rn_tf32(a) and
+// lo = rn_tf32(a - hi); a.b ~ hi.hi + hi.lo + lo.hi, three tcgen05.mma.kind::tf32 into one fp32 TMEM accumulator.  The
+// dropped terms are < 2^-21 |a||b| per product (fp32 rounding of one FMA: 2^-24), far inside the 1e-5 bar.
+//
+// Two kernels from one template:
+//   NT  C[M,N] = A[rows[m], :K] . W[N,K]^T + bias      forward and dX.  A: activations, split while they are staged (one
+//       pass over HBM, the row gather of x[sampled_nodes] is free: a producer thread owns a row pointer).  W: pre-split
+//       once per step into [2][N][Kp] (gnn_linear_split_weights_f32) and loaded by TMA, 128-byte swizzle.
+//   TN  dW[N,K] = sum_m dY[m,n] X[rows[m],k]           both operands are activations whose REDUCTION index is the slow
+//       one in memory: natural [32 rows x 128 B] panels are exactly the MN-major SWIZZLE_128B operand layout, so no
+//       transposes; split over m across CTAs (partials in a workspace, summed in fixed order => reproducible).
+// Per CTA: 8 producer warps (global -> registers -> hi/lo -> swizzled shared), 1 TMA warp (NT), 1 MMA warp (one lane
+// issues), 2 stages of 96 KB, accumulator 128 x BN fp32 in TMEM; the producer warps turn into the epilogue
+// (tcgen05.ld -> shared transpose -> coalesced 128-bit stores, bias fused).
+#pragma once
+
+namespace tc {
+
+constexpr int kBM = 128;                       // UMMA M (TMEM lanes)
+constexpr int kBK = 32;                        // fp32 per k-block: one 128-byte swizzle row
+constexpr int kStages = 2;
+constexpr int kProducerWarps = 8;
+constexpr int kTcThreads = (kProducerWarps + 2) * 32;
+constexpr int kMaxBN = 256;
+constexpr uint32_t kPanelBytes = kBK * 128;    // [32 rows][128 B]
+constexpr uint32_t kATile = kBM * 128;         // 16 KB: K-major 128 rows x 128 B, or 4 MN-major panels
+constexpr uint32_t kBTile = kMaxBN * 128;      // 32 KB
+constexpr uint32_t kStageBytes = 2 * kATile + 2 * kBTile;
+constexpr uint32_t kBarBytes = 256;
+constexpr uint32_t kTcSmemBytes = 1024 + kStages * kStageBytes + kBarBytes;
+constexpr uint32_t kTmemCols = 512;             // two accumulators of 128 x 256 fp32: hi.hi and the cross terms
+constexpr int kEpiStride = 36;                 // floats per scratch row: 16-byte aligned, conflict-free both ways
+
+enum { MODE_NT = 0, MODE_TN = 1 };
+
+struct TcParams {
+  const float *A; int64_t lda; const int64_t *a_rows;   // NT: activations [M,K] (rows optional); TN: dY [M,N]
+  const float *B; int64_t ldb; const int64_t *b_rows;   // TN only: X [M,K] (rows optional)
+  const float *bias;                                    // NT only, may be NULL
+  float *C; int64_t ldc; int64_t c_split_stride;        // TN: partial of split z at C + z * c_split_stride
+  int M, N, K;                                          // NT: C is [M,N], reduce over K.  TN: C is [N,K], reduce over M
+  int BN;                                               // tile width, multiple of 16, <= 256
+  int kb_per_split;                                     // TN
+  uint32_t idesc;
+  uint32_t desc_lbo, desc_sbo, desc_kstep;              // shared-memory descriptor strides of this mode (bytes)
+  int a_vec, b_vec, c_vec;                              // 16-byte access allowed on that operand
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+// A wait that cannot hang the GPU: a protocol bug traps (the launch fails with an error) instead of spinning forever.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++spins > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+// shared-memory matrix descriptor with the sm_100 version bit (cute::UMMA::SmemDescriptor).  layout: 2 = SWIZZLE_128B
+// (16-byte chunks, K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte chunks: the only layout MN-major tf32 accepts)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | ((uint64_t)layout << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// four consecutive floats of a row starting at column `col`; columns >= limit (and a null row) read as zero
+__device__ __forceinline__ float4 load4(const float *row, int col, int limit, int vec_ok) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row == nullptr || col >= limit) return v;
+  if (vec_ok && col + 4 <= limit) return __ldg(reinterpret_cast<const float4 *>(row + col));
+  v.x = __ldg(row + col);
+  if (col + 1 < limit) v.y = __ldg(row + col + 1);
+  if (col + 2 < limit) v.z = __ldg(row + col + 2);
+  if (col + 3 < limit) v.w = __ldg(row + col + 3);
+  return v;
+}
+// hi / lo planes of one 16-byte chunk at the same swizzled offset of their tiles
+__device__ __forceinline__ void split_store(uint32_t hi_addr, uint32_t lo_addr, const float4 v) {
+  const float hx = tf32_rn(v.x), hy = tf32_rn(v.y), hz = tf32_rn(v.z), hw = tf32_rn(v.w);
+  sts128(hi_addr, hx, hy, hz, hw);
+  sts128(lo_addr, tf32_rn(v.x - hx), tf32_rn(v.y - hy), tf32_rn(v.z - hz), tf32_rn(v.w - hw));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1)
+linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  const uint32_t base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + kStages * kStageBytes;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * kStages, bar_accum = bars + 16 * kStages;
+  const uint32_t tmem_slot = bar_accum + 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // tile coordinates
+  //   NT: rows of C = blockIdx.x * 128 (m), columns = blockIdx.y * BN (n), reduce over all of K
+  //   TN: rows of C = blockIdx.x * 128 (n), columns = blockIdx.y * BN (k), reduce over k-blocks of split blockIdx.z
+  const int row0 = blockIdx.x * kBM, col0 = blockIdx.y * p.BN;
+  int kb_begin = 0, kb_end = 0;
+  if (MODE == MODE_NT) {
+    kb_end = (p.K + kBK - 1) / kBK;
+  } else {
+    const int total = (p.M + kBK - 1) / kBK;
+    kb_begin = blockIdx.z * p.kb_per_split;
+    kb_end = min(total, kb_begin + p.kb_per_split);
+  }
+  const int nkb = kb_end - kb_begin;
+
+  if (tid == 0) {
+    const uint32_t producers = kProducerWarps * 32 + (MODE == MODE_NT ? 1 : 0);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, producers);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kProducerWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp < kProducerWarps) {
+    // ===== producers: global -> registers -> (hi, lo) -> swizzled shared =====================================
+    const int c = tid & 7;                       // 16-byte chunk of a 128-byte row
+    const int r = tid >> 3;                      // 0..31
+    // SWIZZLE_128B: 16-byte chunk ^= row & 7.  SWIZZLE_128B_BASE32B: 32-byte chunk ^= row & 3 (byte bits [5,7) ^= [7,9)).
+    const uint32_t swz = (MODE == MODE_NT) ? (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)) : (uint32_t)(r * 128 + ((c ^ ((r & 3) << 1)) << 4));
+    if (MODE == MODE_NT) {
+      const float *rp[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = row0 + r + 32 * i;
+        rp[i] = (m < p.M) ? p.A + (p.a_rows ? p.a_rows[m] : (int64_t)m) * p.lda : nullptr;
+      }
+      float4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = load4(rp[i], c * 4, p.K, p.a_vec);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % kStages;
+        mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
+        const uint32_t a_hi = base + s * kStageBytes, a_lo = a_hi + kATile;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_store(a_hi + swz + i * 4096, a_lo + swz + i * 4096, v[i]);
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * s);
+        if (it + 1 < nkb) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = load4(rp[i], (it + 1) * kBK + c * 4, p.K, p.a_vec);
+        }
+      }
+    } else {
+      const int npanels = (p.BN + 31) >> 5;
+      float4 va[4], vb[8];
+      auto load = [&](int kb) {
+        const int m = kb * kBK + r;
+        const bool ok = m < p.M;
+        const float *ar = ok ? p.A + (int64_t)m * p.lda + row0 : nullptr;
+        const float *br = ok ? p.B + (p.b_rows ? p.b_rows[m] : (int64_t)m) * p.ldb + col0 : nullptr;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) va[q] = load4(ar, 32 * q + 4 * c, p.N - row0, p.a_vec);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) vb[q] = (q < npanels) ? load4(br, 32 * q + 4 * c, p.K - col0, p.b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      if (nkb > 0) load(kb_begin);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % kStages;
+        mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
+        const uint32_t a_hi = base + s * kStageBytes, a_lo = a_hi + kATile, b_hi = a_lo + kATile, b_lo = b_hi + kBTile;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) split_store(a_hi + q * kPanelBytes + swz, a_lo + q * kPanelBytes + swz, va[q]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q < npanels) split_store(b_hi + q * kPanelBytes + swz, b_lo + q * kPanelBytes + swz, vb[q]);
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * s);
+        if (it + 1 < nkb) load(kb_begin + it + 1);
+      }
+    }
+  } else if (warp == kProducerWarps) {
+    // ===== TMA warp (NT): the pre-split weight planes =========================================================
+    if (MODE == MODE_NT && lane == 0) {
+      const uint32_t bytes = 2u * (uint32_t)p.BN * 128u;
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % kStages;
+        mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
+        const uint32_t b_hi = base + s * kStageBytes + 2 * kATile, b_lo = b_hi + kBTile;
+        mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+        tma_load_2d(b_hi, &map_hi, bar_full + 8 * s, it * kBK, col0);
+        tma_load_2d(b_lo, &map_lo, bar_full + 8 * s, it * kBK, col0);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== MMA warp: one lane issues ==========================================================================
+    if (lane == 0) {
+      uint32_t acc = 0;
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % kStages;
+        mbar_wait(bar_full + 8 * s, (it / kStages) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = base + s * kStageBytes, a_lo = a_hi + kATile, b_hi = a_lo + kATile, b_lo = b_hi + kBTile;
+#pragma unroll
+        for (int kk = 0; kk < kBK / 8; ++kk) {
+          // NT (K-major, SWIZZLE_128B): 8-row groups 1024 B apart (SBO), 8 tf32 = 32 B further along the swizzled row.
+          // TN (MN-major, SWIZZLE_128B_BASE32B): 32-element MN blocks one panel apart (LBO), groups of 4 reduction rows
+          // 512 B apart (SBO), 8 reduction rows = 1024 B per MMA.
+          const uint32_t ko = kk * p.desc_kstep;
+          constexpr uint32_t lt = (MODE == MODE_NT) ? 2u : 1u;
+          const uint64_t dah = smem_desc(a_hi + ko, p.desc_lbo, p.desc_sbo, lt), dal = smem_desc(a_lo + ko, p.desc_lbo, p.desc_sbo, lt);
+          const uint64_t dbh = smem_desc(b_hi + ko, p.desc_lbo, p.desc_sbo, lt), dbl = smem_desc(b_lo + ko, p.desc_lbo, p.desc_sbo, lt);
+          // The tensor core truncates (round toward zero) on every accumulation: a bias of ~2^-25 |acc| per step.
+          // The two cross terms are 2^-11 of the main term; in their own accumulator their steps cost nothing and
+          // the main accumulator sees one step per 8 k instead of three.
+          umma_tf32(tmem_base + kMaxBN, dal, dbh, p.idesc, acc);
+          umma_tf32(tmem_base + kMaxBN, dah, dbl, p.idesc, 1);
+          umma_tf32(tmem_base, dah, dbh, p.idesc, acc);
+          acc = 1;
+        }
+        umma_commit(bar_empty + 8 * s);
+      }
+      umma_commit(bar_accum);
+    }
+    __syncwarp();
+  }
+
+  // ===== epilogue: TMEM -> registers -> shared (transpose) -> global ============================================
+  if (warp < kProducerWarps) {
+    float *C = p.C + (MODE == MODE_TN ? (int64_t)blockIdx.z * p.c_split_stride : 0);
+    const int rows_total = (MODE == MODE_NT) ? p.M : p.N;
+    const int cols_total = (MODE == MODE_NT) ? p.N : p.K;
+    const int q = warp & 3, half = warp >> 2;
+    const int nchunks = (p.BN + 31) >> 5;
+    if (nkb > 0) {
+      mbar_wait(bar_accum, 0);
+      tc_fence_after();
+    }
+    const uint32_t scratch = base + warp * (32 * kEpiStride * 4);
+    for (int ch = half; ch < nchunks; ch += 2) {
+      uint32_t v[32];
+      if (nkb > 0) {
+        uint32_t w[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kMaxBN + ch * 32), w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sts128(scratch + (lane * kEpiStride + 4 * j) * 4, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      __syncwarp();
+      const int cl = ch * 32 + (lane & 7) * 4;          // column inside the tile
+      const int col = col0 + cl;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == MODE_NT && p.bias != nullptr) {
+        if (col < cols_total) b4.x = __ldg(p.bias + col);
+        if (col + 1 < cols_total) b4.y = __ldg(p.bias + col + 1);
+        if (col + 2 < cols_total) b4.z = __ldg(p.bias + col + 2);
+        if (col + 3 < cols_total) b4.w = __ldg(p.bias + col + 3);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rl = (lane >> 3) + 4 * i;
+        const int row = row0 + q * 32 + rl;
+        float4 o = lds128(scratch + (rl * kEpiStride + (lane & 7) * 4) * 4);
+        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+        if (row < rows_total && cl < p.BN && col < cols_total) {
+          float *dst = C + (int64_t)row * p.ldc + col;
+          if (p.c_vec && cl + 4 <= p.BN && col + 4 <= cols_total) {
+            *reinterpret_cast<float4 *>(dst) = o;
+          } else {
+            dst[0] = o.x;
+            if (cl + 1 < p.BN && col + 1 < cols_total) dst[1] = o.y;
+            if (cl + 2 < p.BN && col + 2 < cols_total) dst[2] = o.z;
+            if (cl + 3 < p.BN && col + 3 < cols_total) dst[3] = o.w;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---- weights: W[N,K] -> hi/lo planes, zero padded, in both orientations -----------------------------------------
+__global__ void split_weights_kernel(const float *__restrict__ W, int64_t ldw, int N, int K, int Kp, int Np,
+                                     float *__restrict__ w_nk, float *__restrict__ w_kn) {
+  const int64_t n_nk = (int64_t)N * Kp, n_kn = w_kn ? (int64_t)K * Np : 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_nk + n_kn; i += (int64_t)gridDim.x * blockDim.x) {
+    float x;
+    float *hi, *lo;
+    if (i < n_nk) {
+      const int n = (int)(i / Kp), k = (int)(i % Kp);
+      x = k < K ? W[(int64_t)n * ldw + k] : 0.f;
+      hi = w_nk + i; lo = w_nk + n_nk + i;
+    } else {
+      const int64_t j = i - n_nk;
+      const int k = (int)(j / Np), n = (int)(j % Np);
+      x = n < N ? W[(int64_t)n * ldw + k] : 0.f;
+      hi = w_kn + j; lo = w_kn + n_kn + j;
+    }
+    const float h = tf32_rn(x);
+    *hi = h;
+    *lo = tf32_rn(x - h);
+  }
+}
+
+// dW[n,k] = sum over splits in ascending order (fixed => reproducible)
+__global__ void reduce_splits_kernel(const float *__restrict__ ws, int64_t split_stride, int splits, int N, int K, int64_t ldp,
+                                     float *__restrict__ out, int64_t ldo) {
+  const int64_t total = (int64_t)N * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / K), k = (int)(i % K);
+    const float *src = ws + (int64_t)n * ldp + k;
+    float acc = src[0];
+    for (int s = 1; s < splits; ++s) acc += src[(int64_t)s * split_stride];
+    out[(int64_t)n * ldo + k] = acc;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+inline uint32_t dbg_env(const char *name, uint32_t dflt) {      // bring-up aid: descriptor strides overridable per process
+  const char *v = getenv(name);
+  return v ? (uint32_t)strtoul(v, nullptr, 0) : dflt;
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+inline int tile_width(int cols) {
+  const int nt = (cols + kMaxBN - 1) / kMaxBN;
+  return std::min(kMaxBN, round_up((cols + nt - 1) / nt, 16));
+}
+
+inline uint32_t make_idesc(int bn, bool mn_major) {
+  uint32_t d = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+  if (mn_major) d |= (1u << 15) | (1u << 16);
+  return d;
+}
+
+inline int sm_count() {
+  static int n = []() {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
+inline bool aligned16(const void *p, int64_t ld) { return (((uintptr_t)p | (uintptr_t)(ld * 4)) & 15u) == 0; }
+
+}  // namespace tc

@@ -413,6 +413,75 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> elu_rownorm_bwd(const to
   return {dx, dscale, doffset};
 }
 
+// ---- dense linears on tcgen05 (3xTF32) -----------------------------------
+inline const int64_t *rows_ptr(const c10::optional<torch::Tensor> &rows, int64_t M, const torch::Device &dev) {
+  if (!rows.has_value() || !rows.value().defined()) return nullptr;
+  const auto &t = rows.value();
+  TORCH_CHECK(t.is_cuda() && t.device() == dev && t.is_contiguous() && t.scalar_type() == torch::kLong && t.numel() == M,
+              "row index must be a contiguous int64 CUDA tensor with one entry per output row");
+  return t.data_ptr<int64_t>();
+}
+inline void check_rowmajor(const torch::Tensor &t, const char *name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kFloat && t.dim() == 2 && (t.stride(1) == 1 || t.size(1) <= 1) &&
+                  (t.size(0) <= 1 || t.stride(0) >= t.size(1)),
+              name, " must be a row-major float32 CUDA matrix (rows may be padded)");
+}
+inline int64_t ld_of(const torch::Tensor &t) { return t.size(0) > 1 ? t.stride(0) : t.size(1); }
+
+// W[N,K] -> (w_nk [2,N,ceil32(K)], w_kn [2,K,ceil32(N)]): TF32 hi/lo planes for the forward and for dX
+std::tuple<torch::Tensor, torch::Tensor> linear_split_weights(const torch::Tensor &W, bool with_transposed) {
+  check_rowmajor(W, "W");
+  c10::cuda::CUDAGuard g(W.device());
+  const int64_t N = W.size(0), K = W.size(1);
+  auto w_nk = torch::empty({2, N, (K + 31) / 32 * 32}, W.options());
+  auto w_kn = with_transposed ? torch::empty({2, K, (N + 31) / 32 * 32}, W.options()) : torch::empty({0}, W.options());
+  check_rc(gnn_linear_split_weights_f32(W.data_ptr<float>(), ld_of(W), N, K, w_nk.data_ptr<float>(),
+                                        with_transposed ? w_kn.data_ptr<float>() : nullptr, cur_stream()),
+           "gnn_linear_split_weights_f32");
+  return {w_nk, w_kn};
+}
+
+// out[:, 0:N] = A[rows] . W^T + bias   (out may be a column slice of a wider row-major buffer)
+void linear_tf32x3(const torch::Tensor &A, const c10::optional<torch::Tensor> &rows, const torch::Tensor &w_split, int64_t K,
+                   const c10::optional<torch::Tensor> &bias, torch::Tensor out) {
+  check_rowmajor(A, "A"); check_rowmajor(out, "out");
+  TORCH_CHECK(w_split.is_cuda() && w_split.is_contiguous() && w_split.scalar_type() == torch::kFloat && w_split.dim() == 3 &&
+                  w_split.size(0) == 2 && w_split.size(2) == (K + 31) / 32 * 32,
+              "w_split must be the [2, N, ceil32(K)] result of linear_split_weights");
+  TORCH_CHECK(A.size(1) == K, "A must have K = ", K, " columns, got ", A.sizes());
+  const int64_t M = out.size(0), N = w_split.size(1);
+  TORCH_CHECK(out.size(1) == N && out.device() == A.device() && w_split.device() == A.device(), "out must be [M, ", N, "] on A's device");
+  const bool has_rows = rows.has_value() && rows.value().defined();
+  TORCH_CHECK(has_rows || A.size(0) == M, "A must have one row per output row");
+  const float *b = nullptr;
+  if (bias.has_value() && bias.value().defined()) {
+    const auto &t = bias.value();
+    TORCH_CHECK(t.is_cuda() && t.is_contiguous() && t.scalar_type() == torch::kFloat && t.numel() == N, "bias must be N floats");
+    b = t.data_ptr<float>();
+  }
+  c10::cuda::CUDAGuard g(A.device());
+  check_rc(gnn_linear_tf32x3_f32(A.data_ptr<float>(), ld_of(A), rows_ptr(rows, M, A.device()), M, K, w_split.data_ptr<float>(), N, b,
+                                 out.data_ptr<float>(), ld_of(out), cur_stream()),
+           "gnn_linear_tf32x3_f32");
+}
+
+// dW[N,K] = dY^T . X[rows]
+torch::Tensor linear_wgrad_tf32x3(const torch::Tensor &dY, const torch::Tensor &X, const c10::optional<torch::Tensor> &rows) {
+  check_rowmajor(dY, "dY"); check_rowmajor(X, "X");
+  TORCH_CHECK(dY.device() == X.device(), "dY and X must be on the same device");
+  const int64_t M = dY.size(0), N = dY.size(1), K = X.size(1);
+  const bool has_rows = rows.has_value() && rows.value().defined();
+  TORCH_CHECK(has_rows || X.size(0) == M, "X must have one row per row of dY");
+  c10::cuda::CUDAGuard g(X.device());
+  auto dW = torch::empty({N, K}, X.options());
+  const size_t wsb = gnn_linear_wgrad_workspace_bytes(M, N, K);
+  auto ws = workspace(wsb, X.device());
+  check_rc(gnn_linear_wgrad_tf32x3_f32(dY.data_ptr<float>(), ld_of(dY), X.data_ptr<float>(), ld_of(X), rows_ptr(rows, M, X.device()), M, N, K,
+                                       dW.data_ptr<float>(), K, ws.data_ptr(), wsb, cur_stream()),
+           "gnn_linear_wgrad_tf32x3_f32");
+  return dW;
+}
+
 // ---- peer-mappable feature shards ---------------------------------------
 std::tuple<torch::Tensor, py::bytes> shard_alloc(int64_t rows, int64_t ld, int64_t device_index) {
   c10::cuda::CUDAGuard g(c10::Device(c10::kCUDA, (c10::DeviceIndex)device_index));
@@ -479,6 +548,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("column_slice_fill", &column_slice_fill, "local column ids of U[:, after_nodes]", rel());
   m.def("elu_rownorm_fwd", &elu_rownorm_fwd, "y, mean, rstd = rownorm(elu(x)) * scale + offset", rel());
   m.def("elu_rownorm_bwd", &elu_rownorm_bwd, "dx, dscale, doffset", rel());
+  m.def("linear_split_weights", &linear_split_weights, "W[N,K] -> TF32 hi/lo planes (w_nk, w_kn)", rel());
+  m.def("linear_tf32x3", &linear_tf32x3, "out = A[rows] . W^T + bias on tcgen05 (3xTF32)", py::arg("A"), py::arg("rows"),
+        py::arg("w_split"), py::arg("K"), py::arg("bias"), py::arg("out"), rel());
+  m.def("linear_wgrad_tf32x3", &linear_wgrad_tf32x3, "dW = dY^T . X[rows] on tcgen05 (3xTF32)", py::arg("dY"), py::arg("X"),
+        py::arg("rows"), rel());
   m.def("shard_alloc", &shard_alloc, "peer-mappable feature shard + IPC handle", rel());
   m.def("shard_open", &shard_open, "map a peer's shard", rel());
   m.def("host_register", &host_register, "pin+map a host table, returns the device alias", rel());

@@ -80,20 +80,20 @@ class FlatGradients:
         return 0
 
 
-def make_model(cso, shape, orders, nhid, device, fused):
+def make_model(cso, shape, orders, nhid, device, fused, tc=False):
     """Replica of the reference's model for this shape: GraphSAGE (main.py default) or GCN for the +I shapes."""
     from . import models
     torch.manual_seed(1234)                      # same initial replica on every rank (reference main.py:91-97 builds one per thread)
     kind = "gcn" if shape.self_loops else "graphsage"
     return models.build_model(kind, shape.feat_dim, nhid, orders, shape.num_classes, dropout=0.1, fused=fused,
-                              spmm=cso.spmm).to(device), kind
+                              spmm=cso.spmm, tc=tc).to(device), kind
 
 
-def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, world, log, fused=False, flat_grads=False):
+def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, world, log, fused=False, flat_grads=False, tc=False):
     """Full training steps over the rotated pre-sampled minibatches (sampling excluded, as stated in the line)."""
     import torch.distributed as dist
     from . import graphgen
-    model, kind = make_model(cso, shape, orders, nhid, device, fused)
+    model, kind = make_model(cso, shape, orders, nhid, device, fused, tc)
     params = [p for p in model.parameters() if p.requires_grad]
     flat = FlatGradients(params, world) if flat_grads else None
     opt = torch.optim.Adam(params, lr=0.01, fused=bool(flat_grads))
@@ -177,13 +177,13 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
     return {"minibatches_per_s": round(world * steps / max(ms * 1e-3, wall), 2), "unit": "minibatches/s", "steps": steps,
             "ms_per_step_device": round(ms / steps, 3), "ms_per_step_wall": round(wall / steps * 1e3, 3),
             "allreduce_bytes_per_step": int(comm_bytes), "parameters": int(nparams), "final_loss": round(last, 4),
-            "fused_epilogue": bool(fused), "flat_gradients": bool(flat_grads), "model": kind,
+            "fused_epilogue": bool(fused), "flat_gradients": bool(flat_grads), "tensor_core_linears": bool(tc), "model": kind,
             "note": f"gather (next minibatch prefetched on a side stream) + {kind} fwd + BCE loss + bwd + clip + NCCL "
                     "allreduce(sum) + Adam on pre-sampled minibatches (host LADIES sampling and adjacency upload excluded)"}
 
 
 def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log, pool_num=4, fused=False,
-                     prebuild_transpose=True, flat_grads=False, skewed_sampling_nodes=None, scale_factor=1.0):
+                     prebuild_transpose=True, flat_grads=False, skewed_sampling_nodes=None, scale_factor=1.0, tc=False):
     """Training with the sampler IN the loop (BASELINE's second minibatches/s number): ``pool_num`` sampler threads
     (reference main.py:77 uses a ThreadPoolExecutor of --pool_num=4 per GPU) run the device LADIES sampler
     (gnn_b200/gpu_sampler.py: numpy draw on the host, array passes on the GPU) and the feature gather on their own
@@ -193,7 +193,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
     from concurrent.futures import ThreadPoolExecutor
     import torch.distributed as dist
     from . import gpu_sampler, graphgen, pipeline
-    model, kind = make_model(cso, shape, orders, nhid, device, fused)
+    model, kind = make_model(cso, shape, orders, nhid, device, fused, tc)
     params = [p for p in model.parameters() if p.requires_grad]
     flat = FlatGradients(params, world) if flat_grads else None
     opt = torch.optim.Adam(params, lr=0.01, fused=bool(flat_grads))
@@ -290,6 +290,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         wall = float(t.item())
     return {"minibatches_per_s": round(world * steps / wall, 2), "unit": "minibatches/s", "steps": steps,
             "ms_per_step_wall": round(wall / steps * 1e3, 3), "sampler_threads": pool_num, "warmup_steps": warm, "final_loss": round(last, 4),
-            "fused_epilogue": bool(fused), "flat_gradients": bool(flat_grads), "model": kind, "scale_factor": float(scale_factor),
+            "fused_epilogue": bool(fused), "flat_gradients": bool(flat_grads), "tensor_core_linears": bool(tc), "model": kind,
+            "scale_factor": float(scale_factor),
             "note": "live LADIES sampling: numpy draw on the host + device array passes (bit-identical sampled sets), "
                     "gather in the sampler threads, then the same training step; wall clock incl. sampling"}

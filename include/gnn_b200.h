@@ -27,11 +27,12 @@
 extern "C" {
 #endif
 
-#define GNN_B200_ABI_VERSION 2
+#define GNN_B200_ABI_VERSION 3
 
 #define GNN_E_BADARG   (-1)   /* null pointer, negative size, unsupported width */
 #define GNN_E_WORKSPACE (-2)  /* workspace missing or too small */
 #define GNN_E_RANGE    (-3)   /* size exceeds the 32-bit index limits of the path */
+#define GNN_E_DRIVER   (-4)   /* a CUDA driver entry point is missing or rejected a descriptor (TMA tensor map) */
 
 typedef void *gnn_stream_t;   /* cudaStream_t */
 
@@ -289,6 +290,38 @@ int gnn_elu_rownorm_fwd_f32(const float *x, int64_t ldx, int64_t M, int64_t C, c
 int gnn_elu_rownorm_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx, int64_t M, int64_t C,
                             const float *scale, const float *mean, const float *rstd, float *dx, int64_t lddx,
                             float *dscale, float *doffset, void *workspace, size_t workspace_bytes, gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Dense linears of a layer on the tcgen05 tensor cores, fp32 in / fp32 out, 3xTF32 inside.
+ *
+ * Replace, for models.py:18-19 `cat[linearB(x[sampled_nodes]), linearW(feat)]` and models.py:60 `linear(feat)`, the
+ * index kernel + two cuBLAS fp32 GEMMs + concat of the forward and the GEMMs of the autograd backward.  Every operand
+ * element a is split into hi = rn_tf32(a), lo = rn_tf32(a - hi) and a.b is evaluated as lo.hi + hi.lo + hi.hi in one
+ * fp32 accumulator: the dropped terms are < 2^-21 |a||b| per product, results agree with an fp64 product to ~1e-6.
+ * Inf/NaN inputs produce NaN (Inf - Inf in the split) where an fp32 GEMM would keep Inf.
+ *
+ * gnn_linear_split_elems(rows, cols): floats of a split weight buffer = 2 * rows * ceil32(cols).
+ * gnn_linear_split_weights_f32: W[N,K] (leading dimension ldw) -> w_nk = [2][N][ceil32(K)] (hi plane, lo plane, zero
+ *     padded; operand of the forward) and, unless NULL, w_kn = [2][K][ceil32(N)] (W^T, operand of dX).  Both must be
+ *     16-byte aligned.  Once per optimizer step.
+ * gnn_linear_tf32x3_f32: C[m, 0:N] = A[a_rows ? a_rows[m] : m, 0:K] . W^T + bias   for m < M
+ *     A: [*, lda] floats, any alignment (16-byte aligned rows take 128-bit loads); a_rows: int64[M] or NULL - the
+ *     x[sampled_nodes] gather of models.py:19 costs nothing extra; w_split: w_nk of W[N,K]; bias: N floats or NULL;
+ *     C: leading dimension ldc >= N, so a column slice of the concatenated layer output can be written in place.
+ *     dX = dY . W is the same call with A = dY, K = N_out, N = K_in, w_split = w_kn, bias = NULL.
+ * gnn_linear_wgrad_tf32x3_f32: dW[n, k] = sum_m dY[m, n] * X[x_rows ? x_rows[m] : m, k]   (n < N, k < K)
+ *     split over m across CTAs; partial sums are added in ascending order (fixed => bit-reproducible).
+ *     workspace: gnn_linear_wgrad_workspace_bytes(M, N, K) bytes.
+ * ------------------------------------------------------------------------- */
+size_t gnn_linear_split_elems(int64_t rows, int64_t cols);
+int gnn_linear_split_weights_f32(const float *W, int64_t ldw, int64_t N, int64_t K, float *w_nk, float *w_kn,
+                                 gnn_stream_t stream);
+int gnn_linear_tf32x3_f32(const float *A, int64_t lda, const int64_t *a_rows, int64_t M, int64_t K, const float *w_split,
+                          int64_t N, const float *bias, float *C, int64_t ldc, gnn_stream_t stream);
+size_t gnn_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int gnn_linear_wgrad_tf32x3_f32(const float *dY, int64_t lddy, const float *X, int64_t ldx, const int64_t *x_rows, int64_t M,
+                                int64_t N, int64_t K, float *dW, int64_t lddw, void *workspace, size_t workspace_bytes,
+                                gnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * gnn_probe_row_gather_f32 - measurement aid (bench.py): the row gather of an SpMM and nothing else.
