@@ -18,6 +18,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "gnn_b200.h"
 
@@ -1723,9 +1724,11 @@ int gnn_linear_split_weights_f32(const float *W, int64_t ldw, int64_t N, int64_t
   return 0;
 }
 
-int gnn_linear_tf32x3_f32(const float *A, int64_t lda, const int64_t *a_rows, int64_t M, int64_t K, const float *w_split,
-                          int64_t N, const float *bias, float *C, int64_t ldc, gnn_stream_t stream) {
+int gnn_linear_tf32x3_f32_ex(const float *A, int64_t lda, const int64_t *a_rows, int64_t M, int64_t K, const float *w_split,
+                             int64_t N, const float *bias, float *C, int64_t ldc, const int64_t *c_rows, unsigned flags,
+                             gnn_stream_t stream) {
   if (M < 0 || N <= 0 || K <= 0 || lda < 0 || ldc < N) return GNN_E_BADARG;
+  if (c_rows && !(flags & GNN_LINEAR_ACCUMULATE)) return GNN_E_BADARG;     // scattered rows are always added
   if (M == 0) return 0;
   if (!A || !w_split || !C) return GNN_E_BADARG;
   if (M > INT32_MAX / 2 || N > INT32_MAX / 2 || K > INT32_MAX / 2) return GNN_E_RANGE;
@@ -1760,26 +1763,47 @@ int gnn_linear_tf32x3_f32(const float *A, int64_t lda, const int64_t *a_rows, in
   }
   tc::TcParams p{};
   p.A = A; p.lda = lda; p.a_rows = a_rows;
-  p.bias = bias; p.C = C; p.ldc = ldc;
+  p.C = C; p.ldc = ldc; p.c_rows = c_rows;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.BN = BN;
   p.idesc = tc::make_idesc(BN, false);
   p.desc_lbo = 16; p.desc_sbo = 1024; p.desc_kstep = 32;
   p.a_vec = tc::aligned16(A, lda); p.c_vec = tc::aligned16(C, ldc);
+  // The tensor core truncates on every accumulation (linear_tc.cuh): one accumulator chain covers at most 32 k-blocks
+  // (K = 1024, 128 steps, bias < 2.5e-6); a longer K is cut into equal chunks whose results are added in fp32.
+  const int nkb = Kp / tc::kBK, nchunks = (nkb + 31) / 32, kbpc = (nkb + nchunks - 1) / nchunks;
   const dim3 grid((unsigned)cdiv(M, tc::kBM), (unsigned)cdiv(N, BN));
-  kern<<<grid, tc::kTcThreads, tc::kTcSmemBytes, (cudaStream_t)stream>>>(p, maps[0], maps[1]);
-  GNN_LAUNCH_CHECK();
+  for (int ch = 0; ch < nchunks; ++ch) {
+    p.kb0 = ch * kbpc; p.kb_per_split = kbpc;
+    p.bias = ch == 0 ? bias : nullptr;
+    p.accumulate = c_rows ? 2 : (((flags & GNN_LINEAR_ACCUMULATE) || ch > 0) ? 1 : 0);
+    kern<<<grid, tc::kTcThreads, tc::kTcSmemBytes, (cudaStream_t)stream>>>(p, maps[0], maps[1]);
+    GNN_LAUNCH_CHECK();
+  }
   return 0;
+}
+
+int gnn_linear_tf32x3_f32(const float *A, int64_t lda, const int64_t *a_rows, int64_t M, int64_t K, const float *w_split,
+                          int64_t N, const float *bias, float *C, int64_t ldc, gnn_stream_t stream) {
+  return gnn_linear_tf32x3_f32_ex(A, lda, a_rows, M, K, w_split, N, bias, C, ldc, nullptr, 0u, stream);
 }
 
 static void wgrad_plan(int64_t M, int64_t N, int64_t K, int &BN, int &splits, int &kbps, int64_t &ldp) {
   BN = tc::tile_width((int)K);
   const int64_t tiles = cdiv(N, tc::kBM) * cdiv(K, BN), total_kb = std::max<int64_t>(cdiv(M, tc::kBK), 1);
-  int64_t want = std::max<int64_t>(1, tc::sm_count() / tiles);
-  want = std::min<int64_t>(want, std::max<int64_t>(1, total_kb / 4));      // at least 4 k-blocks per CTA
-  // at most 24 k-blocks (768 rows) per CTA: the tensor core truncates on every accumulation (linear_tc.cuh), 96 steps
-  // keep that bias below 2e-6; the partial sums of the splits are added in fp32 with rounding
-  want = std::max<int64_t>(want, cdiv(total_kb, 24));
-  kbps = (int)cdiv(total_kb, want);
+  const int64_t sms = tc::sm_count();
+  // One accumulator chain covers at most 32 k-blocks (1024 rows): the tensor core truncates on every accumulation
+  // (linear_tc.cuh) and 128 steps keep that bias below 2.5e-6; the partial sums of the splits are added in fp32.
+  // Among the split counts that respect it, take the one with the smallest modelled time: waves of CTAs x (k-blocks
+  // per CTA + ~3 k-block times of prologue/epilogue) + the fixed-order sum over the splits.
+  const int64_t s_min = cdiv(total_kb, 32), s_max = std::min<int64_t>(total_kb, std::max<int64_t>(3 * s_min, sms / tiles));
+  int64_t best = s_min;
+  double best_cost = 1e30;
+  for (int64_t s = s_min; s <= s_max; ++s) {
+    const int64_t per = cdiv(total_kb, s), eff = cdiv(total_kb, per);
+    const double cost = (double)cdiv(tiles * eff, sms) * (double)(per + 3) + 0.15 * (double)eff;
+    if (cost < best_cost) { best_cost = cost; best = eff; }
+  }
+  kbps = (int)cdiv(total_kb, best);
   splits = (int)cdiv(total_kb, kbps);
   ldp = (K + 3) / 4 * 4;
 }
@@ -1825,6 +1849,100 @@ int gnn_linear_wgrad_tf32x3_f32(const float *dY, int64_t lddy, const float *X, i
     const int rgrid = (int)std::min<int64_t>(cdiv(N * K, 256), 148 * 8);
     tc::reduce_splits_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(ws, N * ldp, splits, (int)N, (int)K, ldp, dW, lddw);
     GNN_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ---- host-side helper of the device LADIES sampler: numpy's legacy weighted draw without replacement -------------------
+// Reference sampler.py:128 `np.random.choice(num_nodes, s_num, p=p, replace=False)` after `np.random.seed(seed)` (:96).
+// Bit-identical restatement of numpy/random/mtrand.pyx (RandomState.choice, replace=False, p given) on MT19937:
+// repeat { x = random_sample(size - n_uniq); p[found] = 0; cdf = cumsum(p) (sequential); cdf /= cdf[-1];
+//          new = searchsorted(cdf, x, 'right'); keep the first occurrence of every value, in draw order }.
+// 20 ms of numpy per Reddit-shaped minibatch under the GIL become ~4 ms of C without it (the sampler threads of a rank
+// share one interpreter).  Pure host code: no CUDA calls; allocates its scratch on the host heap.
+static inline uint32_t mt_next(uint32_t *st) {
+  constexpr int N = 624, M = 397;
+  constexpr uint32_t A = 0x9908b0dfu, UP = 0x80000000u, LO = 0x7fffffffu;
+  uint32_t *key = st;
+  uint32_t pos = st[624];
+  if (pos >= (uint32_t)N) {
+    int i;
+    uint32_t y;
+    for (i = 0; i < N - M; ++i) { y = (key[i] & UP) | (key[i + 1] & LO); key[i] = key[i + M] ^ (y >> 1) ^ ((0u - (y & 1u)) & A); }
+    for (; i < N - 1; ++i) { y = (key[i] & UP) | (key[i + 1] & LO); key[i] = key[i + (M - N)] ^ (y >> 1) ^ ((0u - (y & 1u)) & A); }
+    y = (key[N - 1] & UP) | (key[0] & LO);
+    key[N - 1] = key[M - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & A);
+    pos = 0;
+  }
+  uint32_t y = key[pos++];
+  st[624] = pos;
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+// number of leading elements of the sorted array a[0..len) that are <= t
+static inline int64_t upper_count(const double *a, int64_t len, double t) {
+  const double *b = a;
+  while (len > 0) {
+    const int64_t half = len >> 1;
+    const bool le = b[half] <= t;
+    b = le ? b + half + 1 : b;
+    len = le ? len - half - 1 : half;
+  }
+  return b - a;
+}
+
+int gnn_legacy_choice_f64(uint32_t *mt_state, const double *p, int64_t n, int64_t size, int64_t *found) {
+  if (!mt_state || !p || !found || n <= 0 || size < 0 || size > n) return GNN_E_BADARG;
+  if (n > INT32_MAX) return GNN_E_RANGE;
+  std::vector<double> pw(p, p + n), raw((size_t)n), x((size_t)std::max<int64_t>(size, 1));
+  std::vector<int32_t> stamp((size_t)n + 1, 0);
+  std::vector<int64_t> cand((size_t)std::max<int64_t>(size, 1));
+  const int64_t nc = (n + 63) / 64;
+  std::vector<double> coarse((size_t)nc);
+  int64_t n_uniq = 0, zeroed = 0;
+  int32_t round = 0;
+  while (n_uniq < size) {
+    const int64_t k = size - n_uniq;
+    for (int64_t i = 0; i < k; ++i) {
+      const uint32_t a = mt_next(mt_state) >> 5, b = mt_next(mt_state) >> 6;
+      x[(size_t)i] = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+    }
+    // p[found[0:n_uniq]] = 0 (earlier ones already are); np.cumsum adds sequentially, so the running sums before the
+    // first entry zeroed in this round are the ones of the previous round, bit for bit - restart from there
+    int64_t lo = round == 0 ? 0 : n;
+    for (; zeroed < n_uniq; ++zeroed) {
+      pw[(size_t)found[zeroed]] = 0.0;
+      lo = std::min(lo, found[zeroed]);
+    }
+    double run = lo > 0 ? raw[(size_t)lo - 1] : 0.0;
+    for (int64_t i = lo; i < n; ++i) { run += pw[(size_t)i]; raw[(size_t)i] = run; }
+    const double last = raw[(size_t)n - 1];
+    if (!(last > 0.0)) return GNN_E_BADARG;                                   // fewer non-zero entries than `size` (numpy raises)
+    for (int64_t c = std::max<int64_t>(lo / 64, 0); c < nc; ++c) coarse[(size_t)c] = raw[(size_t)std::min<int64_t>(c * 64 + 63, n - 1)];
+    ++round;
+    int64_t got = 0;
+    for (int64_t i = 0; i < k; ++i) {
+      // searchsorted(cdf / cdf[-1], x, side='right') = number of entries whose quotient raw[i] / last (the IEEE division
+      // numpy applies to the whole array; rounding keeps it monotone) is <= x.  Located without dividing n numbers: a
+      // division-free two-level search for x * last (coarse = every 64th running sum, L1-resident), then the exact
+      // quotient test on the neighbours decides.
+      const double xi = x[(size_t)i], t = xi * last;
+      const int64_t cb = upper_count(coarse.data(), nc, t);                   // blocks whose LAST element is <= t
+      const int64_t b0 = cb * 64, bl = std::min<int64_t>(64, n - b0);
+      int64_t l = bl > 0 ? b0 + upper_count(raw.data() + b0, bl, t) : n;
+      while (l < n && raw[(size_t)l] / last <= xi) ++l;
+      while (l > 0 && raw[(size_t)l - 1] / last > xi) --l;
+      if (stamp[(size_t)l] != round) {            // np.unique(return_index=True) + sort: first occurrence, draw order
+        stamp[(size_t)l] = round;
+        cand[(size_t)got++] = l;
+      }
+    }
+    for (int64_t i = 0; i < got; ++i) found[n_uniq + i] = cand[(size_t)i];
+    n_uniq += got;
   }
   return 0;
 }

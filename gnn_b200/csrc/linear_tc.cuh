@@ -44,6 +44,9 @@ struct TcParams {
   const float *B; int64_t ldb; const int64_t *b_rows;   // TN only: X [M,K] (rows optional)
   const float *bias;                                    // NT only, may be NULL
   float *C; int64_t ldc; int64_t c_split_stride;        // TN: partial of split z at C + z * c_split_stride
+  const int64_t *c_rows;                                // NT: output row m goes to C[c_rows[m]] (atomic adds), or NULL
+  int accumulate;                                       // NT: 0 store, 1 C += (plain read-modify-write), 2 red.add
+  int kb0;                                              // NT: first k-block of this launch (K chunks of one product)
   int M, N, K;                                          // NT: C is [M,N], reduce over K.  TN: C is [N,K], reduce over M
   int BN;                                               // tile width, multiple of 16, <= 256
   int kb_per_split;                                     // TN
@@ -158,7 +161,8 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
   const int row0 = blockIdx.x * kBM, col0 = blockIdx.y * p.BN;
   int kb_begin = 0, kb_end = 0;
   if (MODE == MODE_NT) {
-    kb_end = (p.K + kBK - 1) / kBK;
+    kb_begin = p.kb0;
+    kb_end = min((p.K + kBK - 1) / kBK, p.kb0 + p.kb_per_split);
   } else {
     const int total = (p.M + kBK - 1) / kBK;
     kb_begin = blockIdx.z * p.kb_per_split;
@@ -200,7 +204,7 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
       }
       float4 v[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = load4(rp[i], c * 4, p.K, p.a_vec);
+      for (int i = 0; i < 4; ++i) v[i] = load4(rp[i], kb_begin * kBK + c * 4, p.K, p.a_vec);
       for (int it = 0; it < nkb; ++it) {
         const int s = it % kStages;
         mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
@@ -211,7 +215,7 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
         mbar_arrive(bar_full + 8 * s);
         if (it + 1 < nkb) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = load4(rp[i], (it + 1) * kBK + c * 4, p.K, p.a_vec);
+          for (int i = 0; i < 4; ++i) v[i] = load4(rp[i], (kb_begin + it + 1) * kBK + c * 4, p.K, p.a_vec);
         }
       }
     } else {
@@ -251,8 +255,8 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
         mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
         const uint32_t b_hi = base + s * kStageBytes + 2 * kATile, b_lo = b_hi + kBTile;
         mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
-        tma_load_2d(b_hi, &map_hi, bar_full + 8 * s, it * kBK, col0);
-        tma_load_2d(b_lo, &map_lo, bar_full + 8 * s, it * kBK, col0);
+        tma_load_2d(b_hi, &map_hi, bar_full + 8 * s, (kb_begin + it) * kBK, col0);
+        tma_load_2d(b_lo, &map_lo, bar_full + 8 * s, (kb_begin + it) * kBK, col0);
       }
     }
     __syncwarp();
@@ -334,14 +338,30 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
         float4 o = lds128(scratch + (rl * kEpiStride + (lane & 7) * 4) * 4);
         o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
         if (row < rows_total && cl < p.BN && col < cols_total) {
-          float *dst = C + (int64_t)row * p.ldc + col;
-          if (p.c_vec && cl + 4 <= p.BN && col + 4 <= cols_total) {
+          const int64_t crow = (MODE == MODE_NT && p.c_rows != nullptr) ? p.c_rows[row] : (int64_t)row;
+          float *dst = C + crow * p.ldc + col;
+          const bool full = cl + 4 <= p.BN && col + 4 <= cols_total;
+          if (MODE == MODE_NT && p.accumulate == 2) {          // rows of several launches / duplicates may meet: L2 reductions
+            if (p.c_vec && full) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+            } else {
+              atomicAdd(dst, o.x);
+              if (cl + 1 < p.BN && col + 1 < cols_total) atomicAdd(dst + 1, o.y);
+              if (cl + 2 < p.BN && col + 2 < cols_total) atomicAdd(dst + 2, o.z);
+              if (cl + 3 < p.BN && col + 3 < cols_total) atomicAdd(dst + 3, o.w);
+            }
+          } else if (p.c_vec && full) {
+            if (MODE == MODE_NT && p.accumulate == 1) {
+              const float4 old = *reinterpret_cast<const float4 *>(dst);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
             *reinterpret_cast<float4 *>(dst) = o;
           } else {
-            dst[0] = o.x;
-            if (cl + 1 < p.BN && col + 1 < cols_total) dst[1] = o.y;
-            if (cl + 2 < p.BN && col + 2 < cols_total) dst[2] = o.z;
-            if (cl + 3 < p.BN && col + 3 < cols_total) dst[3] = o.w;
+            const bool acc = MODE == MODE_NT && p.accumulate == 1;
+            dst[0] = acc ? dst[0] + o.x : o.x;
+            if (cl + 1 < p.BN && col + 1 < cols_total) dst[1] = acc ? dst[1] + o.y : o.y;
+            if (cl + 2 < p.BN && col + 2 < cols_total) dst[2] = acc ? dst[2] + o.z : o.z;
+            if (cl + 3 < p.BN && col + 3 < cols_total) dst[3] = acc ? dst[3] + o.w : o.w;
           }
         }
       }

@@ -91,7 +91,7 @@ inline const int32_t *rowidx_ptr(const c10::optional<torch::Tensor> &rowidx, int
 }
 
 torch::Tensor csr_spmm(const torch::Tensor &rowptr, const torch::Tensor &colidx, const torch::Tensor &vals, int64_t M,
-                       int64_t K, const torch::Tensor &dense, const c10::optional<torch::Tensor> &rowidx) {
+                       int64_t K, const torch::Tensor &dense, const c10::optional<torch::Tensor> &rowidx, bool padded_rows) {
   CHECK_DENSE(rowptr); CHECK_DENSE(colidx); CHECK_DENSE(vals); CHECK_CUDA(dense);
   // rows may be padded (stride(0) >= D) as long as each row is contiguous: the gathered buffer is 16-byte-row aligned
   TORCH_CHECK(dense.dim() == 2 && (dense.stride(1) == 1 || dense.size(1) <= 1) && dense.stride(0) >= dense.size(1),
@@ -104,10 +104,14 @@ torch::Tensor csr_spmm(const torch::Tensor &rowptr, const torch::Tensor &colidx,
               "all operands must be on the same device");
   c10::cuda::CUDAGuard g(dense.device());
   const int64_t nnz = vals.numel(), D = dense.size(1);
-  auto out = torch::empty({M, D}, dense.options());
+  // padded_rows: rows of the result start on 128-byte lines (leading dimension ceil32(D)); the consumer (the tensor-core
+  // linear that follows in a layer) then reads them with 128-bit loads even when D is 602
+  const int64_t ldy = padded_rows ? (D + 31) / 32 * 32 : D;
+  auto out = torch::empty({M, ldy}, dense.options());
+  if (ldy != D) out = out.narrow(1, 0, D);
   auto ws = spmm_workspace(M, nnz, D, dense.device());
   check_rc(gnn_csr_spmm_f32_ex(rowptr.data_ptr<int32_t>(), rowidx_ptr(rowidx, nnz), colidx.data_ptr<int32_t>(),
-                               vals.data_ptr<float>(), M, K, nnz, D, dense.data_ptr<float>(), dense.size(0) > 1 ? dense.stride(0) : D, out.data_ptr<float>(), D,
+                               vals.data_ptr<float>(), M, K, nnz, D, dense.data_ptr<float>(), dense.size(0) > 1 ? dense.stride(0) : D, out.data_ptr<float>(), ldy,
                                reinterpret_cast<int32_t *>(ws.counters.data_ptr()), ws.partials.data_ptr(),
                                (size_t)ws.partials.numel(), ws.flags, cur_stream()),
            "gnn_csr_spmm_f32");
@@ -204,7 +208,7 @@ torch::Tensor spmm_load_balance(const torch::Tensor &sparseMat, const torch::Ten
   CHECK_DENSE(denseMat);
   auto csr = coo_to_csr(sparseMat);
   auto vals = sparseMat._values().contiguous();
-  return csr_spmm(std::get<0>(csr), std::get<1>(csr), vals, sparseMat.size(0), sparseMat.size(1), denseMat, c10::nullopt);
+  return csr_spmm(std::get<0>(csr), std::get<1>(csr), vals, sparseMat.size(0), sparseMat.size(1), denseMat, c10::nullopt, false);
 }
 
 torch::Tensor spmm_naive(const torch::Tensor &sparseMat, const torch::Tensor &denseMat) {
@@ -443,16 +447,19 @@ std::tuple<torch::Tensor, torch::Tensor> linear_split_weights(const torch::Tenso
 
 // out[:, 0:N] = A[rows] . W^T + bias   (out may be a column slice of a wider row-major buffer)
 void linear_tf32x3(const torch::Tensor &A, const c10::optional<torch::Tensor> &rows, const torch::Tensor &w_split, int64_t K,
-                   const c10::optional<torch::Tensor> &bias, torch::Tensor out) {
+                   const c10::optional<torch::Tensor> &bias, torch::Tensor out, const c10::optional<torch::Tensor> &out_rows,
+                   bool accumulate) {
   check_rowmajor(A, "A"); check_rowmajor(out, "out");
   TORCH_CHECK(w_split.is_cuda() && w_split.is_contiguous() && w_split.scalar_type() == torch::kFloat && w_split.dim() == 3 &&
                   w_split.size(0) == 2 && w_split.size(2) == (K + 31) / 32 * 32,
               "w_split must be the [2, N, ceil32(K)] result of linear_split_weights");
   TORCH_CHECK(A.size(1) == K, "A must have K = ", K, " columns, got ", A.sizes());
-  const int64_t M = out.size(0), N = w_split.size(1);
-  TORCH_CHECK(out.size(1) == N && out.device() == A.device() && w_split.device() == A.device(), "out must be [M, ", N, "] on A's device");
   const bool has_rows = rows.has_value() && rows.value().defined();
+  const bool scatter = out_rows.has_value() && out_rows.value().defined();
+  const int64_t M = scatter ? out_rows.value().numel() : out.size(0), N = w_split.size(1);
+  TORCH_CHECK(out.size(1) == N && out.device() == A.device() && w_split.device() == A.device(), "out must be [M, ", N, "] on A's device");
   TORCH_CHECK(has_rows || A.size(0) == M, "A must have one row per output row");
+  TORCH_CHECK(!scatter || accumulate, "scattered output rows are always accumulated: pass accumulate=True");
   const float *b = nullptr;
   if (bias.has_value() && bias.value().defined()) {
     const auto &t = bias.value();
@@ -460,8 +467,9 @@ void linear_tf32x3(const torch::Tensor &A, const c10::optional<torch::Tensor> &r
     b = t.data_ptr<float>();
   }
   c10::cuda::CUDAGuard g(A.device());
-  check_rc(gnn_linear_tf32x3_f32(A.data_ptr<float>(), ld_of(A), rows_ptr(rows, M, A.device()), M, K, w_split.data_ptr<float>(), N, b,
-                                 out.data_ptr<float>(), ld_of(out), cur_stream()),
+  check_rc(gnn_linear_tf32x3_f32_ex(A.data_ptr<float>(), ld_of(A), rows_ptr(rows, M, A.device()), M, K, w_split.data_ptr<float>(), N, b,
+                                    out.data_ptr<float>(), ld_of(out), rows_ptr(out_rows, M, A.device()),
+                                    accumulate ? GNN_LINEAR_ACCUMULATE : 0u, cur_stream()),
            "gnn_linear_tf32x3_f32");
 }
 
@@ -524,7 +532,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("build_adj", &build_adj, "create_coo_tensor that also returns the int32 column ids (CSR for the kernels)", rel());
   m.def("coo_to_csr", &coo_to_csr, "coalesced COO -> (rowptr int32, colidx int32)", rel());
   m.def("csr_spmm", &csr_spmm, "Y = A.X with A in CSR (optional per-entry row ids)", py::arg("rowptr"), py::arg("colidx"),
-        py::arg("vals"), py::arg("M"), py::arg("K"), py::arg("dense"), py::arg("rowidx") = py::none(), rel());
+        py::arg("vals"), py::arg("M"), py::arg("K"), py::arg("dense"), py::arg("rowidx") = py::none(), py::arg("padded_rows") = false, rel());
   m.def("csr_transpose", &csr_transpose, "CSR of A^T, deterministic", rel());
   m.def("csr_spmm_t", &csr_spmm_t, "dX = A^T.G from A's own CSR (transpose-free, vector reductions)", py::arg("rowptr"),
         py::arg("colidx"), py::arg("vals"), py::arg("M"), py::arg("K"), py::arg("grad"), py::arg("rowidx") = py::none(), rel());
@@ -550,7 +558,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("elu_rownorm_bwd", &elu_rownorm_bwd, "dx, dscale, doffset", rel());
   m.def("linear_split_weights", &linear_split_weights, "W[N,K] -> TF32 hi/lo planes (w_nk, w_kn)", rel());
   m.def("linear_tf32x3", &linear_tf32x3, "out = A[rows] . W^T + bias on tcgen05 (3xTF32)", py::arg("A"), py::arg("rows"),
-        py::arg("w_split"), py::arg("K"), py::arg("bias"), py::arg("out"), rel());
+        py::arg("w_split"), py::arg("K"), py::arg("bias"), py::arg("out"), py::arg("out_rows") = py::none(), py::arg("accumulate") = false, rel());
   m.def("linear_wgrad_tf32x3", &linear_wgrad_tf32x3, "dW = dY^T . X[rows] on tcgen05 (3xTF32)", py::arg("dY"), py::arg("X"),
         py::arg("rows"), rel());
   m.def("shard_alloc", &shard_alloc, "peer-mappable feature shard + IPC handle", rel());

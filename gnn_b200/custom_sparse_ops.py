@@ -56,9 +56,10 @@ class Adjacency:
     def nnz(self) -> int:
         return int(self.vals.numel())
 
-    def matmul(self, dense: torch.Tensor) -> torch.Tensor:
-        """A . X   (forward, reference custom_sparse_ops.py:23)."""
-        return spmm_cpp.csr_spmm(self.rowptr, self.colidx, self.vals, self.nrows, self.ncols, dense, self.rowidx)
+    def matmul(self, dense: torch.Tensor, padded_rows: bool = False) -> torch.Tensor:
+        """A . X   (forward, reference custom_sparse_ops.py:23).  ``padded_rows``: the result's rows start on 128-byte
+        lines (a [M, D] view of a [M, ceil32(D)] buffer) for a consumer that reads them with 128-bit loads."""
+        return spmm_cpp.csr_spmm(self.rowptr, self.colidx, self.vals, self.nrows, self.ncols, dense, self.rowidx, padded_rows)
 
     def transpose(self) -> "Adjacency":
         if self._t is None:

@@ -119,6 +119,49 @@ class SageLinears(torch.autograd.Function):
         return dx, None, dagg, dWB, db[:n], dWW, db[n:]
 
 
+class SageLayer(torch.autograd.Function):
+    """A whole GraphSAGE layer up to its pre-activation, reference models.py:18-19:
+    ``agg = spmm(adj, x); pre = cat[linearB(x[rows]), linearW(agg)]``.
+    Owning the SpMM as well lets the backward put both contributions to dX into ONE buffer: the SpMM backward writes
+    dX = A^T.dagg, and the dX of linearB is added onto its rows ``rows`` by the GEMM's own epilogue (L2 reductions) -
+    no zero-filled buffer, no index_add, no gradient-accumulation pass."""
+
+    @staticmethod
+    def forward(ctx, x, mat1, rows, WB, bB, WW, bW):
+        ext = custom_sparse_ops.spmm_cpp
+        adj = custom_sparse_ops.adjacency_of(mat1)
+        custom_sparse_ops._check_dense(x, "denseMat")
+        n, K = WB.shape
+        agg = adj.matmul(x, padded_rows=True)
+        need_dx = ctx.needs_input_grad[0]
+        sB, sBt = ext.linear_split_weights(WB.detach(), need_dx)
+        sW, sWt = ext.linear_split_weights(WW.detach(), need_dx)
+        pre = torch.empty(agg.shape[0], 2 * n, device=x.device, dtype=torch.float32)
+        ext.linear_tf32x3(x, rows, sB, K, bB, pre[:, :n])
+        ext.linear_tf32x3(agg, None, sW, K, bW, pre[:, n:])
+        ctx.adj = adj
+        ctx.save_for_backward(x, rows, agg, sBt, sWt)
+        return pre
+
+    @staticmethod
+    def backward(ctx, dpre):
+        x, rows, agg, sBt, sWt = ctx.saved_tensors
+        ext = custom_sparse_ops.spmm_cpp
+        dpre = dpre if dpre.stride(-1) == 1 else dpre.contiguous()
+        n = dpre.shape[1] // 2
+        dB, dWv = dpre[:, :n], dpre[:, n:]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dagg = torch.empty(dpre.shape[0], x.shape[1], device=x.device, dtype=torch.float32)
+            ext.linear_tf32x3(dWv, None, sWt, n, None, dagg)
+            dx = ctx.adj.matmul_t(dagg)
+            ext.linear_tf32x3(dB, None, sBt, n, None, dx, rows, True)      # dx[rows] += dB . WB
+        dWB = ext.linear_wgrad_tf32x3(dB, x, rows)
+        dWW = ext.linear_wgrad_tf32x3(dWv, agg, None)
+        db = dpre.sum(0)
+        return dx, None, None, dWB, db[:n], dWW, db[n:]
+
+
 def _rows_tensor(rows, device):
     """The reference indexes with whatever the sampler returned (numpy int64 arrays, sampler.py:143); the kernels take an
     int64 tensor on the device."""
@@ -132,6 +175,10 @@ def _rows_tensor(rows, device):
 
 def tc_linear(x, W, b, rows=None):
     return TcLinear.apply(x, _rows_tensor(rows, x.device), W, b)
+
+
+def sage_layer(x, adj, rows, linearB, linearW):
+    return SageLayer.apply(x, adj, _rows_tensor(rows, x.device), linearB.weight, linearB.bias, linearW.weight, linearW.bias)
 
 
 def sage_linears(x, rows, agg, linearB, linearW):
@@ -158,10 +205,10 @@ def patch_reference_models(ref_models, tc: bool = False):
     ``tc=True`` additionally runs the linears (and the gather + concat around them) on the tensor cores."""
     def sage_forward(self, x, adj, sampled_nodes):
         if self.order > 0:
-            agg = custom_sparse_ops.spmm(adj, x)
             if tc and x.is_cuda:
-                pre = sage_linears(x, sampled_nodes, agg, self.linearB, self.linearW)
+                pre = sage_layer(x, adj, sampled_nodes, self.linearB, self.linearW)
             else:
+                agg = custom_sparse_ops.spmm(adj, x)
                 pre = torch.cat([self.linearB(x[sampled_nodes]), self.linearW(agg)], 1)
         else:
             pre = tc_linear(x, self.linearW.weight, self.linearW.bias) if tc and x.is_cuda else self.linearW(x)
@@ -201,7 +248,10 @@ class Conv(nn.Module):
         spmm = self._spmm or custom_sparse_ops.spmm
         if self.tc and x.is_cuda:           # dense linears on the tensor cores (3xTF32), gather and concat fused away
             if self.sage and self.order > 0:
-                pre = sage_linears(x, own_rows, spmm(adj, x), self.linearB, self.linearW)
+                if self._spmm is None or self._spmm is custom_sparse_ops.spmm:
+                    pre = sage_layer(x, adj, own_rows, self.linearB, self.linearW)
+                else:                       # a caller-supplied spmm (instrumented, fused gather) keeps its own autograd node
+                    pre = sage_linears(x, own_rows, spmm(adj, x), self.linearB, self.linearW)
             else:
                 lin = self.linearW if self.sage else self.linear
                 pre = tc_linear(spmm(adj, x) if (self.order > 0 and not self.sage) else x, lin.weight, lin.bias)

@@ -309,6 +309,13 @@ int gnn_elu_rownorm_bwd_f32(const float *dy, int64_t lddy, const float *x, int64
  *     x[sampled_nodes] gather of models.py:19 costs nothing extra; w_split: w_nk of W[N,K]; bias: N floats or NULL;
  *     C: leading dimension ldc >= N, so a column slice of the concatenated layer output can be written in place.
  *     dX = dY . W is the same call with A = dY, K = N_out, N = K_in, w_split = w_kn, bias = NULL.
+ *     K > 1024 is cut into equal chunks (one launch each, added in fp32): the tensor core truncates on every
+ *     accumulation step, and 128 steps per chain keep that bias below 2.5e-6.
+ * gnn_linear_tf32x3_f32_ex: the same product with
+ *     flags & GNN_LINEAR_ACCUMULATE   C += result instead of C = result;
+ *     c_rows (int64[M] or NULL)       result row m is ADDED to C[c_rows[m], :] with L2 reductions (requires the flag;
+ *                                     duplicates are summed).  This is the backward of x[sampled_nodes]: the dX of
+ *                                     linearB lands on top of the dX the SpMM backward wrote, no zero fill, no index_add.
  * gnn_linear_wgrad_tf32x3_f32: dW[n, k] = sum_m dY[m, n] * X[x_rows ? x_rows[m] : m, k]   (n < N, k < K)
  *     split over m across CTAs; partial sums are added in ascending order (fixed => bit-reproducible).
  *     workspace: gnn_linear_wgrad_workspace_bytes(M, N, K) bytes.
@@ -318,6 +325,10 @@ int gnn_linear_split_weights_f32(const float *W, int64_t ldw, int64_t N, int64_t
                                  gnn_stream_t stream);
 int gnn_linear_tf32x3_f32(const float *A, int64_t lda, const int64_t *a_rows, int64_t M, int64_t K, const float *w_split,
                           int64_t N, const float *bias, float *C, int64_t ldc, gnn_stream_t stream);
+#define GNN_LINEAR_ACCUMULATE 1u
+int gnn_linear_tf32x3_f32_ex(const float *A, int64_t lda, const int64_t *a_rows, int64_t M, int64_t K, const float *w_split,
+                             int64_t N, const float *bias, float *C, int64_t ldc, const int64_t *c_rows, unsigned flags,
+                             gnn_stream_t stream);
 size_t gnn_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int gnn_linear_wgrad_tf32x3_f32(const float *dY, int64_t lddy, const float *X, int64_t ldx, const int64_t *x_rows, int64_t M,
                                 int64_t N, int64_t K, float *dW, int64_t lddw, void *workspace, size_t workspace_bytes,
@@ -335,6 +346,19 @@ int gnn_linear_wgrad_tf32x3_f32(const float *dY, int64_t lddy, const float *X, i
  * ------------------------------------------------------------------------- */
 int gnn_probe_row_gather_f32(const float *X, int64_t ldx, int64_t D, const int32_t *colidx, int64_t nnz, int nv,
                              int warps_per_sm, float *sink, int64_t *bytes_gathered, gnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * gnn_legacy_choice_f64 - HOST helper of the device LADIES sampler (no CUDA calls, allocates host scratch).
+ *
+ * Replaces `np.random.choice(num_nodes, s_num, p=p, replace=False)` of sampler.py:128 (numpy legacy RandomState,
+ * seeded by sampler.py:96) bit for bit: the same MT19937 stream, the same sequential cumsum / normalise / right-sided
+ * search / first-occurrence filter per round as numpy's mtrand.pyx, so the sampled node set is unchanged.
+ *   mt_state : uint32[625] = RandomState.get_state()[1] (624 key words) followed by get_state()[2] (position);
+ *              advanced in place, so the draws of consecutive layers continue one stream like the reference's.
+ *   p        : n probabilities (any entries may be zero; they can never be drawn), found: `size` indices out.
+ * Returns GNN_E_BADARG when fewer than `size` entries of p are non-zero (numpy raises ValueError there).
+ * ------------------------------------------------------------------------- */
+int gnn_legacy_choice_f64(uint32_t *mt_state, const double *p, int64_t n, int64_t size, int64_t *found);
 
 /* ---------------------------------------------------------------------------
  * Feature-shard memory that peers can map (one process per GPU).

@@ -83,6 +83,49 @@ def test_forward_matches_fp64(lib, M, K, N, gather, pad, bias):
     assert _row_rel(out, ref) <= ROW_TOL
 
 
+@pytest.mark.parametrize("K", [1433, 2500])
+def test_long_reductions_are_chunked(lib, K):
+    """K > 1024 runs as several launches whose results are added in fp32 (accumulation-bias bound, see the header)."""
+    M, N = 700, 96
+    x = torch.randn(M, K, device="cuda")
+    W = torch.randn(N, K, device="cuda") * 0.1
+    b = torch.randn(N, device="cuda")
+    w_nk, _ = _split(lib, W, False)
+    n0 = lib.gnn_launch_count()
+    _, out = _linear(lib, x, None, M, K, w_nk, N, b)
+    assert lib.gnn_launch_count() - n0 == (K + 1023) // 1024
+    ref = x.double() @ W.double().t() + b.double()
+    assert _rel(out, ref) <= TOL and _row_rel(out, ref) <= ROW_TOL
+
+
+def test_accumulate_and_row_scatter(lib):
+    """gnn_linear_tf32x3_f32_ex: C += A.W^T, and result rows added onto C[c_rows[m]] (the backward of x[sampled_nodes]),
+    duplicates summed."""
+    M, K, N, n_rows = 600, 512, 602, 900
+    g = torch.Generator(device="cpu").manual_seed(5)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) * 0.1).cuda()
+    w_nk, _ = _split(lib, W, False)
+    base = torch.randn(n_rows, N, generator=g).cuda()
+    prod = A.double() @ W.double().t()
+    # plain accumulate
+    C = base[:M].clone()
+    _native.check(lib.gnn_linear_tf32x3_f32_ex(_p(A), K, None, M, K, _p(w_nk), N, None, _p(C), N, None, 1, _stream()), "ex")
+    assert _rel(C, base[:M].double() + prod) <= TOL
+    # scattered rows with duplicates
+    rows = torch.randint(0, n_rows, (M,), generator=g).cuda()
+    rows[:50] = rows[50:100]
+    C = base.clone()
+    _native.check(lib.gnn_linear_tf32x3_f32_ex(_p(A), K, None, M, K, _p(w_nk), N, None, _p(C), N, _p(rows), 1, _stream()), "ex")
+    ref = base.double().index_add(0, rows, prod)
+    assert _rel(C, ref) <= TOL
+    untouched = torch.ones(n_rows, dtype=torch.bool, device="cuda")
+    untouched[rows] = False
+    assert torch.equal(C[untouched], base[untouched])
+    # scatter without the accumulate flag is refused
+    assert lib.gnn_linear_tf32x3_f32_ex(_p(A), K, None, M, K, _p(w_nk), N, None, _p(C), N, _p(rows), 0, _stream()) == -1
+
+
 def test_split_planes_are_tf32_and_sum_back(lib):
     W = (torch.randn(70, 45, device="cuda") * 3)
     w_nk, w_kn = _split(lib, W, True)
@@ -173,6 +216,31 @@ def test_sage_linears_autograd_matches_fp64():
     g0 = torch.autograd.grad(pre0, [WB, bB, WW, bW], gout)
     for a, b in zip(g0, [ref[2], ref[3], ref[4], ref[5]]):
         assert _rel(a, b) <= TOL
+
+
+def test_sage_layer_autograd_matches_fp64():
+    """The whole layer (SpMM + both linears) as one autograd node: dX = A^T.dagg with linearB's dX added onto its rows."""
+    from gnn_b200 import models
+    torch.manual_seed(2)
+    M, n_in, K, n = 300, 700, 100, 64
+    dense = (torch.rand(M, n_in, device="cuda") < 0.05).float() * torch.rand(M, n_in, device="cuda")
+    adj = dense.to_sparse().coalesce()
+    x = torch.randn(n_in, K, device="cuda", requires_grad=True)
+    rows = torch.randperm(n_in, device="cuda")[:M]
+    WB = (torch.randn(n, K, device="cuda") * 0.1).requires_grad_(True)
+    WW = (torch.randn(n, K, device="cuda") * 0.1).requires_grad_(True)
+    bB = torch.randn(n, device="cuda", requires_grad=True)
+    bW = torch.randn(n, device="cuda", requires_grad=True)
+    ins = [x, WB, bB, WW, bW]
+    pre = models.SageLayer.apply(x, adj, rows, WB, bB, WW, bW)
+    gout = torch.randn_like(pre)
+    got = torch.autograd.grad(pre, ins, gout)
+    x6, WB6, bB6, WW6, bW6 = ins64 = [t.detach().double().requires_grad_(True) for t in ins]
+    pre64 = torch.cat([x6[rows] @ WB6.t() + bB6, (dense.double() @ x6) @ WW6.t() + bW6], 1)
+    ref = torch.autograd.grad(pre64, ins64, gout.double())
+    assert _rel(pre, pre64.detach()) <= TOL
+    for name, a, b in zip(["dx", "dWB", "dbB", "dWW", "dbW"], got, ref):
+        assert _rel(a, b) <= TOL, name
 
 
 def test_tc_linear_autograd_matches_fp64():

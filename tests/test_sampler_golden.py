@@ -97,7 +97,7 @@ def test_oracle_sampled_nodes_direct():
 def test_legacy_choice_on_support_equals_numpy_choice():
     """The device sampler evaluates numpy's legacy weighted draw on the support of p only; it must return exactly what
     RandomState.choice(N, size, p=p, replace=False) returns on the full-length p (reference sampler.py:128)."""
-    from gnn_b200.gpu_sampler import legacy_choice_on_support
+    from gnn_b200.gpu_sampler import legacy_choice_on_support, legacy_choice_on_support_numpy
     rng = np.random.Generator(np.random.PCG64(0))
     for trial in range(40):
         n = int(rng.integers(50, 20000))
@@ -111,7 +111,25 @@ def test_legacy_choice_on_support_equals_numpy_choice():
         rs = np.random.RandomState(trial)
         b = nz[legacy_choice_on_support(rs, p[nz], size)]
         assert np.array_equal(a, b), trial
+        assert np.array_equal(a, nz[legacy_choice_on_support_numpy(np.random.RandomState(trial), p[nz], size)]), trial
         # and the generator state afterwards is the same (the next layer's draw continues the stream)
         rs2 = np.random.RandomState(trial)
         rs2.choice(n, size, p=p, replace=False)
         assert rs.random_sample() == rs2.random_sample()
+
+
+def test_native_draw_on_sampler_sized_inputs_and_errors():
+    """gnn_legacy_choice_f64 on LADIES-sized supports (heavy-tailed counts, several consecutive draws on one stream, like
+    the layers of one minibatch) and its error return when p has fewer non-zero entries than the sample."""
+    from gnn_b200.gpu_sampler import legacy_choice_on_support
+    rng = np.random.Generator(np.random.PCG64(1))
+    for n, size, seed in [(200000, 8192, 5), (30000, 8192, 7), (5000, 4999, 3), (10, 10, 1), (1000, 1, 123456789)]:
+        counts = rng.zipf(1.6, n).clip(max=5000).astype(np.int64)
+        p = counts / counts.sum()
+        rs, ref = np.random.RandomState(seed), np.random.RandomState(seed)
+        for _ in range(3):
+            assert np.array_equal(legacy_choice_on_support(rs, p, size), ref.choice(n, size, p=p, replace=False))
+    p = np.zeros(100)
+    p[:5] = 0.2
+    with pytest.raises(ValueError):
+        legacy_choice_on_support(np.random.RandomState(0), p, 6)

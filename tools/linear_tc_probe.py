@@ -183,6 +183,18 @@ if __name__ == "__main__":
                      dict(M=5000, N=512, K=602, gather=True, lddy_extra=512), dict(M=8689, N=512, K=1024, lddy_extra=512),
                      dict(M=333, N=100, K=47), dict(M=16157, N=512, K=602, gather=True)]:
             ok = run_tn(**args) and ok
+    elif grp == "ncu":      # one launch of each production shape, for `ncu --set full -k regex:linear_tc`
+        for (M, K, N) in [(16157, 602, 512), (8689, 1024, 512), (8689, 512, 1024)]:
+            x = torch.randn(M, 608 if K == 602 else K, device=dev)[:, :K]
+            W = torch.randn(N, K, device=dev) * 0.1
+            out = torch.empty(M, N, device=dev)
+            w_nk, _ = ext.linear_split_weights(W, False)
+            ext.linear_tf32x3(x, None, w_nk, K, None, out)
+        for (M, N, K) in [(16157, 512, 602), (8689, 512, 1024)]:
+            X = torch.randn(M, K, device=dev)
+            dY = torch.randn(M, 2 * N, device=dev)[:, N:]
+            ext.linear_wgrad_tf32x3(dY, X, None)
+        torch.cuda.synchronize()
     elif grp == "tndbg":
         tn_decode()
     elif grp == "time":
