@@ -1747,12 +1747,13 @@ int gnn_linear_tf32x3_f32_ex(const float *A, int64_t lda, const int64_t *a_rows,
     const cuuint32_t box[2] = {(cuuint32_t)tc::kBK, (cuuint32_t)BN};
     const cuuint32_t estr[2] = {1, 1};
     void *g = (void *)(w_split + (size_t)pl * (size_t)N * (size_t)Kp);
+    const CUtensorMapSwizzle swz = tc::kBK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;   // = the row bytes
     CUresult r = encode(&maps[pl], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_ERROR_INVALID_CONTEXT) {
       (void)cudaFree(nullptr);
       r = encode(&maps[pl], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                 swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) {
       if (getenv("GNN_TC_DEBUG"))
@@ -1766,11 +1767,12 @@ int gnn_linear_tf32x3_f32_ex(const float *A, int64_t lda, const int64_t *a_rows,
   p.C = C; p.ldc = ldc; p.c_rows = c_rows;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.BN = BN;
   p.idesc = tc::make_idesc(BN, false);
-  p.desc_lbo = 16; p.desc_sbo = 1024; p.desc_kstep = 32;
+  p.desc_lbo = 16; p.desc_sbo = 8 * tc::kBK * 4; p.desc_kstep = 32; p.desc_layout = tc::kBK == 32 ? 2u : 4u;   // SWIZZLE_128B / _64B
   p.a_vec = tc::aligned16(A, lda); p.c_vec = tc::aligned16(C, ldc);
-  // The tensor core truncates on every accumulation (linear_tc.cuh): one accumulator chain covers at most 32 k-blocks
-  // (K = 1024, 128 steps, bias < 2.5e-6); a longer K is cut into equal chunks whose results are added in fp32.
-  const int nkb = Kp / tc::kBK, nchunks = (nkb + 31) / 32, kbpc = (nkb + nchunks - 1) / nchunks;
+  // The tensor core truncates on every accumulation (linear_tc.cuh): one accumulator chain covers at most K = 1024
+  // (128 steps, bias < 2.5e-6); a longer K is cut into equal chunks whose results are added in fp32.
+  constexpr int kChain = 1024 / tc::kBK;
+  const int nkb = Kp / tc::kBK, nchunks = (nkb + kChain - 1) / kChain, kbpc = (nkb + nchunks - 1) / nchunks;
   const dim3 grid((unsigned)cdiv(M, tc::kBM), (unsigned)cdiv(N, BN));
   for (int ch = 0; ch < nchunks; ++ch) {
     p.kb0 = ch * kbpc; p.kb_per_split = kbpc;
@@ -1791,16 +1793,17 @@ static void wgrad_plan(int64_t M, int64_t N, int64_t K, int &BN, int &splits, in
   BN = tc::tile_width((int)K);
   const int64_t tiles = cdiv(N, tc::kBM) * cdiv(K, BN), total_kb = std::max<int64_t>(cdiv(M, tc::kBK), 1);
   const int64_t sms = tc::sm_count();
-  // One accumulator chain covers at most 32 k-blocks (1024 rows): the tensor core truncates on every accumulation
+  // One accumulator chain covers at most 1024 rows: the tensor core truncates on every accumulation
   // (linear_tc.cuh) and 128 steps keep that bias below 2.5e-6; the partial sums of the splits are added in fp32.
   // Among the split counts that respect it, take the one with the smallest modelled time: waves of CTAs x (k-blocks
   // per CTA + ~3 k-block times of prologue/epilogue) + the fixed-order sum over the splits.
-  const int64_t s_min = cdiv(total_kb, 32), s_max = std::min<int64_t>(total_kb, std::max<int64_t>(3 * s_min, sms / tiles));
+  constexpr int kChain = 1024 / tc::kBK, kOver = 96 / tc::kBK;       // k-blocks per 1024 rows; prologue + epilogue in k-block times
+  const int64_t s_min = cdiv(total_kb, kChain), s_max = std::min<int64_t>(total_kb, std::max<int64_t>(3 * s_min, sms / tiles));
   int64_t best = s_min;
   double best_cost = 1e30;
   for (int64_t s = s_min; s <= s_max; ++s) {
     const int64_t per = cdiv(total_kb, s), eff = cdiv(total_kb, per);
-    const double cost = (double)cdiv(tiles * eff, sms) * (double)(per + 3) + 0.15 * (double)eff;
+    const double cost = (double)cdiv(tiles * eff, sms) * (double)(per + kOver) + 0.15 * (32.0 / tc::kBK) * (double)eff;
     if (cost < best_cost) { best_cost = cost; best = eff; }
   }
   kbps = (int)cdiv(total_kb, best);
@@ -1833,8 +1836,7 @@ int gnn_linear_wgrad_tf32x3_f32(const float *dY, int64_t lddy, const float *X, i
   p.A = dY; p.lda = lddy; p.B = X; p.ldb = ldx; p.b_rows = x_rows;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.BN = BN; p.kb_per_split = kbps;
   p.idesc = tc::make_idesc(BN, true);
-  p.desc_lbo = tc::dbg_env("GNN_TC_TN_LBO", tc::kPanelBytes); p.desc_sbo = tc::dbg_env("GNN_TC_TN_SBO", 512);
-  p.desc_kstep = tc::dbg_env("GNN_TC_TN_KSTEP", 1024);
+  p.desc_lbo = tc::kPanelBytes; p.desc_sbo = 512; p.desc_kstep = 1024; p.desc_layout = 1u;   // SWIZZLE_128B_BASE32B
   p.a_vec = tc::aligned16(dY, lddy); p.b_vec = tc::aligned16(X, ldx);
   const bool direct = splits == 1;
   p.C = direct ? dW : ws; p.ldc = direct ? lddw : ldp; p.c_split_stride = N * ldp;

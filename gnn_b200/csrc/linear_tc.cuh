@@ -23,14 +23,23 @@
 namespace tc {
 
 constexpr int kBM = 128;                       // UMMA M (TMEM lanes)
-constexpr int kBK = 32;                        // fp32 per k-block: one 128-byte swizzle row
-constexpr int kStages = 2;
+#ifndef GNN_TC_BK
+#define GNN_TC_BK 32
+#endif
+// fp32 per k-block: 32 (128-byte rows, SWIZZLE_128B, 2 stages of 96 KB) or 16 (64-byte rows, SWIZZLE_64B, 4 stages of
+// 48 KB).  Measured A/B on one B200 (profiles/r2_linear_tc.md): the 4-stage variant is SLOWER (NT 60 vs 56 us, dW 160 vs
+// 118 us) - the kernel is bound by shared-memory bandwidth (operand reads of three products + hi/lo writes: ~240 KB per
+// 32-wide k-block against 128 B/clk), not by the refill latency more stages would hide, and halving the stage doubles the
+// per-stage barrier / fence cost.
+constexpr int kBK = GNN_TC_BK;
+static_assert(kBK == 16 || kBK == 32, "k-block is 16 or 32 floats");
+constexpr int kStages = kBK == 16 ? 4 : 2;
 constexpr int kProducerWarps = 8;
 constexpr int kTcThreads = (kProducerWarps + 2) * 32;
 constexpr int kMaxBN = 256;
-constexpr uint32_t kPanelBytes = kBK * 128;    // [32 rows][128 B]
-constexpr uint32_t kATile = kBM * 128;         // 16 KB: K-major 128 rows x 128 B, or 4 MN-major panels
-constexpr uint32_t kBTile = kMaxBN * 128;      // 32 KB
+constexpr uint32_t kPanelBytes = kBK * 128;    // MN-major panel: [kBK rows][128 B]
+constexpr uint32_t kATile = kBM * kBK * 4;     // K-major: 128 rows x kBK floats; MN-major: 4 panels
+constexpr uint32_t kBTile = kMaxBN * kBK * 4;
 constexpr uint32_t kStageBytes = 2 * kATile + 2 * kBTile;
 constexpr uint32_t kBarBytes = 256;
 constexpr uint32_t kTcSmemBytes = 1024 + kStages * kStageBytes + kBarBytes;
@@ -51,7 +60,7 @@ struct TcParams {
   int BN;                                               // tile width, multiple of 16, <= 256
   int kb_per_split;                                     // TN
   uint32_t idesc;
-  uint32_t desc_lbo, desc_sbo, desc_kstep;              // shared-memory descriptor strides of this mode (bytes)
+  uint32_t desc_lbo, desc_sbo, desc_kstep, desc_layout; // shared-memory descriptor strides (bytes) and layout type of this mode
   int a_vec, b_vec, c_vec;                              // 16-byte access allowed on that operand
 };
 
@@ -121,10 +130,11 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// round to nearest TF32 (ties away from zero, what cvt.rna.tf32.f32 does): add half an ulp of the 10-bit mantissa to the
+// magnitude bits and clear the 13 low bits.  Two integer instructions instead of the four the cvt expands to (it
+// special-cases Inf/NaN; here Inf stays Inf and NaN stays NaN as well, only the NaN payload may differ).
 __device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // four consecutive floats of a row starting at column `col`; columns >= limit (and a null row) read as zero
@@ -191,45 +201,88 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
 
   if (warp < kProducerWarps) {
     // ===== producers: global -> registers -> (hi, lo) -> swizzled shared =====================================
-    const int c = tid & 7;                       // 16-byte chunk of a 128-byte row
-    const int r = tid >> 3;                      // 0..31
-    // SWIZZLE_128B: 16-byte chunk ^= row & 7.  SWIZZLE_128B_BASE32B: 32-byte chunk ^= row & 3 (byte bits [5,7) ^= [7,9)).
-    const uint32_t swz = (MODE == MODE_NT) ? (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)) : (uint32_t)(r * 128 + ((c ^ ((r & 3) << 1)) << 4));
+    // NT (K-major): a row of the tile is kBK floats = CPR 16-byte chunks; 256 threads cover RPP rows per pass.
+    //   SWIZZLE_128B (kBK 32): chunk ^= row & 7.   SWIZZLE_64B (kBK 16): chunk ^= (row >> 1) & 3  (byte bits [4,6) ^= [7,9)).
+    // TN (MN-major): a panel is kBK reduction rows of 128 bytes; SWIZZLE_128B_BASE32B: 32-byte chunk ^= row & 3
+    //   (byte bits [5,7) ^= [7,9)).  With kBK 16 a panel has 128 chunk slots: the two thread halves take different panels.
+    constexpr int CPR = (MODE == MODE_NT) ? kBK / 4 : 8;
+    constexpr int RPP = (kProducerWarps * 32) / CPR;
+    constexpr int NPASS = kBM / RPP;                       // NT: row passes per thread
+    constexpr int TNG = (kProducerWarps * 32) / (kBK * 8); // TN: thread groups (1 or 2)
+    const int c = tid % CPR;
+    const int r = (MODE == MODE_NT) ? tid / CPR : (tid / 8) % kBK;
+    const int grp = (MODE == MODE_NT) ? 0 : tid / (kBK * 8);
+    const uint32_t swz = (MODE == MODE_NT)
+                             ? (uint32_t)(r * (kBK * 4) + ((c ^ (kBK == 32 ? (r & 7) : ((r >> 1) & 3))) << 4))
+                             : (uint32_t)(r * 128 + ((c ^ ((r & 3) << 1)) << 4));
     if (MODE == MODE_NT) {
-      const float *rp[4];
+      const float *rp[NPASS];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = row0 + r + 32 * i;
+      for (int i = 0; i < NPASS; ++i) {
+        const int m = row0 + r + RPP * i;
         rp[i] = (m < p.M) ? p.A + (p.a_rows ? p.a_rows[m] : (int64_t)m) * p.lda : nullptr;
       }
-      float4 v[4];
+      float4 v[NPASS];
+      // whole k-block inside K and 16-byte aligned rows (warp-uniform): one predicated 128-bit load per row; otherwise
+      // (last k-block of K = 602, unaligned rows) the bounds-checked path
+      auto load = [&](int kb) {
+        const int col = kb * kBK + c * 4;
+        if (p.a_vec && kb * kBK + kBK <= p.K) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = load4(rp[i], kb_begin * kBK + c * 4, p.K, p.a_vec);
+          for (int i = 0; i < NPASS; ++i)
+            v[i] = rp[i] ? __ldg(reinterpret_cast<const float4 *>(rp[i] + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+          for (int i = 0; i < NPASS; ++i) v[i] = load4(rp[i], col, p.K, p.a_vec);
+        }
+      };
+      if (nkb > 0) load(kb_begin);
       for (int it = 0; it < nkb; ++it) {
         const int s = it % kStages;
         mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
         const uint32_t a_hi = base + s * kStageBytes, a_lo = a_hi + kATile;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_store(a_hi + swz + i * 4096, a_lo + swz + i * 4096, v[i]);
+        for (int i = 0; i < NPASS; ++i) split_store(a_hi + swz + i * (RPP * kBK * 4), a_lo + swz + i * (RPP * kBK * 4), v[i]);
         fence_proxy_async();
         mbar_arrive(bar_full + 8 * s);
-        if (it + 1 < nkb) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = load4(rp[i], (kb_begin + it + 1) * kBK + c * 4, p.K, p.a_vec);
-        }
+        if (it + 1 < nkb) load(kb_begin + it + 1);
       }
     } else {
       const int npanels = (p.BN + 31) >> 5;
-      float4 va[4], vb[8];
+      constexpr int NA = 4 / TNG, NB = 8 / TNG;            // A / B panels per thread
+      float4 va[NA], vb[NB];
+      // which of this thread's 16-byte chunks are fully inside the operand (128-bit load), partly inside (bounds-checked
+      // path) or outside: loop-invariant, only the reduction row changes per k-block
+      uint32_t a_full = 0, a_part = 0, b_full = 0, b_part = 0;
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        const int col = 32 * (grp * NA + q) + 4 * c, lim = p.N - row0;
+        if (p.a_vec && col + 4 <= lim) a_full |= 1u << q; else if (col < lim) a_part |= 1u << q;
+      }
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const int col = 32 * (grp * NB + q) + 4 * c, lim = p.K - col0;
+        if (grp * NB + q < npanels) { if (p.b_vec && col + 4 <= lim) b_full |= 1u << q; else if (col < lim) b_part |= 1u << q; }
+      }
+      const int a_col0 = 32 * grp * NA + 4 * c, b_col0 = 32 * grp * NB + 4 * c;
       auto load = [&](int kb) {
         const int m = kb * kBK + r;
         const bool ok = m < p.M;
-        const float *ar = ok ? p.A + (int64_t)m * p.lda + row0 : nullptr;
-        const float *br = ok ? p.B + (p.b_rows ? p.b_rows[m] : (int64_t)m) * p.ldb + col0 : nullptr;
+        const float *ar = p.A + (int64_t)(ok ? m : 0) * p.lda + row0 + a_col0;
+        const float *br = p.B + (ok ? (p.b_rows ? p.b_rows[m] : (int64_t)m) : 0) * p.ldb + col0 + b_col0;
+        const uint32_t af = ok ? a_full : 0u, ap = ok ? a_part : 0u, bf = ok ? b_full : 0u, bp = ok ? b_part : 0u;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) va[q] = load4(ar, 32 * q + 4 * c, p.N - row0, p.a_vec);
+        for (int q = 0; q < NA; ++q) {
+          va[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (af >> q & 1u) va[q] = __ldg(reinterpret_cast<const float4 *>(ar + 32 * q));
+          else if (ap >> q & 1u) va[q] = load4(ar - a_col0, a_col0 + 32 * q, p.N - row0, 0);
+        }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) vb[q] = (q < npanels) ? load4(br, 32 * q + 4 * c, p.K - col0, p.b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < NB; ++q) {
+          vb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bf >> q & 1u) vb[q] = __ldg(reinterpret_cast<const float4 *>(br + 32 * q));
+          else if (bp >> q & 1u) vb[q] = load4(br - b_col0, b_col0 + 32 * q, p.K - col0, 0);
+        }
       };
       if (nkb > 0) load(kb_begin);
       for (int it = 0; it < nkb; ++it) {
@@ -237,10 +290,12 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
         mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
         const uint32_t a_hi = base + s * kStageBytes, a_lo = a_hi + kATile, b_hi = a_lo + kATile, b_lo = b_hi + kBTile;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) split_store(a_hi + q * kPanelBytes + swz, a_lo + q * kPanelBytes + swz, va[q]);
+        for (int q = 0; q < NA; ++q)
+          split_store(a_hi + (grp * NA + q) * kPanelBytes + swz, a_lo + (grp * NA + q) * kPanelBytes + swz, va[q]);
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (q < npanels) split_store(b_hi + q * kPanelBytes + swz, b_lo + q * kPanelBytes + swz, vb[q]);
+        for (int q = 0; q < NB; ++q)
+          if (grp * NB + q < npanels)
+            split_store(b_hi + (grp * NB + q) * kPanelBytes + swz, b_lo + (grp * NB + q) * kPanelBytes + swz, vb[q]);
         fence_proxy_async();
         mbar_arrive(bar_full + 8 * s);
         if (it + 1 < nkb) load(kb_begin + it + 1);
@@ -249,7 +304,7 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
   } else if (warp == kProducerWarps) {
     // ===== TMA warp (NT): the pre-split weight planes =========================================================
     if (MODE == MODE_NT && lane == 0) {
-      const uint32_t bytes = 2u * (uint32_t)p.BN * 128u;
+      const uint32_t bytes = 2u * (uint32_t)p.BN * (uint32_t)(kBK * 4);
       for (int it = 0; it < nkb; ++it) {
         const int s = it % kStages;
         mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
@@ -271,11 +326,11 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
         const uint32_t a_hi = base + s * kStageBytes, a_lo = a_hi + kATile, b_hi = a_lo + kATile, b_lo = b_hi + kBTile;
 #pragma unroll
         for (int kk = 0; kk < kBK / 8; ++kk) {
-          // NT (K-major, SWIZZLE_128B): 8-row groups 1024 B apart (SBO), 8 tf32 = 32 B further along the swizzled row.
-          // TN (MN-major, SWIZZLE_128B_BASE32B): 32-element MN blocks one panel apart (LBO), groups of 4 reduction rows
-          // 512 B apart (SBO), 8 reduction rows = 1024 B per MMA.
+          // NT (K-major, SWIZZLE_128B / _64B): 8-row groups 8 * row bytes apart (SBO), 8 tf32 = 32 B further along the
+          // swizzled row per MMA.  TN (MN-major, SWIZZLE_128B_BASE32B): 32-element MN blocks one panel apart (LBO),
+          // groups of 4 reduction rows 512 B apart (SBO), 8 reduction rows = 1024 B per MMA.
           const uint32_t ko = kk * p.desc_kstep;
-          constexpr uint32_t lt = (MODE == MODE_NT) ? 2u : 1u;
+          const uint32_t lt = p.desc_layout;
           const uint64_t dah = smem_desc(a_hi + ko, p.desc_lbo, p.desc_sbo, lt), dal = smem_desc(a_lo + ko, p.desc_lbo, p.desc_sbo, lt);
           const uint64_t dbh = smem_desc(b_hi + ko, p.desc_lbo, p.desc_sbo, lt), dbl = smem_desc(b_lo + ko, p.desc_lbo, p.desc_sbo, lt);
           // The tensor core truncates (round toward zero) on every accumulation: a bias of ~2^-25 |acc| per step.
@@ -428,11 +483,6 @@ inline EncodeTiledFn encode_tiled_fn() {
     return (EncodeTiledFn)f;
   }();
   return fn;
-}
-
-inline uint32_t dbg_env(const char *name, uint32_t dflt) {      // bring-up aid: descriptor strides overridable per process
-  const char *v = getenv(name);
-  return v ? (uint32_t)strtoul(v, nullptr, 0) : dflt;
 }
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
