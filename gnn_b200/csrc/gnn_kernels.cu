@@ -1739,7 +1739,7 @@ int gnn_linear_tf32x3_f32_ex(const float *A, int64_t lda, const int64_t *a_rows,
   // this function without one, and the driver-API encode below then fails with CUDA_ERROR_INVALID_CONTEXT)
   auto kern = tc::linear_tc_kernel<tc::MODE_NT>;
   GNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kTcSmemBytes));
-  const int Kp = tc::round_up((int)K, 32), BN = tc::tile_width((int)N);
+  const int Kp = tc::round_up((int)K, 32), BN = tc::tile_width_rows((int)N, M);
   CUtensorMap maps[2];
   for (int pl = 0; pl < 2; ++pl) {
     const cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)N};

@@ -485,19 +485,6 @@ inline EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-
-inline int tile_width(int cols) {
-  const int nt = (cols + kMaxBN - 1) / kMaxBN;
-  return std::min(kMaxBN, round_up((cols + nt - 1) / nt, 16));
-}
-
-inline uint32_t make_idesc(int bn, bool mn_major) {
-  uint32_t d = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-  if (mn_major) d |= (1u << 15) | (1u << 16);
-  return d;
-}
-
 inline int sm_count() {
   static int n = []() {
     int dev = 0, v = 148;
@@ -505,6 +492,29 @@ inline int sm_count() {
     return v;
   }();
   return n;
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+inline int tile_width(int cols) {
+  const int nt = (cols + kMaxBN - 1) / kMaxBN;
+  return std::min(kMaxBN, round_up((cols + nt - 1) / nt, 16));
+}
+
+// NT: with few row tiles (the 512-row top layer) 256-wide tiles leave most SMs idle and the k loop of a CTA is a pure
+// latency chain; narrower tiles (down to 64) give ~half the SMs something to do
+inline int tile_width_rows(int cols, int64_t rows) {
+  const int64_t row_tiles = (rows + kBM - 1) / kBM;
+  int nt = (cols + kMaxBN - 1) / kMaxBN;
+  const int64_t want = (sm_count() / 2 + row_tiles - 1) / row_tiles;
+  if (want > nt) nt = (int)std::min<int64_t>(want, std::max(1, cols / 64));
+  return std::min(kMaxBN, round_up((cols + nt - 1) / nt, 16));
+}
+
+inline uint32_t make_idesc(int bn, bool mn_major) {
+  uint32_t d = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+  if (mn_major) d |= (1u << 15) | (1u << 16);
+  return d;
 }
 
 inline bool aligned16(const void *p, int64_t ld) { return (((uintptr_t)p | (uintptr_t)(ld * 4)) & 15u) == 0; }
