@@ -1949,4 +1949,67 @@ int gnn_legacy_choice_f64(uint32_t *mt_state, const double *p, int64_t n, int64_
   return 0;
 }
 
+// The whole host part of one LADIES layer (reference sampler.py:117-143) in one GIL-free call: probabilities from the
+// integer column counts, the weighted draw above, after_nodes = unique(drawn + previous), the normalisation factors and
+// the sampled_nodes remap.  Every step is integer arithmetic or the reference's own IEEE expressions, so the outputs
+// equal the numpy code's bit for bit (tests/test_sampler_golden.py compares them).
+int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32_t *counts, int64_t n_nz,
+                              const int64_t *skew_nodes, int64_t n_skew, double scale_factor, const int64_t *previous_nodes,
+                              int64_t n_prev, int64_t samp_num, int64_t *after_nodes, float *normfact, int64_t *sampled,
+                              int64_t *n_sampled) {
+  if (!mt_state || !nz || !counts || n_nz <= 0 || !previous_nodes || n_prev < 0 || samp_num < 0 || !after_nodes || !normfact ||
+      !sampled || !n_sampled)
+    return GNN_E_BADARG;
+  // pi = column counts (sampler.py:117); locality sampling scales the counts of the nodes cached on this GPU and the
+  // reference stores the scaled values back into an int64 array (:119-121): truncation
+  std::vector<int64_t> pi((size_t)n_nz);
+  for (int64_t i = 0; i < n_nz; ++i) pi[(size_t)i] = counts[i];
+  if (scale_factor > 1.0 && skew_nodes && n_skew > 0) {
+    int64_t j = 0;
+    for (int64_t i = 0; i < n_nz; ++i) {                                     // both ascending: merge
+      while (j < n_skew && skew_nodes[j] < nz[i]) ++j;
+      if (j < n_skew && skew_nodes[j] == nz[i]) pi[(size_t)i] = (int64_t)((double)pi[(size_t)i] * scale_factor);
+    }
+  }
+  int64_t total = 0;
+  for (int64_t i = 0; i < n_nz; ++i) total += pi[(size_t)i];
+  if (total <= 0) return GNN_E_BADARG;
+  std::vector<double> p((size_t)n_nz);
+  for (int64_t i = 0; i < n_nz; ++i) p[(size_t)i] = (double)pi[(size_t)i] / (double)total;          // p = pi / np.sum(pi)  (:124)
+  int64_t n_pos = 0;
+  for (int64_t i = 0; i < n_nz; ++i) n_pos += pi[(size_t)i] > 0;
+  const int64_t s_num = std::min(n_pos, samp_num);                                                 // :126
+  std::vector<int64_t> found((size_t)std::max<int64_t>(s_num, 1));
+  const int rc = gnn_legacy_choice_f64(mt_state, p.data(), n_nz, s_num, found.data());              // :128
+  if (rc != 0) return rc;
+  // after_nodes = np.unique(np.concatenate((after_nodes, previous_nodes)))  (:131)
+  std::vector<int64_t> all((size_t)(s_num + n_prev));
+  for (int64_t i = 0; i < s_num; ++i) all[(size_t)i] = nz[found[(size_t)i]];
+  for (int64_t i = 0; i < n_prev; ++i) all[(size_t)(s_num + i)] = previous_nodes[i];
+  std::sort(all.begin(), all.end());
+  const int64_t n_after = std::unique(all.begin(), all.end()) - all.begin();
+  // normfact = 1 / np.clip(s_num * p[after_nodes], 1e-10, 1).astype(np.float32)   (:137); p is zero off the support
+  int64_t j = 0;
+  for (int64_t i = 0; i < n_after; ++i) {
+    const int64_t node = all[(size_t)i];
+    while (j < n_nz && nz[j] < node) ++j;
+    const double pa = (j < n_nz && nz[j] == node) ? p[(size_t)j] : 0.0;
+    double v = (double)s_num * pa;
+    v = v < 1e-10 ? 1e-10 : (v > 1.0 ? 1.0 : v);
+    after_nodes[i] = node;
+    normfact[i] = 1.0f / (float)v;
+  }
+  // sampled_nodes = np.where(np.in1d(after_nodes, previous_nodes))[0]   (:143): ascending positions of the distinct previous nodes
+  std::vector<int64_t> prev(previous_nodes, previous_nodes + n_prev);
+  std::sort(prev.begin(), prev.end());
+  const int64_t n_up = std::unique(prev.begin(), prev.end()) - prev.begin();
+  int64_t k = 0, ns = 0;
+  for (int64_t i = 0; i < n_up; ++i) {
+    while (k < n_after && all[(size_t)k] < prev[(size_t)i]) ++k;
+    if (k < n_after && all[(size_t)k] == prev[(size_t)i]) sampled[ns++] = k;
+  }
+  *n_sampled = ns;
+  return n_after;
+}
+
 }  // extern "C"

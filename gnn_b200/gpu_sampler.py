@@ -127,6 +127,76 @@ def legacy_choice_on_support_numpy(rs: np.random.RandomState, p_nz: np.ndarray, 
     return found
 
 
+def mt_state_of(rs: np.random.RandomState) -> np.ndarray:
+    """uint32[625]: the 624 key words of a legacy RandomState followed by its position (what gnn_legacy_choice_f64 and
+    gnn_ladies_layer_host advance in place)."""
+    _, key, pos, _, _ = rs.get_state()
+    state = np.empty(625, dtype=np.uint32)
+    state[:624] = key
+    state[624] = pos
+    return state
+
+
+_skew_cache = {}
+
+
+def _sorted_skew_set(skewed_sampling_nodes, layer: int) -> np.ndarray:
+    """Ascending distinct ids of one layer's locality set (np.isin of sampler.py:120 does not care about order); sorted
+    once per set, not per minibatch."""
+    arr = skewed_sampling_nodes[layer]
+    key = (id(arr), len(arr))
+    hit = _skew_cache.get(key)
+    if hit is None or hit[0] is not arr:
+        hit = (arr, np.unique(np.asarray(arr, dtype=np.int64)))
+        if len(_skew_cache) > 64:
+            _skew_cache.clear()
+        _skew_cache[key] = hit
+    return hit[1]
+
+
+def host_layer_native(mt_state, nz, cnt, skew, scale_factor, previous_nodes, samp_num):
+    """gnn_ladies_layer_host through ctypes -> (after_nodes int64, normfact float32, sampled positions int64, s_num)."""
+    import ctypes
+    lib = _native.cabi()
+    nz = np.ascontiguousarray(nz, dtype=np.int64)
+    cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+    prev = np.ascontiguousarray(previous_nodes, dtype=np.int64)
+    s_num = min(int(nz.size), int(samp_num))
+    cap = s_num + prev.size
+    after = np.empty(cap, dtype=np.int64)
+    normfact = np.empty(cap, dtype=np.float32)
+    sampled = np.empty(prev.size, dtype=np.int64)
+    n_sampled = ctypes.c_int64(0)
+    vp = ctypes.c_void_p
+    use_skew = skew is not None and scale_factor > 1
+    n_after = lib.gnn_ladies_layer_host(vp(mt_state.ctypes.data), vp(nz.ctypes.data), vp(cnt.ctypes.data), nz.size,
+                                        vp(skew.ctypes.data) if use_skew else None, skew.size if use_skew else 0,
+                                        float(scale_factor), vp(prev.ctypes.data), prev.size, int(samp_num), vp(after.ctypes.data),
+                                        vp(normfact.ctypes.data), vp(sampled.ctypes.data), ctypes.byref(n_sampled))
+    if n_after < 0:
+        _native.check(int(n_after), "gnn_ladies_layer_host")
+    return after[:n_after], normfact[:n_after], sampled[:n_sampled.value], s_num
+
+
+def host_layer_numpy(rs, nz, cnt, skew, scale_factor, previous_nodes, samp_num):
+    """The same host part in the reference's numpy expressions (sampler.py:117-143 restricted to the support of p):
+    the readable restatement, and what the tests compare the native call against."""
+    pi_nz = np.asarray(cnt).astype(np.int64)
+    if scale_factor > 1 and skew is not None:
+        # integer counts stay integer (the reference assigns the scaled values into scipy's int64 count array, which
+        # truncates them), so the normaliser below is an exact integer sum on the support as on the full array
+        sel = np.isin(nz, skew)
+        pi_nz[sel] = pi_nz[sel] * scale_factor
+    p_nz = pi_nz / np.sum(pi_nz)                                                            # :124 (same quotients)
+    s_num = np.min([nz.size, samp_num])                                                     # :126 (count of p > 0)
+    after_nodes = nz[legacy_choice_on_support_numpy(rs, p_nz, int(s_num))]                  # :128
+    after_nodes = sorted_unique(np.concatenate((after_nodes, previous_nodes)))              # :131 (np.unique)
+    pos = np.minimum(np.searchsorted(nz, after_nodes), nz.size - 1)
+    p_after = np.where(nz[pos] == after_nodes, p_nz[pos], 0.0)                              # p[after_nodes]
+    normfact = 1 / np.clip(s_num * p_after, 1e-10, 1).astype(np.float32)                    # :137
+    return after_nodes, normfact, sampled_nodes_remap(after_nodes, previous_nodes), int(s_num)
+
+
 def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], graph: DeviceGraph, orders: Sequence[int],
                          create_coo_tensor=None, int16_ids: bool = True, skewed_sampling_nodes=None,
                          scale_factor: float = 1.0, scratch: Optional[SamplerScratch] = None,
@@ -136,7 +206,9 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
         from .custom_sparse_ops import create_coo_tensor
     dev, n = graph.device, graph.num_nodes
     scratch = scratch or graph.default_scratch()
-    rs = np.random.RandomState(seed)       # == np.random.seed(seed) + the global legacy functions (sampler.py:96), thread-safe
+    # == np.random.seed(seed) + the global legacy functions (sampler.py:96), as a private MT19937 state: thread-safe, and
+    # the draws of consecutive layers continue one stream like the reference's
+    mt_state = mt_state_of(np.random.RandomState(seed))
     previous_nodes = np.asarray(batch_nodes)
     batch = previous_nodes
     orders1 = list(orders)[::-1]
@@ -158,18 +230,15 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
         # (index, count) pairs instead of an N-long array (N = 111 M on the papers100M shape)
         nz_dev = torch.nonzero(scratch.counts).flatten()
         nz = nz_dev.cpu().numpy()
-        pi_nz = scratch.counts[nz_dev].cpu().numpy().astype(np.int64)                       # :117 on the support
+        cnt = scratch.counts[nz_dev].cpu().numpy()                                          # :117 on the support (int32)
+        skew = None
         if scale_factor > 1:                                                                # :119-121
-            # integer counts stay integer (the reference assigns the scaled values into scipy's int64 count array, which
-            # truncates them), so the normaliser below is an exact integer sum on the support as on the full array
-            sel = np.isin(nz, skewed_sampling_nodes[len(orders1) - d - 1])
-            pi_nz[sel] = pi_nz[sel] * scale_factor
-        p_nz = pi_nz / np.sum(pi_nz)                                                        # :124 (same quotients)
-        s_num = np.min([nz.size, samp_num_list[d]])                                         # :126 (count of p > 0)
-        after_nodes = nz[legacy_choice_on_support(rs, p_nz, int(s_num))]                    # :128
-        after_nodes = sorted_unique(np.concatenate((after_nodes, previous_nodes)))          # :131 (np.unique)
-        pos = np.minimum(np.searchsorted(nz, after_nodes), nz.size - 1)
-        p_after = np.where(nz[pos] == after_nodes, p_nz[pos], 0.0)                          # p[after_nodes]
+            skew = _sorted_skew_set(skewed_sampling_nodes, len(orders1) - d - 1)
+        # :117-143 on the host in one native call (gnn_ladies_layer_host): p, s_num, the legacy weighted draw, the union
+        # with previous_nodes, normfact and the sampled_nodes remap - same bits as the numpy expressions of
+        # host_layer_numpy() below, a third of the time and outside the GIL
+        after_nodes, normfact, sampled_pos, s_num = host_layer_native(mt_state, nz, cnt, skew, scale_factor, previous_nodes,
+                                                                       int(samp_num_list[d]))
         after_dev = torch.from_numpy(after_nodes.astype(np.int64, copy=False)).to(dev)
         ext.lookup_set(scratch.lookup, after_dev, True)
         try:
@@ -179,12 +248,11 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
             colidx = ext.column_slice_fill(ucols, fullrowptr, scratch.lookup, rowptr, nnz, use16)  # :136
         finally:
             ext.lookup_set(scratch.lookup, after_dev, False)      # the table must be all -1 for the next minibatch, whatever happened
-        normfact = 1 / np.clip(s_num * p_after, 1e-10, 1).astype(np.float32)                # :137
         nf_dev = torch.from_numpy(normfact).to(dev)
         layer = DeviceLayer(fullrowptr, rowptr, colidx, nf_dev, int(previous_nodes.size), int(after_nodes.size))
         layers.append(layer)
         adjs.append(create_coo_tensor(fullrowptr, rowptr, colidx, nf_dev, layer.nrows, layer.ncols))   # :139
-        sampled.append(sampled_nodes_remap(after_nodes, previous_nodes))                    # :143
+        sampled.append(sampled_pos)                                                         # :143
         previous_nodes = after_nodes
     layers.reverse()
     adjs.reverse()

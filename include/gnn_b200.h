@@ -360,6 +360,20 @@ int gnn_probe_row_gather_f32(const float *X, int64_t ldx, int64_t D, const int32
  * ------------------------------------------------------------------------- */
 int gnn_legacy_choice_f64(uint32_t *mt_state, const double *p, int64_t n, int64_t size, int64_t *found);
 
+/* gnn_ladies_layer_host - the whole host part of one LADIES layer, sampler.py:117-143, in one call outside the GIL:
+ *   pi = counts (scaled by scale_factor and truncated for the nodes in skew_nodes, :119-121);  p = pi / sum(pi)  (:124)
+ *   s_num = min(#p > 0, samp_num) (:126);  draw = choice(p, s_num) (:128, gnn_legacy_choice_f64)
+ *   after_nodes = unique(nz[draw] ++ previous_nodes) (:131);  normfact = 1 / float32(clip(s_num * p[after_nodes], 1e-10, 1)) (:137)
+ *   sampled = positions of the distinct previous_nodes inside after_nodes (:143)
+ * nz: the n_nz node ids with a non-zero count, ascending; counts: their int32 column counts (the device sampler brings
+ * both back from the GPU); skew_nodes: ascending distinct ids or NULL.  after_nodes / normfact need room for
+ * min(n_nz, samp_num) + n_prev entries, sampled for n_prev.  Returns the number of after_nodes (>= 0) or a negative code.
+ * Integer arithmetic and the reference's own IEEE expressions only: identical to the numpy code bit for bit. */
+int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32_t *counts, int64_t n_nz,
+                              const int64_t *skew_nodes, int64_t n_skew, double scale_factor, const int64_t *previous_nodes,
+                              int64_t n_prev, int64_t samp_num, int64_t *after_nodes, float *normfact, int64_t *sampled,
+                              int64_t *n_sampled);
+
 /* ---------------------------------------------------------------------------
  * Feature-shard memory that peers can map (one process per GPU).
  *

@@ -133,3 +133,29 @@ def test_native_draw_on_sampler_sized_inputs_and_errors():
     p[:5] = 0.2
     with pytest.raises(ValueError):
         legacy_choice_on_support(np.random.RandomState(0), p, 6)
+
+
+def test_native_host_layer_equals_the_numpy_expressions():
+    """gnn_ladies_layer_host (p, s_num, draw, union with previous_nodes, normfact, sampled_nodes remap in one native call)
+    against the reference's numpy expressions on the same inputs, over several consecutive layers of one stream, with and
+    without locality scaling (integer, dyadic and non-dyadic factors)."""
+    from gnn_b200 import gpu_sampler as gs
+    rng = np.random.Generator(np.random.PCG64(7))
+    for trial, (n_nodes, n_nz, samp, scale) in enumerate([(50000, 30000, 8192, 1.0), (50000, 30000, 8192, 2.0), (200000, 9000, 8192, 1.5),
+                                                         (3000, 50, 64, 16.0), (3000, 2000, 10000, 1.0), (100, 1, 5, 1.0)]):
+        rs = np.random.RandomState(100 + trial)
+        state = gs.mt_state_of(np.random.RandomState(100 + trial))
+        previous = rng.choice(n_nodes, size=min(512, n_nodes // 2), replace=False)
+        for layer in range(3):
+            nz = np.sort(rng.choice(n_nodes, size=n_nz, replace=False)).astype(np.int64)
+            cnt = rng.zipf(1.7, n_nz).clip(max=4000).astype(np.int32)
+            skew = np.unique(rng.choice(n_nodes, size=n_nodes // 10, replace=False)).astype(np.int64) if scale > 1 else None
+            a = gs.host_layer_native(state, nz, cnt, skew, scale, previous, samp)
+            b = gs.host_layer_numpy(rs, nz, cnt, skew, scale, previous, samp)
+            assert np.array_equal(a[0], b[0]), (trial, layer, "after_nodes")
+            assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), (trial, layer, "normfact bits")
+            assert np.array_equal(a[2], b[2]), (trial, layer, "sampled_nodes")
+            assert a[3] == b[3]
+            previous = a[0]
+        # the generator ends in the same state
+        assert np.array_equal(state, gs.mt_state_of(rs))
