@@ -608,6 +608,13 @@ def main():
                     train[key] = fn(args, cso, store, shape, g, ORDERS, NHID, samp, batch, device, rank, world, log, **kw)
             except Exception as exc:                   # secondary numbers must not take the headline down
                 train[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        # one-glance summary: the reference-shaped torch model on the new ops (top level of `train`) against the fastest
+        # variant of the optional fused model pieces, pre-sampled and with the sampler in the loop
+        pre = {k: v["minibatches_per_s"] for k, v in train.items() if isinstance(v, dict) and "minibatches_per_s" in v and not k.startswith("live")}
+        live = {k: v["minibatches_per_s"] for k, v in train.items() if isinstance(v, dict) and "minibatches_per_s" in v and k.startswith("live")}
+        train["summary"] = {"reference_shaped_model": train.get("minibatches_per_s"),
+                            "best_pre_sampled": max(pre.items(), key=lambda kv: kv[1]) if pre else None,
+                            "best_live_sampler": max(live.items(), key=lambda kv: kv[1]) if live else None, "unit": "minibatches/s (all ranks)"}
     if store is not None:
         store.close()
         store = None

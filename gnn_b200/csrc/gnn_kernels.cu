@@ -1900,11 +1900,17 @@ static inline int64_t upper_count(const double *a, int64_t len, double t) {
 int gnn_legacy_choice_f64(uint32_t *mt_state, const double *p, int64_t n, int64_t size, int64_t *found) {
   if (!mt_state || !p || !found || n <= 0 || size < 0 || size > n) return GNN_E_BADARG;
   if (n > INT32_MAX) return GNN_E_RANGE;
-  std::vector<double> pw(p, p + n), raw((size_t)n), x((size_t)std::max<int64_t>(size, 1));
-  std::vector<int32_t> stamp((size_t)n + 1, 0);
-  std::vector<int64_t> cand((size_t)std::max<int64_t>(size, 1));
+  // scratch lives per thread and only grows: fresh multi-megabyte vectors per call cost more in page faults than the draw
+  static thread_local std::vector<double> pw, raw, x, coarse;
+  static thread_local std::vector<int32_t> stamp;
+  static thread_local std::vector<int64_t> cand;
   const int64_t nc = (n + 63) / 64;
-  std::vector<double> coarse((size_t)nc);
+  pw.assign(p, p + n);
+  if ((int64_t)raw.size() < n) raw.resize((size_t)n);
+  if ((int64_t)x.size() < size + 1) x.resize((size_t)size + 1);
+  if ((int64_t)cand.size() < size + 1) cand.resize((size_t)size + 1);
+  if ((int64_t)coarse.size() < nc) coarse.resize((size_t)nc);
+  stamp.assign((size_t)n + 1, 0);
   int64_t n_uniq = 0, zeroed = 0;
   int32_t round = 0;
   while (n_uniq < size) {
@@ -1962,7 +1968,9 @@ int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32
     return GNN_E_BADARG;
   // pi = column counts (sampler.py:117); locality sampling scales the counts of the nodes cached on this GPU and the
   // reference stores the scaled values back into an int64 array (:119-121): truncation
-  std::vector<int64_t> pi((size_t)n_nz);
+  static thread_local std::vector<int64_t> pi, found, all, prev;
+  static thread_local std::vector<double> p;
+  pi.resize((size_t)n_nz);
   for (int64_t i = 0; i < n_nz; ++i) pi[(size_t)i] = counts[i];
   if (scale_factor > 1.0 && skew_nodes && n_skew > 0) {
     int64_t j = 0;
@@ -1974,16 +1982,16 @@ int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32
   int64_t total = 0;
   for (int64_t i = 0; i < n_nz; ++i) total += pi[(size_t)i];
   if (total <= 0) return GNN_E_BADARG;
-  std::vector<double> p((size_t)n_nz);
+  p.resize((size_t)n_nz);
   for (int64_t i = 0; i < n_nz; ++i) p[(size_t)i] = (double)pi[(size_t)i] / (double)total;          // p = pi / np.sum(pi)  (:124)
   int64_t n_pos = 0;
   for (int64_t i = 0; i < n_nz; ++i) n_pos += pi[(size_t)i] > 0;
   const int64_t s_num = std::min(n_pos, samp_num);                                                 // :126
-  std::vector<int64_t> found((size_t)std::max<int64_t>(s_num, 1));
+  found.resize((size_t)std::max<int64_t>(s_num, 1));
   const int rc = gnn_legacy_choice_f64(mt_state, p.data(), n_nz, s_num, found.data());              // :128
   if (rc != 0) return rc;
   // after_nodes = np.unique(np.concatenate((after_nodes, previous_nodes)))  (:131)
-  std::vector<int64_t> all((size_t)(s_num + n_prev));
+  all.resize((size_t)(s_num + n_prev));
   for (int64_t i = 0; i < s_num; ++i) all[(size_t)i] = nz[found[(size_t)i]];
   for (int64_t i = 0; i < n_prev; ++i) all[(size_t)(s_num + i)] = previous_nodes[i];
   std::sort(all.begin(), all.end());
@@ -2000,7 +2008,7 @@ int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32
     normfact[i] = 1.0f / (float)v;
   }
   // sampled_nodes = np.where(np.in1d(after_nodes, previous_nodes))[0]   (:143): ascending positions of the distinct previous nodes
-  std::vector<int64_t> prev(previous_nodes, previous_nodes + n_prev);
+  prev.assign(previous_nodes, previous_nodes + n_prev);
   std::sort(prev.begin(), prev.end());
   const int64_t n_up = std::unique(prev.begin(), prev.end()) - prev.begin();
   int64_t k = 0, ns = 0;
