@@ -155,6 +155,7 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
     if world > 1:
         dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mallocs0 = torch.cuda.memory_stats(device).get("num_device_alloc", 0)
     t0 = time.perf_counter()
     ev0.record()
     for s in range(steps):
@@ -178,6 +179,7 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
             "ms_per_step_device": round(ms / steps, 3), "ms_per_step_wall": round(wall / steps * 1e3, 3),
             "allreduce_bytes_per_step": int(comm_bytes), "parameters": int(nparams), "final_loss": round(last, 4),
             "fused_epilogue": bool(fused), "flat_gradients": bool(flat_grads), "tensor_core_linears": bool(tc), "model": kind,
+            "cuda_mallocs_in_timed_region": int(torch.cuda.memory_stats(device).get("num_device_alloc", 0) - mallocs0),
             "note": f"gather (next minibatch prefetched on a side stream) + {kind} fwd + BCE loss + bwd + clip + NCCL "
                     "allreduce(sum) + Adam on pre-sampled minibatches (host LADIES sampling and adjacency upload excluded)"}
 
