@@ -1990,11 +1990,15 @@ int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32
   found.resize((size_t)std::max<int64_t>(s_num, 1));
   const int rc = gnn_legacy_choice_f64(mt_state, p.data(), n_nz, s_num, found.data());              // :128
   if (rc != 0) return rc;
-  // after_nodes = np.unique(np.concatenate((after_nodes, previous_nodes)))  (:131)
-  all.resize((size_t)(s_num + n_prev));
-  for (int64_t i = 0; i < s_num; ++i) all[(size_t)i] = nz[found[(size_t)i]];
-  for (int64_t i = 0; i < n_prev; ++i) all[(size_t)(s_num + i)] = previous_nodes[i];
-  std::sort(all.begin(), all.end());
+  // after_nodes = np.unique(np.concatenate((after_nodes, previous_nodes)))  (:131).  previous_nodes is the sorted-unique
+  // after_nodes of the layer above (only the batch itself arrives unsorted): sort the drawn nodes, merge, drop repeats
+  prev.assign(previous_nodes, previous_nodes + n_prev);
+  if (!std::is_sorted(prev.begin(), prev.end())) std::sort(prev.begin(), prev.end());
+  const int64_t n_up = std::unique(prev.begin(), prev.end()) - prev.begin();
+  for (int64_t i = 0; i < s_num; ++i) found[(size_t)i] = nz[found[(size_t)i]];
+  std::sort(found.begin(), found.begin() + s_num);
+  all.resize((size_t)(s_num + n_up));
+  std::merge(found.begin(), found.begin() + s_num, prev.begin(), prev.begin() + n_up, all.begin());
   const int64_t n_after = std::unique(all.begin(), all.end()) - all.begin();
   // normfact = 1 / np.clip(s_num * p[after_nodes], 1e-10, 1).astype(np.float32)   (:137); p is zero off the support
   int64_t j = 0;
@@ -2008,9 +2012,6 @@ int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32
     normfact[i] = 1.0f / (float)v;
   }
   // sampled_nodes = np.where(np.in1d(after_nodes, previous_nodes))[0]   (:143): ascending positions of the distinct previous nodes
-  prev.assign(previous_nodes, previous_nodes + n_prev);
-  std::sort(prev.begin(), prev.end());
-  const int64_t n_up = std::unique(prev.begin(), prev.end()) - prev.begin();
   int64_t k = 0, ns = 0;
   for (int64_t i = 0; i < n_up; ++i) {
     while (k < n_after && all[(size_t)k] < prev[(size_t)i]) ++k;

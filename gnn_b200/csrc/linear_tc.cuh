@@ -222,10 +222,12 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
         const int m = row0 + r + RPP * i;
         rp[i] = (m < p.M) ? p.A + (p.a_rows ? p.a_rows[m] : (int64_t)m) * p.lda : nullptr;
       }
-      float4 v[NPASS];
+      // Two register sets: the loads of k-block it+1 are issued BEFORE the stores of k-block it, so a whole k-block
+      // period (not just the wait for a free stage) covers their latency.
+      float4 v0[NPASS], v1[NPASS];
       // whole k-block inside K and 16-byte aligned rows (warp-uniform): one predicated 128-bit load per row; otherwise
       // (last k-block of K = 602, unaligned rows) the bounds-checked path
-      auto load = [&](int kb) {
+      auto load = [&](int kb, float4 (&v)[NPASS]) {
         const int col = kb * kBK + c * 4;
         if (p.a_vec && kb * kBK + kBK <= p.K) {
 #pragma unroll
@@ -236,8 +238,7 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
           for (int i = 0; i < NPASS; ++i) v[i] = load4(rp[i], col, p.K, p.a_vec);
         }
       };
-      if (nkb > 0) load(kb_begin);
-      for (int it = 0; it < nkb; ++it) {
+      auto put = [&](int it, const float4 (&v)[NPASS]) {
         const int s = it % kStages;
         mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
         const uint32_t a_hi = base + s * kStageBytes, a_lo = a_hi + kATile;
@@ -245,12 +246,22 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
         for (int i = 0; i < NPASS; ++i) split_store(a_hi + swz + i * (RPP * kBK * 4), a_lo + swz + i * (RPP * kBK * 4), v[i]);
         fence_proxy_async();
         mbar_arrive(bar_full + 8 * s);
-        if (it + 1 < nkb) load(kb_begin + it + 1);
+      };
+      if (nkb > 0) load(kb_begin, v0);
+      for (int it = 0; it < nkb; it += 2) {
+        if (it + 1 < nkb) load(kb_begin + it + 1, v1);
+        put(it, v0);
+        if (it + 1 < nkb) {
+          if (it + 2 < nkb) load(kb_begin + it + 2, v0);
+          put(it + 1, v1);
+        }
       }
     } else {
       const int npanels = (p.BN + 31) >> 5;
       constexpr int NA = 4 / TNG, NB = 8 / TNG;            // A / B panels per thread
-      float4 va[NA], vb[NB];
+      // two register sets, as in the NT producer: loads one k-block ahead of the stores; the gather index of the row
+      // after that is fetched alongside, so a gathered row costs one exposed round trip, not two
+      float4 va0[NA], vb0[NB], va1[NA], vb1[NB];
       // which of this thread's 16-byte chunks are fully inside the operand (128-bit load), partly inside (bounds-checked
       // path) or outside: loop-invariant, only the reduction row changes per k-block
       uint32_t a_full = 0, a_part = 0, b_full = 0, b_part = 0;
@@ -265,11 +276,19 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
         if (grp * NB + q < npanels) { if (p.b_vec && col + 4 <= lim) b_full |= 1u << q; else if (col < lim) b_part |= 1u << q; }
       }
       const int a_col0 = 32 * grp * NA + 4 * c, b_col0 = 32 * grp * NB + 4 * c;
-      auto load = [&](int kb) {
+      auto row_of = [&](int kb) -> int64_t {                // X row of this thread's reduction row in k-block kb (-1: past the end)
         const int m = kb * kBK + r;
-        const bool ok = m < p.M;
+        if (kb >= kb_end || m >= p.M) return -1;
+        return p.b_rows ? __ldg(p.b_rows + m) : (int64_t)m;
+      };
+      int64_t xrow_next = nkb > 0 ? row_of(kb_begin) : -1;
+      auto load = [&](int kb, float4 (&va)[NA], float4 (&vb)[NB]) {
+        const int m = kb * kBK + r;
+        const int64_t xrow = xrow_next;
+        xrow_next = row_of(kb + 1);
+        const bool ok = xrow >= 0;
         const float *ar = p.A + (int64_t)(ok ? m : 0) * p.lda + row0 + a_col0;
-        const float *br = p.B + (ok ? (p.b_rows ? p.b_rows[m] : (int64_t)m) : 0) * p.ldb + col0 + b_col0;
+        const float *br = p.B + (ok ? xrow : 0) * p.ldb + col0 + b_col0;
         const uint32_t af = ok ? a_full : 0u, ap = ok ? a_part : 0u, bf = ok ? b_full : 0u, bp = ok ? b_part : 0u;
 #pragma unroll
         for (int q = 0; q < NA; ++q) {
@@ -284,8 +303,7 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
           else if (bp >> q & 1u) vb[q] = load4(br - b_col0, b_col0 + 32 * q, p.K - col0, 0);
         }
       };
-      if (nkb > 0) load(kb_begin);
-      for (int it = 0; it < nkb; ++it) {
+      auto put = [&](int it, const float4 (&va)[NA], const float4 (&vb)[NB]) {
         const int s = it % kStages;
         mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
         const uint32_t a_hi = base + s * kStageBytes, a_lo = a_hi + kATile, b_hi = a_lo + kATile, b_lo = b_hi + kBTile;
@@ -298,7 +316,15 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
             split_store(b_hi + (grp * NB + q) * kPanelBytes + swz, b_lo + (grp * NB + q) * kPanelBytes + swz, vb[q]);
         fence_proxy_async();
         mbar_arrive(bar_full + 8 * s);
-        if (it + 1 < nkb) load(kb_begin + it + 1);
+      };
+      if (nkb > 0) load(kb_begin, va0, vb0);
+      for (int it = 0; it < nkb; it += 2) {
+        if (it + 1 < nkb) load(kb_begin + it + 1, va1, vb1);
+        put(it, va0, vb0);
+        if (it + 1 < nkb) {
+          if (it + 2 < nkb) load(kb_begin + it + 2, va0, vb0);
+          put(it + 1, va1, vb1);
+        }
       }
     }
   } else if (warp == kProducerWarps) {

@@ -133,11 +133,18 @@ def group_time():
         ts = timed(lambda: ext.linear_split_weights(W, True))
         print(f"| split W | {N}x{K} | {ts:.1f} | | |", flush=True)
     for (M, N, K) in [(16157, 512, 602), (8689, 512, 1024), (512, 512, 1024)]:
-        X = torch.randn(M, K, device=dev)
+        X = torch.randn(M, (K + 31) // 32 * 32, device=dev)[:, :K]          # rows on 128-byte lines, as the layer feeds them
         dY = torch.randn(M, 2 * N, device=dev)[:, N:]
         t = timed(lambda: ext.linear_wgrad_tf32x3(dY, X, None))
         t0 = timed(lambda: torch.mm(dY.t(), X))
         print(f"| TN | M{M} N{N} K{K} | {t:.1f} | {2*M*K*N/t/1e6:.0f} | {t0:.1f} |", flush=True)
+        if K % 4:
+            Xu = torch.randn(M, K, device=dev)
+            t = timed(lambda: ext.linear_wgrad_tf32x3(dY, Xu, None))
+            print(f"| TN (rows {K} floats apart: scalar loads) | M{M} N{N} K{K} | {t:.1f} | {2*M*K*N/t/1e6:.0f} | |", flush=True)
+        rows = torch.randperm(M, device=dev)
+        t = timed(lambda: ext.linear_wgrad_tf32x3(dY, X, rows))
+        print(f"| TN (gathered rows) | M{M} N{N} K{K} | {t:.1f} | {2*M*K*N/t/1e6:.0f} | |", flush=True)
 
 
 def group_model():
