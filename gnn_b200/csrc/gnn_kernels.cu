@@ -1778,7 +1778,7 @@ int gnn_linear_tf32x3_f32_ex(const float *A, int64_t lda, const int64_t *a_rows,
     p.kb0 = ch * kbpc; p.kb_per_split = kbpc;
     p.bias = ch == 0 ? bias : nullptr;
     p.accumulate = c_rows ? 2 : (((flags & GNN_LINEAR_ACCUMULATE) || ch > 0) ? 1 : 0);
-    kern<<<grid, tc::kTcThreads, tc::kTcSmemBytes, (cudaStream_t)stream>>>(p, maps[0], maps[1]);
+    kern<<<grid, tc::tc_threads(tc::MODE_NT), tc::kTcSmemBytes, (cudaStream_t)stream>>>(p, maps[0], maps[1]);
     GNN_LAUNCH_CHECK();
   }
   return 0;
@@ -1845,7 +1845,7 @@ int gnn_linear_wgrad_tf32x3_f32(const float *dY, int64_t lddy, const float *X, i
   GNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kTcSmemBytes));
   const dim3 grid((unsigned)cdiv(N, tc::kBM), (unsigned)cdiv(K, BN), (unsigned)splits);
   CUtensorMap dummy{};
-  kern<<<grid, tc::kTcThreads, tc::kTcSmemBytes, (cudaStream_t)stream>>>(p, dummy, dummy);
+  kern<<<grid, tc::tc_threads(tc::MODE_TN), tc::kTcSmemBytes, (cudaStream_t)stream>>>(p, dummy, dummy);
   GNN_LAUNCH_CHECK();
   if (!direct) {
     const int rgrid = (int)std::min<int64_t>(cdiv(N * K, 256), 148 * 8);

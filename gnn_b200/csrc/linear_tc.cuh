@@ -34,8 +34,10 @@ constexpr int kBM = 128;                       // UMMA M (TMEM lanes)
 constexpr int kBK = GNN_TC_BK;
 static_assert(kBK == 16 || kBK == 32, "k-block is 16 or 32 floats");
 constexpr int kStages = kBK == 16 ? 4 : 2;
-constexpr int kProducerWarps = 8;
-constexpr int kTcThreads = (kProducerWarps + 2) * 32;
+// producer warps: 8 for NT (4 chunks per thread and k-block; the kernel is shared-memory-bound), 16 for TN, whose producers move
+// three times the bytes through registers and are issue-bound (6 chunks per thread and k-block instead of 12)
+__host__ __device__ constexpr int producer_warps(int mode) { return mode == 1 ? 16 : 8; }
+__host__ __device__ constexpr int tc_threads(int mode) { return (producer_warps(mode) + 2) * 32; }
 constexpr int kMaxBN = 256;
 constexpr uint32_t kPanelBytes = kBK * 128;    // MN-major panel: [kBK rows][128 B]
 constexpr uint32_t kATile = kBM * kBK * 4;     // K-major: 128 rows x kBK floats; MN-major: 4 panels
@@ -156,7 +158,7 @@ __device__ __forceinline__ void split_store(uint32_t hi_addr, uint32_t lo_addr, 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(tc_threads(MODE), 1)
 linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
   extern __shared__ uint8_t tc_smem_raw[];
   const uint32_t base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
@@ -164,6 +166,7 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kStages, bar_accum = bars + 16 * kStages;
   const uint32_t tmem_slot = bar_accum + 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kProducerWarps = producer_warps(MODE);
 
   // tile coordinates
   //   NT: rows of C = blockIdx.x * 128 (m), columns = blockIdx.y * BN (n), reduce over all of K
@@ -379,14 +382,14 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
     float *C = p.C + (MODE == MODE_TN ? (int64_t)blockIdx.z * p.c_split_stride : 0);
     const int rows_total = (MODE == MODE_NT) ? p.M : p.N;
     const int cols_total = (MODE == MODE_NT) ? p.N : p.K;
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, part = warp >> 2;              // TMEM lane quarter of this warp; column chunks are dealt round-robin
     const int nchunks = (p.BN + 31) >> 5;
     if (nkb > 0) {
       mbar_wait(bar_accum, 0);
       tc_fence_after();
     }
     const uint32_t scratch = base + warp * (32 * kEpiStride * 4);
-    for (int ch = half; ch < nchunks; ch += 2) {
+    for (int ch = part; ch < nchunks; ch += kProducerWarps / 4) {
       uint32_t v[32];
       if (nkb > 0) {
         uint32_t w[32];
