@@ -154,19 +154,32 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
     gc.disable()              # a full collection of a torch process takes 5-12 ms; training scripts freeze/disable it too
     if world > 1:
         dist.barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    mallocs0 = torch.cuda.memory_stats(device).get("num_device_alloc", 0)
-    t0 = time.perf_counter()
-    ev0.record()
-    for s in range(steps):
-        loss = step(s)
-    ev1.record()
+    # A cudaMalloc inside the timed steps (the caching allocator still growing: each one stalls every stream for tens of
+    # ms) means the loop has not reached its steady state; every rank then times the same number of steps once more, and
+    # the line says so.
+    repeats = 0
+    step_base = 0
+    while True:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        mallocs0 = torch.cuda.memory_stats(device).get("num_device_alloc", 0)
+        t0 = time.perf_counter()
+        ev0.record()
+        for s in range(steps):
+            loss = step(step_base + s)
+        ev1.record()
+        last = float(loss.item())
+        torch.cuda.synchronize()
+        mallocs = int(torch.cuda.memory_stats(device).get("num_device_alloc", 0) - mallocs0)
+        again = torch.tensor([1 if (mallocs > 0 and repeats == 0) else 0], device=device)
+        if world > 1:
+            dist.all_reduce(again, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        wall = time.perf_counter() - t0
+        if int(again.item()) == 0:
+            break
+        repeats += 1
+        step_base += steps
     pending.clear()
-    last = float(loss.item())
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    wall = time.perf_counter() - t0
     gc.enable()
     ms = ev0.elapsed_time(ev1)
     store.end_co_running(co_token)
@@ -179,7 +192,7 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
             "ms_per_step_device": round(ms / steps, 3), "ms_per_step_wall": round(wall / steps * 1e3, 3),
             "allreduce_bytes_per_step": int(comm_bytes), "parameters": int(nparams), "final_loss": round(last, 4),
             "fused_epilogue": bool(fused), "flat_gradients": bool(flat_grads), "tensor_core_linears": bool(tc), "model": kind,
-            "cuda_mallocs_in_timed_region": int(torch.cuda.memory_stats(device).get("num_device_alloc", 0) - mallocs0),
+            "cuda_mallocs_in_timed_region": mallocs, "timed_region_repeated_after_allocator_growth": bool(repeats),
             "note": f"gather (next minibatch prefetched on a side stream) + {kind} fwd + BCE loss + bwd + clip + NCCL "
                     "allreduce(sum) + Adam on pre-sampled minibatches (host LADIES sampling and adjacency upload excluded)"}
 
