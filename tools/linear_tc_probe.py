@@ -198,7 +198,7 @@ if __name__ == "__main__":
             w_nk, _ = ext.linear_split_weights(W, False)
             ext.linear_tf32x3(x, None, w_nk, K, None, out)
         for (M, N, K) in [(16157, 512, 602), (8689, 512, 1024)]:
-            X = torch.randn(M, K, device=dev)
+            X = torch.randn(M, (K + 31) // 32 * 32, device=dev)[:, :K]
             dY = torch.randn(M, 2 * N, device=dev)[:, N:]
             ext.linear_wgrad_tf32x3(dY, X, None)
         torch.cuda.synchronize()

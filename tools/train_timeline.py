@@ -22,7 +22,7 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
 print(f"profiled: {r['ms_per_step_device']} ms device", flush=True)
 ev = [e for e in prof.profiler.kineto_results.events()] if False else None
 ka = prof.key_averages()
-steps = 3 + r['steps']
+steps = 6 + r['steps'] * (2 if r.get('timed_region_repeated_after_allocator_growth') else 1)   # warm-up + timed steps of bench_train
 from torch.autograd import DeviceType
 rows = sorted([(k.self_device_time_total, k.count, k.key) for k in ka
                if k.device_type == DeviceType.CUDA and k.self_device_time_total > 0], reverse=True)      # kernels and memcpys only
