@@ -80,10 +80,11 @@ def cabi() -> ctypes.CDLL:
                 "gnn_elu_rownorm_bwd_f32": (ctypes.c_int, [vp, i64, vp, i64, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, sz, vp]),
                 "gnn_linear_split_elems": (sz, [i64, i64]),
                 "gnn_linear_split_weights_f32": (ctypes.c_int, [vp, i64, i64, i64, vp, vp, vp]),
+                "gnn_linear_split_weights2_f32": (ctypes.c_int, [vp, i64, i64, i64, vp, vp, vp, i64, i64, i64, vp, vp, vp]),
                 "gnn_linear_tf32x3_f32": (ctypes.c_int, [vp, i64, vp, i64, i64, vp, i64, vp, vp, i64, vp]),
                 "gnn_linear_tf32x3_f32_ex": (ctypes.c_int, [vp, i64, vp, i64, i64, vp, i64, vp, vp, i64, vp, ctypes.c_uint, vp]),
                 "gnn_linear_wgrad_workspace_bytes": (sz, [i64, i64, i64]),
-                "gnn_linear_wgrad_tf32x3_f32": (ctypes.c_int, [vp, i64, vp, i64, vp, i64, i64, i64, vp, i64, vp, sz, vp]),
+                "gnn_linear_wgrad_tf32x3_f32": (ctypes.c_int, [vp, i64, vp, i64, vp, i64, i64, i64, vp, i64, vp, vp, sz, vp]),
                 "gnn_legacy_choice_f64": (ctypes.c_int, [vp, vp, i64, i64, vp]),
                 "gnn_ladies_layer_host": (i64, [vp, vp, vp, i64, vp, i64, ctypes.c_double, vp, i64, i64, vp, vp, vp, vp]),
                 "gnn_shard_alloc": (ctypes.c_int, [sz, ctypes.POINTER(vp), ctypes.c_char_p]),

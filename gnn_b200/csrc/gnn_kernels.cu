@@ -1724,6 +1724,19 @@ int gnn_linear_split_weights_f32(const float *W, int64_t ldw, int64_t N, int64_t
   return 0;
 }
 
+int gnn_linear_split_weights2_f32(const float *W0, int64_t ldw0, int64_t N0, int64_t K0, float *w_nk0, float *w_kn0, const float *W1,
+                                  int64_t ldw1, int64_t N1, int64_t K1, float *w_nk1, float *w_kn1, gnn_stream_t stream) {
+  if (!W0 || !w_nk0 || N0 <= 0 || K0 <= 0 || ldw0 < K0 || !W1 || !w_nk1 || N1 <= 0 || K1 <= 0 || ldw1 < K1) return GNN_E_BADARG;
+  if (N0 > INT32_MAX / 2 || K0 > INT32_MAX / 2 || N1 > INT32_MAX / 2 || K1 > INT32_MAX / 2) return GNN_E_RANGE;
+  tc::SplitJob j0{W0, ldw0, (int)N0, (int)K0, tc::round_up((int)K0, 32), tc::round_up((int)N0, 32), w_nk0, w_kn0};
+  tc::SplitJob j1{W1, ldw1, (int)N1, (int)K1, tc::round_up((int)K1, 32), tc::round_up((int)N1, 32), w_nk1, w_kn1};
+  const int64_t t0 = N0 * j0.Kp + (w_kn0 ? K0 * j0.Np : 0), t1 = N1 * j1.Kp + (w_kn1 ? K1 * j1.Np : 0);
+  const dim3 grid((unsigned)std::min<int64_t>(cdiv(std::max(t0, t1), 256), 148 * 4), 2);
+  tc::split_weights2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(j0, j1);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
 int gnn_linear_tf32x3_f32_ex(const float *A, int64_t lda, const int64_t *a_rows, int64_t M, int64_t K, const float *w_split,
                              int64_t N, const float *bias, float *C, int64_t ldc, const int64_t *c_rows, unsigned flags,
                              gnn_stream_t stream) {
@@ -1815,16 +1828,17 @@ size_t gnn_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   if (M < 0 || N <= 0 || K <= 0) return 0;
   int BN, splits, kbps; int64_t ldp;
   wgrad_plan(M, N, K, BN, splits, kbps, ldp);
-  return (size_t)splits * (size_t)N * (size_t)ldp * 4 + 16;
+  return (size_t)splits * ((size_t)N * (size_t)ldp + (size_t)((N + 3) / 4 * 4)) * 4 + 16;      // dW partials + dbias partials
 }
 
 int gnn_linear_wgrad_tf32x3_f32(const float *dY, int64_t lddy, const float *X, int64_t ldx, const int64_t *x_rows, int64_t M,
-                                int64_t N, int64_t K, float *dW, int64_t lddw, void *workspace, size_t workspace_bytes,
-                                gnn_stream_t stream) {
+                                int64_t N, int64_t K, float *dW, int64_t lddw, float *dbias, void *workspace,
+                                size_t workspace_bytes, gnn_stream_t stream) {
   if (M < 0 || N <= 0 || K <= 0 || lddy < N || lddw < K || !dW) return GNN_E_BADARG;
   if (M > INT32_MAX / 2 || N > INT32_MAX / 2 || K > INT32_MAX / 2) return GNN_E_RANGE;
   if (M == 0) {
     GNN_CUDA(cudaMemset2DAsync(dW, (size_t)lddw * 4, 0, (size_t)K * 4, (size_t)N, (cudaStream_t)stream));
+    if (dbias) GNN_CUDA(cudaMemsetAsync(dbias, 0, (size_t)N * 4, (cudaStream_t)stream));
     return 0;
   }
   if (!dY || !X) return GNN_E_BADARG;
@@ -1840,6 +1854,9 @@ int gnn_linear_wgrad_tf32x3_f32(const float *dY, int64_t lddy, const float *X, i
   p.a_vec = tc::aligned16(dY, lddy); p.b_vec = tc::aligned16(X, ldx);
   const bool direct = splits == 1;
   p.C = direct ? dW : ws; p.ldc = direct ? lddw : ldp; p.c_split_stride = N * ldp;
+  const int64_t Np4 = (N + 3) / 4 * 4;
+  float *db_ws = ws + (size_t)splits * (size_t)N * (size_t)ldp;
+  p.dbias = dbias ? (direct ? dbias : db_ws) : nullptr; p.dbias_split_stride = Np4;
   p.c_vec = tc::aligned16(p.C, p.ldc);
   auto kern = tc::linear_tc_kernel<tc::MODE_TN>;
   GNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kTcSmemBytes));
@@ -1849,7 +1866,8 @@ int gnn_linear_wgrad_tf32x3_f32(const float *dY, int64_t lddy, const float *X, i
   GNN_LAUNCH_CHECK();
   if (!direct) {
     const int rgrid = (int)std::min<int64_t>(cdiv(N * K, 256), 148 * 8);
-    tc::reduce_splits_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(ws, N * ldp, splits, (int)N, (int)K, ldp, dW, lddw);
+    tc::reduce_splits_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(ws, N * ldp, splits, (int)N, (int)K, ldp, dW, lddw, db_ws, Np4,
+                                                                      dbias);
     GNN_LAUNCH_CHECK();
   }
   return 0;

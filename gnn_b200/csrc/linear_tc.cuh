@@ -54,6 +54,7 @@ struct TcParams {
   const float *A; int64_t lda; const int64_t *a_rows;   // NT: activations [M,K] (rows optional); TN: dY [M,N]
   const float *B; int64_t ldb; const int64_t *b_rows;   // TN only: X [M,K] (rows optional)
   const float *bias;                                    // NT only, may be NULL
+  float *dbias; int64_t dbias_split_stride;             // TN only, may be NULL: column sums of dY (bias gradient), per split
   float *C; int64_t ldc; int64_t c_split_stride;        // TN: partial of split z at C + z * c_split_stride
   const int64_t *c_rows;                                // NT: output row m goes to C[c_rows[m]] (atomic adds), or NULL
   int accumulate;                                       // NT: 0 store, 1 C += (plain read-modify-write), 2 red.add
@@ -265,6 +266,9 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
       // two register sets, as in the NT producer: loads one k-block ahead of the stores; the gather index of the row
       // after that is fetched alongside, so a gathered row costs one exposed round trip, not two
       float4 va0[NA], vb0[NB], va1[NA], vb1[NB];
+      float4 dsum[NA];
+#pragma unroll
+      for (int q = 0; q < NA; ++q) dsum[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       // which of this thread's 16-byte chunks are fully inside the operand (128-bit load), partly inside (bounds-checked
       // path) or outside: loop-invariant, only the reduction row changes per k-block
       uint32_t a_full = 0, a_part = 0, b_full = 0, b_part = 0;
@@ -311,8 +315,10 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
         mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
         const uint32_t a_hi = base + s * kStageBytes, a_lo = a_hi + kATile, b_hi = a_lo + kATile, b_lo = b_hi + kBTile;
 #pragma unroll
-        for (int q = 0; q < NA; ++q)
+        for (int q = 0; q < NA; ++q) {
           split_store(a_hi + (grp * NA + q) * kPanelBytes + swz, a_lo + (grp * NA + q) * kPanelBytes + swz, va[q]);
+          dsum[q].x += va[q].x; dsum[q].y += va[q].y; dsum[q].z += va[q].z; dsum[q].w += va[q].w;    // bias gradient: column sums of dY
+        }
 #pragma unroll
         for (int q = 0; q < NB; ++q)
           if (grp * NB + q < npanels)
@@ -327,6 +333,21 @@ linear_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap map_hi, c
         if (it + 1 < nkb) {
           if (it + 2 < nkb) load(kb_begin + it + 2, va0, vb0);
           put(it + 1, va1, vb1);
+        }
+      }
+      // Bias gradient (column sums of this CTA's dY rows): the k-tile-0 CTAs fold their threads' running sums over the 32
+      // reduction rows in a fixed order, through the second operand stage (free once the accumulator is complete).
+      if (p.dbias != nullptr && blockIdx.y == 0) {
+        if (nkb > 0) mbar_wait(bar_accum, 0);
+        float *dbs = reinterpret_cast<float *>(tc_smem_raw + (base - smem_u32(tc_smem_raw)) + kStageBytes);     // [32 rows][128 columns]
+#pragma unroll
+        for (int q = 0; q < NA; ++q) *reinterpret_cast<float4 *>(dbs + r * kBM + 32 * (grp * NA + q) + 4 * c) = dsum[q];
+        asm volatile("bar.sync 1, %0;" ::"r"(kProducerWarps * 32) : "memory");
+        if (tid < kBM) {
+          float acc = 0.f;
+#pragma unroll 8
+          for (int j = 0; j < kBK; ++j) acc += dbs[j * kBM + tid];
+          if (row0 + tid < p.N) p.dbias[(int64_t)blockIdx.z * p.dbias_split_stride + row0 + tid] = acc;
         }
       }
     }
@@ -483,10 +504,42 @@ __global__ void split_weights_kernel(const float *__restrict__ W, int64_t ldw, i
   }
 }
 
+// the two weight matrices of a GraphSAGE layer (linearB, linearW) in one launch: blockIdx.y picks the matrix
+struct SplitJob { const float *W; int64_t ldw; int N, K, Kp, Np; float *w_nk, *w_kn; };
+__global__ void split_weights2_kernel(const SplitJob j0, const SplitJob j1) {
+  const SplitJob &j = blockIdx.y == 0 ? j0 : j1;
+  const int64_t n_nk = (int64_t)j.N * j.Kp, n_kn = j.w_kn ? (int64_t)j.K * j.Np : 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_nk + n_kn; i += (int64_t)gridDim.x * blockDim.x) {
+    float x;
+    float *hi, *lo;
+    if (i < n_nk) {
+      const int n = (int)(i / j.Kp), k = (int)(i % j.Kp);
+      x = k < j.K ? j.W[(int64_t)n * j.ldw + k] : 0.f;
+      hi = j.w_nk + i; lo = j.w_nk + n_nk + i;
+    } else {
+      const int64_t t = i - n_nk;
+      const int k = (int)(t / j.Np), n = (int)(t % j.Np);
+      x = n < j.N ? j.W[(int64_t)n * j.ldw + k] : 0.f;
+      hi = j.w_kn + t; lo = j.w_kn + n_kn + t;
+    }
+    const float h = tf32_rn(x);
+    *hi = h;
+    *lo = tf32_rn(x - h);
+  }
+}
+
 // dW[n,k] = sum over splits in ascending order (fixed => reproducible)
 __global__ void reduce_splits_kernel(const float *__restrict__ ws, int64_t split_stride, int splits, int N, int K, int64_t ldp,
-                                     float *__restrict__ out, int64_t ldo) {
+                                     float *__restrict__ out, int64_t ldo, const float *__restrict__ db_ws, int64_t db_stride,
+                                     float *__restrict__ db_out) {
   const int64_t total = (int64_t)N * K;
+  if (db_out != nullptr) {
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+      float acc = db_ws[n];
+      for (int s = 1; s < splits; ++s) acc += db_ws[(int64_t)s * db_stride + n];
+      db_out[n] = acc;
+    }
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int n = (int)(i / K), k = (int)(i % K);
     const float *src = ws + (int64_t)n * ldp + k;

@@ -445,6 +445,26 @@ std::tuple<torch::Tensor, torch::Tensor> linear_split_weights(const torch::Tenso
   return {w_nk, w_kn};
 }
 
+// both weight matrices of a GraphSAGE layer in one launch -> (w_nk0, w_kn0, w_nk1, w_kn1)
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> linear_split_weights2(const torch::Tensor &W0, const torch::Tensor &W1,
+                                                                                             bool with_transposed) {
+  check_rowmajor(W0, "W0"); check_rowmajor(W1, "W1");
+  TORCH_CHECK(W0.device() == W1.device(), "both weights must be on the same device");
+  c10::cuda::CUDAGuard g(W0.device());
+  auto mk = [&](const torch::Tensor &W) {
+    const int64_t N = W.size(0), K = W.size(1);
+    return std::make_pair(torch::empty({2, N, (K + 31) / 32 * 32}, W.options()),
+                          with_transposed ? torch::empty({2, K, (N + 31) / 32 * 32}, W.options()) : torch::empty({0}, W.options()));
+  };
+  auto a = mk(W0), b = mk(W1);
+  check_rc(gnn_linear_split_weights2_f32(W0.data_ptr<float>(), ld_of(W0), W0.size(0), W0.size(1), a.first.data_ptr<float>(),
+                                         with_transposed ? a.second.data_ptr<float>() : nullptr, W1.data_ptr<float>(), ld_of(W1),
+                                         W1.size(0), W1.size(1), b.first.data_ptr<float>(),
+                                         with_transposed ? b.second.data_ptr<float>() : nullptr, cur_stream()),
+           "gnn_linear_split_weights2_f32");
+  return {a.first, a.second, b.first, b.second};
+}
+
 // out[:, 0:N] = A[rows] . W^T + bias   (out may be a column slice of a wider row-major buffer)
 void linear_tf32x3(const torch::Tensor &A, const c10::optional<torch::Tensor> &rows, const torch::Tensor &w_split, int64_t K,
                    const c10::optional<torch::Tensor> &bias, torch::Tensor out, const c10::optional<torch::Tensor> &out_rows,
@@ -473,8 +493,9 @@ void linear_tf32x3(const torch::Tensor &A, const c10::optional<torch::Tensor> &r
            "gnn_linear_tf32x3_f32");
 }
 
-// dW[N,K] = dY^T . X[rows]
-torch::Tensor linear_wgrad_tf32x3(const torch::Tensor &dY, const torch::Tensor &X, const c10::optional<torch::Tensor> &rows) {
+// dW[N,K] = dY^T . X[rows];  with_bias: also db[N] = column sums of dY (from the same pass)
+std::tuple<torch::Tensor, torch::Tensor> linear_wgrad_tf32x3(const torch::Tensor &dY, const torch::Tensor &X,
+                                                               const c10::optional<torch::Tensor> &rows, bool with_bias) {
   check_rowmajor(dY, "dY"); check_rowmajor(X, "X");
   TORCH_CHECK(dY.device() == X.device(), "dY and X must be on the same device");
   const int64_t M = dY.size(0), N = dY.size(1), K = X.size(1);
@@ -482,12 +503,13 @@ torch::Tensor linear_wgrad_tf32x3(const torch::Tensor &dY, const torch::Tensor &
   TORCH_CHECK(has_rows || X.size(0) == M, "X must have one row per row of dY");
   c10::cuda::CUDAGuard g(X.device());
   auto dW = torch::empty({N, K}, X.options());
+  auto db = with_bias ? torch::empty({N}, X.options()) : torch::empty({0}, X.options());
   const size_t wsb = gnn_linear_wgrad_workspace_bytes(M, N, K);
   auto ws = workspace(wsb, X.device());
   check_rc(gnn_linear_wgrad_tf32x3_f32(dY.data_ptr<float>(), ld_of(dY), X.data_ptr<float>(), ld_of(X), rows_ptr(rows, M, X.device()), M, N, K,
-                                       dW.data_ptr<float>(), K, ws.data_ptr(), wsb, cur_stream()),
+                                       dW.data_ptr<float>(), K, with_bias ? db.data_ptr<float>() : nullptr, ws.data_ptr(), wsb, cur_stream()),
            "gnn_linear_wgrad_tf32x3_f32");
-  return dW;
+  return {dW, db};
 }
 
 // ---- peer-mappable feature shards ---------------------------------------
@@ -557,10 +579,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("elu_rownorm_fwd", &elu_rownorm_fwd, "y, mean, rstd = rownorm(elu(x)) * scale + offset", rel());
   m.def("elu_rownorm_bwd", &elu_rownorm_bwd, "dx, dscale, doffset", rel());
   m.def("linear_split_weights", &linear_split_weights, "W[N,K] -> TF32 hi/lo planes (w_nk, w_kn)", rel());
+  m.def("linear_split_weights2", &linear_split_weights2, "two weight matrices -> TF32 planes in one launch", rel());
   m.def("linear_tf32x3", &linear_tf32x3, "out = A[rows] . W^T + bias on tcgen05 (3xTF32)", py::arg("A"), py::arg("rows"),
         py::arg("w_split"), py::arg("K"), py::arg("bias"), py::arg("out"), py::arg("out_rows") = py::none(), py::arg("accumulate") = false, rel());
   m.def("linear_wgrad_tf32x3", &linear_wgrad_tf32x3, "dW = dY^T . X[rows] on tcgen05 (3xTF32)", py::arg("dY"), py::arg("X"),
-        py::arg("rows"), rel());
+        py::arg("rows"), py::arg("with_bias") = false, rel());
   m.def("shard_alloc", &shard_alloc, "peer-mappable feature shard + IPC handle", rel());
   m.def("shard_open", &shard_open, "map a peer's shard", rel());
   m.def("host_register", &host_register, "pin+map a host table, returns the device alias", rel());

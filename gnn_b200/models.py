@@ -75,9 +75,10 @@ class TcLinear(torch.autograd.Function):
             dxr = torch.empty(dy.shape[0], x.shape[1], device=x.device, dtype=torch.float32)
             ext.linear_tf32x3(dy, None, w_kn, dy.shape[1], None, dxr)
             dx = dxr if rows is None else torch.zeros_like(x).index_add_(0, rows, dxr)
-        dW = ext.linear_wgrad_tf32x3(dy, x, rows) if ctx.needs_input_grad[2] else None
-        db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[3] else None
-        return dx, None, dW, db
+        dW = db = None
+        if ctx.needs_input_grad[2] or (ctx.has_bias and ctx.needs_input_grad[3]):
+            dW, db = ext.linear_wgrad_tf32x3(dy, x, rows, ctx.has_bias)        # db: column sums of dy from the same pass
+        return dx, None, dW, (db if ctx.has_bias else None)
 
 
 class SageLinears(torch.autograd.Function):
@@ -113,10 +114,9 @@ class SageLinears(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             dagg = torch.empty(dpre.shape[0], agg.shape[1], device=x.device, dtype=torch.float32)
             ext.linear_tf32x3(dWv, None, sWt, n, None, dagg)
-        dWB = ext.linear_wgrad_tf32x3(dB, x, rows)
-        dWW = ext.linear_wgrad_tf32x3(dWv, agg, None)
-        db = dpre.sum(0)
-        return dx, None, dagg, dWB, db[:n], dWW, db[n:]
+        dWB, dbB = ext.linear_wgrad_tf32x3(dB, x, rows, True)
+        dWW, dbW = ext.linear_wgrad_tf32x3(dWv, agg, None, True)
+        return dx, None, dagg, dWB, dbB, dWW, dbW
 
 
 class SageLayer(torch.autograd.Function):
@@ -134,8 +134,7 @@ class SageLayer(torch.autograd.Function):
         n, K = WB.shape
         agg = adj.matmul(x, padded_rows=True)
         need_dx = ctx.needs_input_grad[0]
-        sB, sBt = ext.linear_split_weights(WB.detach(), need_dx)
-        sW, sWt = ext.linear_split_weights(WW.detach(), need_dx)
+        sB, sBt, sW, sWt = ext.linear_split_weights2(WB.detach(), WW.detach(), need_dx)
         pre = torch.empty(agg.shape[0], 2 * n, device=x.device, dtype=torch.float32)
         ext.linear_tf32x3(x, rows, sB, K, bB, pre[:, :n])
         ext.linear_tf32x3(agg, None, sW, K, bW, pre[:, n:])
@@ -156,10 +155,9 @@ class SageLayer(torch.autograd.Function):
             ext.linear_tf32x3(dWv, None, sWt, n, None, dagg)
             dx = ctx.adj.matmul_t(dagg)
             ext.linear_tf32x3(dB, None, sBt, n, None, dx, rows, True)      # dx[rows] += dB . WB
-        dWB = ext.linear_wgrad_tf32x3(dB, x, rows)
-        dWW = ext.linear_wgrad_tf32x3(dWv, agg, None)
-        db = dpre.sum(0)
-        return dx, None, None, dWB, db[:n], dWW, db[n:]
+        dWB, dbB = ext.linear_wgrad_tf32x3(dB, x, rows, True)          # bias gradients: column sums of dpre from the same pass
+        dWW, dbW = ext.linear_wgrad_tf32x3(dWv, agg, None, True)
+        return dx, None, None, dWB, dbB, dWW, dbW
 
 
 def _rows_tensor(rows, device):

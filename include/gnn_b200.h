@@ -318,11 +318,16 @@ int gnn_elu_rownorm_bwd_f32(const float *dy, int64_t lddy, const float *x, int64
  *                                     linearB lands on top of the dX the SpMM backward wrote, no zero fill, no index_add.
  * gnn_linear_wgrad_tf32x3_f32: dW[n, k] = sum_m dY[m, n] * X[x_rows ? x_rows[m] : m, k]   (n < N, k < K)
  *     split over m across CTAs; partial sums are added in ascending order (fixed => bit-reproducible).
+ *     dbias (N floats or NULL): the bias gradient sum_m dY[m, n], plain fp32 sums in a fixed order, from the dY values
+ *     the operand loader holds anyway (no extra pass over dY).
  *     workspace: gnn_linear_wgrad_workspace_bytes(M, N, K) bytes.
  * ------------------------------------------------------------------------- */
 size_t gnn_linear_split_elems(int64_t rows, int64_t cols);
 int gnn_linear_split_weights_f32(const float *W, int64_t ldw, int64_t N, int64_t K, float *w_nk, float *w_kn,
                                  gnn_stream_t stream);
+/* the two weight matrices of one GraphSAGE layer (linearB, linearW: models.py:11-12) split in ONE launch */
+int gnn_linear_split_weights2_f32(const float *W0, int64_t ldw0, int64_t N0, int64_t K0, float *w_nk0, float *w_kn0, const float *W1,
+                                  int64_t ldw1, int64_t N1, int64_t K1, float *w_nk1, float *w_kn1, gnn_stream_t stream);
 int gnn_linear_tf32x3_f32(const float *A, int64_t lda, const int64_t *a_rows, int64_t M, int64_t K, const float *w_split,
                           int64_t N, const float *bias, float *C, int64_t ldc, gnn_stream_t stream);
 #define GNN_LINEAR_ACCUMULATE 1u
@@ -331,8 +336,8 @@ int gnn_linear_tf32x3_f32_ex(const float *A, int64_t lda, const int64_t *a_rows,
                              gnn_stream_t stream);
 size_t gnn_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int gnn_linear_wgrad_tf32x3_f32(const float *dY, int64_t lddy, const float *X, int64_t ldx, const int64_t *x_rows, int64_t M,
-                                int64_t N, int64_t K, float *dW, int64_t lddw, void *workspace, size_t workspace_bytes,
-                                gnn_stream_t stream);
+                                int64_t N, int64_t K, float *dW, int64_t lddw, float *dbias, void *workspace,
+                                size_t workspace_bytes, gnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * gnn_probe_row_gather_f32 - measurement aid (bench.py): the row gather of an SpMM and nothing else.

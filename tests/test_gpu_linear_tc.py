@@ -139,6 +139,20 @@ def test_split_planes_are_tf32_and_sum_back(lib):
     assert torch.equal(kn[:, :, :70], nk[:, :, :45].transpose(1, 2))
 
 
+def test_two_weight_matrices_split_in_one_launch(lib):
+    W0 = torch.randn(70, 45, device="cuda")
+    W1 = torch.randn(33, 45, device="cuda") * 5
+    a_nk, a_kn = _split(lib, W0, True)
+    b_nk, b_kn = _split(lib, W1, True)
+    outs = [torch.full_like(t, float("nan")) for t in (a_nk, a_kn, b_nk, b_kn)]
+    n0 = lib.gnn_launch_count()
+    _native.check(lib.gnn_linear_split_weights2_f32(_p(W0), 45, 70, 45, _p(outs[0]), _p(outs[1]), _p(W1), 45, 33, 45, _p(outs[2]), _p(outs[3]),
+                                                    _stream()), "split2")
+    assert lib.gnn_launch_count() - n0 == 1
+    for got, ref in zip(outs, (a_nk, a_kn, b_nk, b_kn)):
+        assert torch.equal(got, ref)
+
+
 def test_dx_is_the_same_kernel_on_the_transposed_planes(lib):
     M, n_out, k_in = 900, 512, 602
     dY = torch.randn(M, 2 * n_out, device="cuda")[:, n_out:]          # column slice of a wider gradient
@@ -161,12 +175,19 @@ def test_wgrad_matches_fp64_and_is_reproducible(lib, M, N, K, gather, off):
     wsb = lib.gnn_linear_wgrad_workspace_bytes(M, N, K)
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
 
-    def run():
+    db = torch.full((N + 3,), float("nan"), device="cuda")
+
+    def run(with_bias=False):
         dW = torch.full((N, K + 5), float("nan"), device="cuda")
-        rc = lib.gnn_linear_wgrad_tf32x3_f32(_p(dY), dY.stride(0), _p(X), X.stride(0), _p(rows), M, N, K, _p(dW), K + 5, _p(ws), wsb, _stream())
+        rc = lib.gnn_linear_wgrad_tf32x3_f32(_p(dY), dY.stride(0), _p(X), X.stride(0), _p(rows), M, N, K, _p(dW), K + 5,
+                                             _p(db) if with_bias else None, _p(ws), wsb, _stream())
         _native.check(rc, "gnn_linear_wgrad_tf32x3_f32")
         return dW
-    dW = run()
+    dW = run(with_bias=True)
+    # bias gradient = column sums of dY, from the same pass; plain fp32 sums (no TF32 involved)
+    assert torch.isnan(db[N:]).all() and not torch.isnan(db[:N]).any()
+    dbref = dY.double().sum(0)
+    assert ((db[:N].double() - dbref).norm() / dbref.norm().clamp_min(1e-30)).item() <= 1e-6
     assert torch.isnan(dW[:, K:]).all() and not torch.isnan(dW[:, :K]).any()
     xa = X if rows is None else X[rows]
     ref = dY.double().t() @ xa.double()
@@ -182,11 +203,12 @@ def test_bad_arguments(lib):
     assert lib.gnn_linear_tf32x3_f32(None, 8, None, 4, 8, _p(w), 8, None, _p(out), 8, _stream()) == -1
     assert lib.gnn_linear_tf32x3_f32(_p(x), 8, None, 4, 8, _p(w), 8, None, _p(out), 4, _stream()) == -1      # ldc < N
     assert lib.gnn_linear_tf32x3_f32(_p(x), 8, None, 0, 8, _p(w), 8, None, _p(out), 8, _stream()) == 0       # empty: no launch
-    assert lib.gnn_linear_wgrad_tf32x3_f32(_p(x), 8, _p(x), 8, None, 4, 8, 8, _p(out), 8, None, 0, _stream()) == -2
+    assert lib.gnn_linear_wgrad_tf32x3_f32(_p(x), 8, _p(x), 8, None, 4, 8, 8, _p(out), 8, None, None, 0, _stream()) == -2
     dW = torch.full((8, 8), float("nan"), device="cuda")
-    assert lib.gnn_linear_wgrad_tf32x3_f32(_p(x), 8, _p(x), 8, None, 0, 8, 8, _p(dW), 8, None, 0, _stream()) == 0
+    db = torch.full((8,), float("nan"), device="cuda")
+    assert lib.gnn_linear_wgrad_tf32x3_f32(_p(x), 8, _p(x), 8, None, 0, 8, 8, _p(dW), 8, _p(db), None, 0, _stream()) == 0
     torch.cuda.synchronize()
-    assert torch.equal(dW, torch.zeros_like(dW)), "an empty reduction is a zero gradient"
+    assert torch.equal(dW, torch.zeros_like(dW)) and torch.equal(db, torch.zeros_like(db)), "an empty reduction is a zero gradient"
 
 
 def test_sage_linears_autograd_matches_fp64():

@@ -62,7 +62,7 @@ def run_tn(M, N, K, gather=False, seed=0, lddy_extra=0):
     dyfull = torch.randn(M, N + lddy_extra, generator=g).to(dev)
     dY = dyfull[:, lddy_extra:]
     rows = torch.randperm(n_in, generator=g)[:M].to(dev) if gather else None
-    dW = ext.linear_wgrad_tf32x3(dY, X, rows)
+    dW, _ = ext.linear_wgrad_tf32x3(dY, X, rows)
     torch.cuda.synchronize()
     xa = X if rows is None else X[rows]
     ref = dY.double().t() @ xa.double()
@@ -81,7 +81,7 @@ def tn_decode():
     for (m0, n0) in [(0, 0), (0, 1), (0, 4), (0, 32), (1, 0), (7, 5), (3, 100)]:
         dY = torch.zeros(M, N, device=dev); dY[m0, n0] = 1.0
         X = torch.zeros(M, K, device=dev); X[m0, :] = torch.arange(1, K + 1, device=dev).float()
-        dW = ext.linear_wgrad_tf32x3(dY, X, None)
+        dW, _ = ext.linear_wgrad_tf32x3(dY, X, None)
         torch.cuda.synchronize()
         nz = dW.nonzero()
         head = [(int(a), int(b), float(dW[a, b])) for a, b in nz[:6].tolist()]
@@ -90,14 +90,14 @@ def tn_decode():
     for (m0, k0) in [(0, 0), (0, 1), (0, 4), (0, 32), (1, 0), (7, 5), (3, 200)]:
         X = torch.zeros(M, K, device=dev); X[m0, k0] = 1.0
         dY = torch.zeros(M, N, device=dev); dY[m0, :] = torch.arange(1, N + 1, device=dev).float()
-        dW = ext.linear_wgrad_tf32x3(dY, X, None)
+        dW, _ = ext.linear_wgrad_tf32x3(dY, X, None)
         torch.cuda.synchronize()
         nz = dW.nonzero()
         head = [(int(a), int(b), float(dW[a, b])) for a, b in nz[:6].tolist()]
         cols = sorted(set(nz[:, 1].tolist()))[:8]
         print(f"X one-hot (m={m0}, k={k0}): {len(nz)} nonzeros, max {dW.abs().max().item():.3g}, cols {cols}, head {head}", flush=True)
     dY = torch.ones(M, N, device=dev); X = torch.ones(M, K, device=dev)
-    dW = ext.linear_wgrad_tf32x3(dY, X, None)
+    dW, _ = ext.linear_wgrad_tf32x3(dY, X, None)
     print("all-ones: min", dW.min().item(), "max", dW.max().item(), "expected", M, flush=True)
 
 
