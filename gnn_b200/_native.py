@@ -52,6 +52,7 @@ def cabi() -> ctypes.CDLL:
                 "gnn_launch_count": (i64, []),
                 "gnn_set_corunner_ctas": (ctypes.c_int, [ctypes.c_int]),
                 "gnn_host_gather_ctas": (ctypes.c_int, []),
+                "gnn_set_blocking_sync": (ctypes.c_int, [ctypes.c_int]),
                 "gnn_build_adj": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, vp, i64, i64, i64, vp, vp, vp, vp, vp]),
                 "gnn_coo_to_csr": (ctypes.c_int, [vp, i64, i64, vp, vp, vp]),
                 "gnn_csr_spmm_workspace_bytes": (sz, [i64, i64, i64]),

@@ -1692,6 +1692,14 @@ int gnn_shard_free(void *dev_ptr) {
   return 0;
 }
 
+int gnn_set_blocking_sync(int on) {
+  // cudaDeviceScheduleBlockingSync: threads waiting in a synchronise call sleep instead of spinning.  The sampler threads of
+  // a rank wait on three small device-to-host reads per layer; with fewer host cores than threads their spinning takes
+  // the cores the other threads need (8 ranks x 5 threads on a 32-core host).
+  GNN_CUDA(cudaSetDeviceFlags(on ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto));
+  return 0;
+}
+
 int gnn_host_register(void *host_ptr, size_t bytes, void **dev_alias) {
   if (!host_ptr || !dev_alias || bytes == 0) return GNN_E_BADARG;
   GNN_CUDA(cudaHostRegister(host_ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
@@ -1920,7 +1928,7 @@ int gnn_legacy_choice_f64(uint32_t *mt_state, const double *p, int64_t n, int64_
   if (n > INT32_MAX) return GNN_E_RANGE;
   // scratch lives per thread and only grows: fresh multi-megabyte vectors per call cost more in page faults than the draw
   static thread_local std::vector<double> pw, raw, x, coarse;
-  static thread_local std::vector<int32_t> stamp;
+  static thread_local std::vector<int32_t> stamp, hint;
   static thread_local std::vector<int64_t> cand;
   const int64_t nc = (n + 63) / 64;
   pw.assign(p, p + n);
@@ -1948,18 +1956,37 @@ int gnn_legacy_choice_f64(uint32_t *mt_state, const double *p, int64_t n, int64_
     for (int64_t i = lo; i < n; ++i) { run += pw[(size_t)i]; raw[(size_t)i] = run; }
     const double last = raw[(size_t)n - 1];
     if (!(last > 0.0)) return GNN_E_BADARG;                                   // fewer non-zero entries than `size` (numpy raises)
-    for (int64_t c = std::max<int64_t>(lo / 64, 0); c < nc; ++c) coarse[(size_t)c] = raw[(size_t)std::min<int64_t>(c * 64 + 63, n - 1)];
+    // searchsorted(cdf / cdf[-1], x, side='right') = number of entries whose quotient raw[i] / last (the IEEE division
+    // numpy applies to the whole array; rounding keeps it monotone) is <= x.  Located without dividing n numbers:
+    // a division-free approximate position for x * last, then the exact quotient test on the neighbours decides.
+    // Many draws (the first rounds): a 65,536-bucket table of positions built in one merge pass over the running sums,
+    // ~3 entries to scan per draw.  Few draws: a two-level binary search (coarse = every 64th sum, L1-resident).
+    constexpr int kBuckets = 1 << 16;
+    const bool use_table = k >= 1024 && n >= 4096;
+    if (use_table) {
+      if ((int64_t)hint.size() < kBuckets + 1) hint.resize(kBuckets + 1);
+      int64_t j = 0;
+      for (int b = 0; b <= kBuckets; ++b) {
+        const double thr = ((double)b / (double)kBuckets) * last;
+        while (j < n && raw[(size_t)j] <= thr) ++j;
+        hint[(size_t)b] = (int32_t)j;                  // entries with running sum <= b/65536 of the total
+      }
+    } else {
+      for (int64_t c = 0; c < nc; ++c) coarse[(size_t)c] = raw[(size_t)std::min<int64_t>(c * 64 + 63, n - 1)];
+    }
     ++round;
     int64_t got = 0;
     for (int64_t i = 0; i < k; ++i) {
-      // searchsorted(cdf / cdf[-1], x, side='right') = number of entries whose quotient raw[i] / last (the IEEE division
-      // numpy applies to the whole array; rounding keeps it monotone) is <= x.  Located without dividing n numbers: a
-      // division-free two-level search for x * last (coarse = every 64th running sum, L1-resident), then the exact
-      // quotient test on the neighbours decides.
       const double xi = x[(size_t)i], t = xi * last;
-      const int64_t cb = upper_count(coarse.data(), nc, t);                   // blocks whose LAST element is <= t
-      const int64_t b0 = cb * 64, bl = std::min<int64_t>(64, n - b0);
-      int64_t l = bl > 0 ? b0 + upper_count(raw.data() + b0, bl, t) : n;
+      int64_t l;
+      if (use_table) {
+        l = hint[(size_t)(xi * (double)kBuckets)];
+        while (l < n && raw[(size_t)l] <= t) ++l;
+      } else {
+        const int64_t cb = upper_count(coarse.data(), nc, t);                 // blocks whose LAST element is <= t
+        const int64_t b0 = cb * 64, bl = std::min<int64_t>(64, n - b0);
+        l = bl > 0 ? b0 + upper_count(raw.data() + b0, bl, t) : n;
+      }
       while (l < n && raw[(size_t)l] / last <= xi) ++l;
       while (l > 0 && raw[(size_t)l - 1] / last > xi) --l;
       if (stamp[(size_t)l] != round) {            // np.unique(return_index=True) + sort: first occurrence, draw order

@@ -595,5 +595,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     return prev;
   });
   m.def("host_gather_ctas", []() { return gnn_host_gather_ctas(); });
+  m.def("set_blocking_sync", [](bool on) { check_rc(gnn_set_blocking_sync(on ? 1 : 0), "gnn_set_blocking_sync"); });
   m.def("abi_version", []() { return gnn_abi_version(); });
 }

@@ -55,6 +55,11 @@ int64_t gnn_launch_count(void);
 int gnn_set_corunner_ctas(int ctas);
 int gnn_host_gather_ctas(void);
 
+/* Host threads that wait in a stream / event synchronise of the CURRENT device sleep (on != 0, cudaDeviceScheduleBlockingSync)
+ * or spin (0, the CUDA default).  For processes that run more waiting threads than they have host cores: the reference's
+ * sampler pool (main.py:77, --pool_num threads per GPU) next to the trainer thread. */
+int gnn_set_blocking_sync(int on);
+
 /* ---------------------------------------------------------------------------
  * gnn_build_adj - sampled CSR + LADIES weights -> COO (API) + CSR (kernels).
  *
