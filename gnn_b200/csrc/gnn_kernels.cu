@@ -1923,22 +1923,28 @@ static inline int64_t upper_count(const double *a, int64_t len, double t) {
   return b - a;
 }
 
-int gnn_legacy_choice_f64(uint32_t *mt_state, const double *p, int64_t n, int64_t size, int64_t *found) {
-  if (!mt_state || !p || !found || n <= 0 || size < 0 || size > n) return GNN_E_BADARG;
-  if (n > INT32_MAX) return GNN_E_RANGE;
+// The draw itself.  `pw` is the caller's WORKING copy of the probabilities: the entries drawn are zeroed in it (what numpy
+// does to its own copy of p), nothing else is written.
+static int legacy_choice_core(uint32_t *mt_state, double *pw, int64_t n, int64_t size, int64_t *found) {
   // scratch lives per thread and only grows: fresh multi-megabyte vectors per call cost more in page faults than the draw
-  static thread_local std::vector<double> pw, raw, x, coarse;
-  static thread_local std::vector<int32_t> stamp, hint;
+  static thread_local std::vector<double> raw, x, coarse;
+  static thread_local std::vector<int32_t> stamp, ends;
   static thread_local std::vector<int64_t> cand;
+  static thread_local int32_t epoch = 0;          // stamp[l] == epoch: position l was already drawn in the current round
   const int64_t nc = (n + 63) / 64;
-  pw.assign(p, p + n);
   if ((int64_t)raw.size() < n) raw.resize((size_t)n);
   if ((int64_t)x.size() < size + 1) x.resize((size_t)size + 1);
   if ((int64_t)cand.size() < size + 1) cand.resize((size_t)size + 1);
   if ((int64_t)coarse.size() < nc) coarse.resize((size_t)nc);
-  stamp.assign((size_t)n + 1, 0);
+  if ((int64_t)stamp.size() < n + 1) stamp.resize((size_t)n + 1, 0);
+  if (epoch > INT32_MAX - (1 << 20)) {            // rounds are numbered across calls so that the marks need no clearing
+    std::fill(stamp.begin(), stamp.end(), 0);
+    epoch = 0;
+  }
+  constexpr int kBuckets = 1 << 16;
   int64_t n_uniq = 0, zeroed = 0;
-  int32_t round = 0;
+  int round = 0;
+  double mass = 1.0;                              // estimate of cdf[-1] of the coming round (exactness does not matter)
   while (n_uniq < size) {
     const int64_t k = size - n_uniq;
     for (int64_t i = 0; i < k; ++i) {
@@ -1949,39 +1955,58 @@ int gnn_legacy_choice_f64(uint32_t *mt_state, const double *p, int64_t n, int64_
     // first entry zeroed in this round are the ones of the previous round, bit for bit - restart from there
     int64_t lo = round == 0 ? 0 : n;
     for (; zeroed < n_uniq; ++zeroed) {
-      pw[(size_t)found[zeroed]] = 0.0;
-      lo = std::min(lo, found[zeroed]);
+      const int64_t f = found[zeroed];
+      mass -= pw[(size_t)f];
+      pw[(size_t)f] = 0.0;
+      lo = std::min(lo, f);
     }
-    double run = lo > 0 ? raw[(size_t)lo - 1] : 0.0;
-    for (int64_t i = lo; i < n; ++i) { run += pw[(size_t)i]; raw[(size_t)i] = run; }
-    const double last = raw[(size_t)n - 1];
-    if (!(last > 0.0)) return GNN_E_BADARG;                                   // fewer non-zero entries than `size` (numpy raises)
     // searchsorted(cdf / cdf[-1], x, side='right') = number of entries whose quotient raw[i] / last (the IEEE division
     // numpy applies to the whole array; rounding keeps it monotone) is <= x.  Located without dividing n numbers:
     // a division-free approximate position for x * last, then the exact quotient test on the neighbours decides.
-    // Many draws (the first rounds): a 65,536-bucket table of positions built in one merge pass over the running sums,
-    // ~3 entries to scan per draw.  Few draws: a two-level binary search (coarse = every 64th sum, L1-resident).
-    constexpr int kBuckets = 1 << 16;
-    const bool use_table = k >= 1024 && n >= 4096;
+    // Many draws (the first rounds): a 65,536-bucket table of positions; bucket = floor(running sum * scale), the same
+    // monotone map for the sums and for x * last, filled by the cumsum loop itself (the loop is bound by the latency of
+    // its dependent additions, the bucket arithmetic rides along).  Few draws: a two-level binary search (coarse = every
+    // 64th sum, L1-resident).
+    const bool use_table = k >= 1024 && n >= 4096 && mass > 0.0;
+    const double scale = use_table ? (double)kBuckets / mass : 0.0;
+    double run = lo > 0 ? raw[(size_t)lo - 1] : 0.0;
     if (use_table) {
-      if ((int64_t)hint.size() < kBuckets + 1) hint.resize(kBuckets + 1);
-      int64_t j = 0;
-      for (int b = 0; b <= kBuckets; ++b) {
-        const double thr = ((double)b / (double)kBuckets) * last;
-        while (j < n && raw[(size_t)j] <= thr) ++j;
-        hint[(size_t)b] = (int32_t)j;                  // entries with running sum <= b/65536 of the total
+      if ((int64_t)ends.size() < kBuckets + 1) ends.resize(kBuckets + 1);
+      std::fill(ends.begin(), ends.begin() + kBuckets + 1, 0);
+      int32_t *e = ends.data() + 1;               // e[b] = 1 + the last position whose sum falls into bucket b
+      for (int64_t i = 0; i < lo; ++i) {
+        const double v = raw[(size_t)i] * scale;
+        e[(v >= 0.0 && v < (double)kBuckets) ? (int)v : kBuckets - 1] = (int32_t)i + 1;
       }
+      for (int64_t i = lo; i < n; ++i) {
+        run += pw[(size_t)i];
+        raw[(size_t)i] = run;
+        const double v = run * scale;
+        e[(v >= 0.0 && v < (double)kBuckets) ? (int)v : kBuckets - 1] = (int32_t)i + 1;
+      }
+      int32_t m = 0;                              // ends[b] := positions in buckets < b (running maximum; ends[0] = 0)
+      for (int b = 1; b <= kBuckets; ++b) { m = std::max(m, ends[(size_t)b]); ends[(size_t)b] = m; }
     } else {
+      for (int64_t i = lo; i < n; ++i) { run += pw[(size_t)i]; raw[(size_t)i] = run; }
       for (int64_t c = 0; c < nc; ++c) coarse[(size_t)c] = raw[(size_t)std::min<int64_t>(c * 64 + 63, n - 1)];
     }
+    const double last = raw[(size_t)n - 1];
+    if (!(last > 0.0)) return GNN_E_BADARG;                                   // fewer non-zero entries than `size` (numpy raises)
+    mass = last;
     ++round;
+    ++epoch;
     int64_t got = 0;
     for (int64_t i = 0; i < k; ++i) {
       const double xi = x[(size_t)i], t = xi * last;
       int64_t l;
       if (use_table) {
-        l = hint[(size_t)(xi * (double)kBuckets)];
-        while (l < n && raw[(size_t)l] <= t) ++l;
+        const double v = t * scale;
+        l = ends[(size_t)((v >= 0.0 && v < (double)kBuckets) ? (int)v : kBuckets - 1)];   // every sum before l is <= t
+        int steps = 0;
+        while (l < n && raw[(size_t)l] <= t) {
+          ++l;
+          if (++steps == 48) { l += upper_count(raw.data() + l, n - l, t); break; }        // a crowded bucket
+        }
       } else {
         const int64_t cb = upper_count(coarse.data(), nc, t);                 // blocks whose LAST element is <= t
         const int64_t b0 = cb * 64, bl = std::min<int64_t>(64, n - b0);
@@ -1989,8 +2014,8 @@ int gnn_legacy_choice_f64(uint32_t *mt_state, const double *p, int64_t n, int64_
       }
       while (l < n && raw[(size_t)l] / last <= xi) ++l;
       while (l > 0 && raw[(size_t)l - 1] / last > xi) --l;
-      if (stamp[(size_t)l] != round) {            // np.unique(return_index=True) + sort: first occurrence, draw order
-        stamp[(size_t)l] = round;
+      if (stamp[(size_t)l] != epoch) {            // np.unique(return_index=True) + sort: first occurrence, draw order
+        stamp[(size_t)l] = epoch;
         cand[(size_t)got++] = l;
       }
     }
@@ -1998,6 +2023,14 @@ int gnn_legacy_choice_f64(uint32_t *mt_state, const double *p, int64_t n, int64_
     n_uniq += got;
   }
   return 0;
+}
+
+int gnn_legacy_choice_f64(uint32_t *mt_state, const double *p, int64_t n, int64_t size, int64_t *found) {
+  if (!mt_state || !p || !found || n <= 0 || size < 0 || size > n) return GNN_E_BADARG;
+  if (n > INT32_MAX) return GNN_E_RANGE;
+  static thread_local std::vector<double> pw;
+  pw.assign(p, p + n);
+  return legacy_choice_core(mt_state, pw.data(), n, size, found);
 }
 
 // The whole host part of one LADIES layer (reference sampler.py:117-143) in one GIL-free call: probabilities from the
@@ -2011,59 +2044,145 @@ int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32
   if (!mt_state || !nz || !counts || n_nz <= 0 || !previous_nodes || n_prev < 0 || samp_num < 0 || !after_nodes || !normfact ||
       !sampled || !n_sampled)
     return GNN_E_BADARG;
-  // pi = column counts (sampler.py:117); locality sampling scales the counts of the nodes cached on this GPU and the
-  // reference stores the scaled values back into an int64 array (:119-121): truncation
+  if (n_nz > INT32_MAX) return GNN_E_RANGE;
   static thread_local std::vector<int64_t> pi, found, all, prev;
   static thread_local std::vector<double> p;
-  pi.resize((size_t)n_nz);
-  for (int64_t i = 0; i < n_nz; ++i) pi[(size_t)i] = counts[i];
-  if (scale_factor > 1.0 && skew_nodes && n_skew > 0) {
+  static thread_local std::vector<uint64_t> bits;
+  static thread_local std::vector<int32_t> rank0, pos_of;
+  // pi = column counts (sampler.py:117); locality sampling scales the counts of the nodes cached on this GPU and the
+  // reference stores the scaled values back into an int64 array (:119-121): truncation.  Without scaling the int32 counts
+  // are read where they lie.
+  const bool scaled = scale_factor > 1.0 && skew_nodes && n_skew > 0;
+  int64_t total = 0, n_pos = 0;
+  if (scaled) {
+    pi.resize((size_t)n_nz);
     int64_t j = 0;
     for (int64_t i = 0; i < n_nz; ++i) {                                     // both ascending: merge
+      int64_t v = counts[i];
       while (j < n_skew && skew_nodes[j] < nz[i]) ++j;
-      if (j < n_skew && skew_nodes[j] == nz[i]) pi[(size_t)i] = (int64_t)((double)pi[(size_t)i] * scale_factor);
+      if (j < n_skew && skew_nodes[j] == nz[i]) v = (int64_t)((double)v * scale_factor);
+      pi[(size_t)i] = v;
+      total += v;
+      n_pos += v > 0;
     }
+  } else {
+    for (int64_t i = 0; i < n_nz; ++i) { total += counts[i]; n_pos += counts[i] > 0; }
   }
-  int64_t total = 0;
-  for (int64_t i = 0; i < n_nz; ++i) total += pi[(size_t)i];
   if (total <= 0) return GNN_E_BADARG;
+  const double dtotal = (double)total;
+  auto pi_at = [&](int64_t i) -> double { return scaled ? (double)pi[(size_t)i] : (double)counts[i]; };
   p.resize((size_t)n_nz);
-  for (int64_t i = 0; i < n_nz; ++i) p[(size_t)i] = (double)pi[(size_t)i] / (double)total;          // p = pi / np.sum(pi)  (:124)
-  int64_t n_pos = 0;
-  for (int64_t i = 0; i < n_nz; ++i) n_pos += pi[(size_t)i] > 0;
+  if (scaled) for (int64_t i = 0; i < n_nz; ++i) p[(size_t)i] = (double)pi[(size_t)i] / dtotal;    // p = pi / np.sum(pi)  (:124)
+  else        for (int64_t i = 0; i < n_nz; ++i) p[(size_t)i] = (double)counts[i] / dtotal;
   const int64_t s_num = std::min(n_pos, samp_num);                                                 // :126
   found.resize((size_t)std::max<int64_t>(s_num, 1));
-  const int rc = gnn_legacy_choice_f64(mt_state, p.data(), n_nz, s_num, found.data());              // :128
+  // the draw zeroes the entries it takes in p; p[after_nodes] below is re-derived by the same division
+  const int rc = legacy_choice_core(mt_state, p.data(), n_nz, s_num, found.data());                 // :128
   if (rc != 0) return rc;
-  // after_nodes = np.unique(np.concatenate((after_nodes, previous_nodes)))  (:131).  previous_nodes is the sorted-unique
-  // after_nodes of the layer above (only the batch itself arrives unsorted): sort the drawn nodes, merge, drop repeats
-  prev.assign(previous_nodes, previous_nodes + n_prev);
-  if (!std::is_sorted(prev.begin(), prev.end())) std::sort(prev.begin(), prev.end());
-  const int64_t n_up = std::unique(prev.begin(), prev.end()) - prev.begin();
-  for (int64_t i = 0; i < s_num; ++i) found[(size_t)i] = nz[found[(size_t)i]];
-  std::sort(found.begin(), found.begin() + s_num);
-  all.resize((size_t)(s_num + n_up));
-  std::merge(found.begin(), found.begin() + s_num, prev.begin(), prev.begin() + n_up, all.begin());
-  const int64_t n_after = std::unique(all.begin(), all.end()) - all.begin();
-  // normfact = 1 / np.clip(s_num * p[after_nodes], 1e-10, 1).astype(np.float32)   (:137); p is zero off the support
-  int64_t j = 0;
-  for (int64_t i = 0; i < n_after; ++i) {
-    const int64_t node = all[(size_t)i];
-    while (j < n_nz && nz[j] < node) ++j;
-    const double pa = (j < n_nz && nz[j] == node) ? p[(size_t)j] : 0.0;
-    double v = (double)s_num * pa;
-    v = v < 1e-10 ? 1e-10 : (v > 1.0 ? 1.0 : v);
-    after_nodes[i] = node;
-    normfact[i] = 1.0f / (float)v;
+  int64_t max_id = nz[n_nz - 1];
+  bool prev_sorted = true;
+  for (int64_t i = 0; i < n_prev; ++i) {
+    if (previous_nodes[i] < 0) return GNN_E_BADARG;
+    max_id = std::max(max_id, previous_nodes[i]);
+    prev_sorted = prev_sorted && (i == 0 || previous_nodes[i - 1] < previous_nodes[i]);            // strictly: distinct too
   }
-  // sampled_nodes = np.where(np.in1d(after_nodes, previous_nodes))[0]   (:143): ascending positions of the distinct previous nodes
-  int64_t k = 0, ns = 0;
-  for (int64_t i = 0; i < n_up; ++i) {
-    while (k < n_after && all[(size_t)k] < prev[(size_t)i]) ++k;
-    if (k < n_after && all[(size_t)k] == prev[(size_t)i]) sampled[ns++] = k;
+  if (nz[0] < 0) return GNN_E_BADARG;
+  const int64_t range = max_id + 1;
+  int64_t n_after = 0, ns = 0;
+  if (range <= 16 * (n_nz + n_prev) + 65536 && range < INT32_MAX) {
+    // ids are dense enough for tables over the id range (the Reddit/products shapes: the support is most of the graph):
+    // after_nodes = np.unique(drawn ++ previous_nodes) (:131) is a bitmap scan, p[after_nodes] a table lookup and
+    // sampled_nodes (:143) a popcount rank - no sorting, no merging
+    const int64_t words = (range + 63) >> 6;
+    bits.assign((size_t)words, 0);
+    for (int64_t i = 0; i < s_num; ++i) { const int64_t v = nz[found[(size_t)i]]; bits[(size_t)(v >> 6)] |= 1ull << (v & 63); }
+    for (int64_t i = 0; i < n_prev; ++i) { const int64_t v = previous_nodes[i]; bits[(size_t)(v >> 6)] |= 1ull << (v & 63); }
+    // position of a node inside the support: arithmetic when the support is one contiguous id range, else a table
+    // (written for every support entry, validated on read: stale contents are harmless)
+    const bool contiguous = nz[n_nz - 1] - nz[0] == n_nz - 1;
+    if (!contiguous) {
+      if ((int64_t)pos_of.size() < range) pos_of.resize((size_t)range);
+      for (int64_t j = 0; j < n_nz; ++j) pos_of[(size_t)nz[j]] = (int32_t)j;
+    }
+    rank0.resize((size_t)words + 1);
+    for (int64_t w = 0; w < words; ++w) {
+      rank0[(size_t)w] = (int32_t)n_after;
+      uint64_t m = bits[(size_t)w];
+      while (m) {
+        const int64_t node = (w << 6) + __builtin_ctzll(m);
+        m &= m - 1;
+        int64_t j = contiguous ? node - nz[0] : (int64_t)pos_of[(size_t)node];
+        const bool in_support = j >= 0 && j < n_nz && nz[j] == node;
+        // normfact = 1 / np.clip(s_num * p[after_nodes], 1e-10, 1).astype(np.float32)   (:137); p is zero off the support
+        double v = (double)s_num * (in_support ? pi_at(j) / dtotal : 0.0);
+        v = v < 1e-10 ? 1e-10 : (v > 1.0 ? 1.0 : v);
+        after_nodes[n_after] = node;
+        normfact[n_after] = 1.0f / (float)v;
+        ++n_after;
+      }
+    }
+    // sampled_nodes = np.where(np.in1d(after_nodes, previous_nodes))[0]   (:143): ascending positions of the distinct previous nodes
+    for (int64_t i = 0; i < n_prev; ++i) {
+      const int64_t v = previous_nodes[i];
+      sampled[i] = rank0[(size_t)(v >> 6)] + __builtin_popcountll(bits[(size_t)(v >> 6)] & ((1ull << (v & 63)) - 1));
+    }
+    ns = n_prev;
+    if (!prev_sorted) {                                                       // the batch itself: any order, maybe repeats
+      std::sort(sampled, sampled + n_prev);
+      ns = std::unique(sampled, sampled + n_prev) - sampled;
+    }
+  } else {
+    // sparse ids (papers100M-shaped: a support of ~1e5-1e6 nodes out of 1e8): sort the drawn nodes, merge, drop repeats
+    prev.assign(previous_nodes, previous_nodes + n_prev);
+    if (!prev_sorted) std::sort(prev.begin(), prev.end());
+    const int64_t n_up = std::unique(prev.begin(), prev.end()) - prev.begin();
+    for (int64_t i = 0; i < s_num; ++i) found[(size_t)i] = nz[found[(size_t)i]];
+    std::sort(found.begin(), found.begin() + s_num);
+    all.resize((size_t)(s_num + n_up));
+    std::merge(found.begin(), found.begin() + s_num, prev.begin(), prev.begin() + n_up, all.begin());
+    n_after = std::unique(all.begin(), all.end()) - all.begin();
+    int64_t j = 0;
+    for (int64_t i = 0; i < n_after; ++i) {
+      const int64_t node = all[(size_t)i];
+      while (j < n_nz && nz[j] < node) ++j;
+      const double pa = (j < n_nz && nz[j] == node) ? pi_at(j) / dtotal : 0.0;
+      double v = (double)s_num * pa;                                           // :137
+      v = v < 1e-10 ? 1e-10 : (v > 1.0 ? 1.0 : v);
+      after_nodes[i] = node;
+      normfact[i] = 1.0f / (float)v;
+    }
+    int64_t k = 0;                                                             // :143
+    for (int64_t i = 0; i < n_up; ++i) {
+      while (k < n_after && all[(size_t)k] < prev[(size_t)i]) ++k;
+      if (k < n_after && all[(size_t)k] == prev[(size_t)i]) sampled[ns++] = k;
+    }
   }
   *n_sampled = ns;
   return n_after;
+}
+
+// Same, fed with the device sampler's whole count array (one D2H copy of num_nodes int32 into pinned memory instead of
+// a device-side compaction with its two extra stream synchronisations): the support is compacted here, in one pass.
+int64_t gnn_ladies_layer_host_dense(uint32_t *mt_state, const int32_t *counts_dense, int64_t num_nodes, const int64_t *skew_nodes,
+                                    int64_t n_skew, double scale_factor, const int64_t *previous_nodes, int64_t n_prev,
+                                    int64_t samp_num, int64_t *after_nodes, float *normfact, int64_t *sampled, int64_t *n_sampled,
+                                    int64_t *n_support) {
+  if (!counts_dense || num_nodes <= 0) return GNN_E_BADARG;
+  if (num_nodes > INT32_MAX) return GNN_E_RANGE;
+  static thread_local std::vector<int64_t> nzv;
+  static thread_local std::vector<int32_t> cntv;
+  if ((int64_t)nzv.size() < num_nodes + 1) { nzv.resize((size_t)num_nodes + 1); cntv.resize((size_t)num_nodes + 1); }
+  int64_t m = 0;
+  for (int64_t i = 0; i < num_nodes; ++i) {                                   // branch-free: write always, advance on non-zero
+    const int32_t c = counts_dense[i];
+    nzv[(size_t)m] = i;
+    cntv[(size_t)m] = c;
+    m += c != 0;
+  }
+  if (n_support) *n_support = m;
+  if (m == 0) return GNN_E_BADARG;
+  return gnn_ladies_layer_host(mt_state, nzv.data(), cntv.data(), m, skew_nodes, n_skew, scale_factor, previous_nodes, n_prev,
+                               samp_num, after_nodes, normfact, sampled, n_sampled);
 }
 
 }  // extern "C"

@@ -10,8 +10,11 @@ own expression).  What moves to the GPU are the passes that cost the reference ~
     adj = U[:, after_nodes]                    (sampler.py:133)   gnn_lookup_set + gnn_column_slice_count / _fill
     create_coo_tensor(...)                     (sampler.py:139)   gnn_build_adj (unchanged)
 
-Three small D2H reads per layer (slice size, column counts, kept count) synchronise the stream; everything else is
-asynchronous.  The graph structure lives on the device (int64 indptr, int32 indices).
+Two D2H reads per layer synchronise the stream (the column counts - the whole array into pinned memory when the graph
+has at most DENSE_COUNTS_MAX nodes, else a device-side compaction - and the kept count); everything else is
+asynchronous: host arrays go up through pinned staging (a pageable source makes cudaMemcpyAsync synchronise the stream
+before it copies), and the slice size is computed from the host copy of indptr.  The graph structure lives on the
+device (int64 indptr, int32 indices).
 """
 from __future__ import annotations
 
@@ -44,11 +47,28 @@ class DeviceMinibatch:
     batch_nodes: np.ndarray
 
 
+DENSE_COUNTS_MAX = 1 << 22      # up to this many nodes the whole count array crosses PCIe (16 MiB) instead of being compacted
+
+
+def h2d(arr: np.ndarray, device) -> torch.Tensor:
+    """Host array -> device without synchronising the stream: through a pinned block of torch's caching host allocator
+    (which keeps the block alive until the copy has run)."""
+    t = torch.from_numpy(arr)
+    if t.numel() == 0:
+        return torch.empty(t.shape, dtype=t.dtype, device=device)
+    return t.pin_memory().to(device, non_blocking=True)
+
+
 class SamplerScratch:
-    """Per-caller scratch tables (one per sampler thread): column lookup (-1 between uses) and column counts."""
+    """Per-caller scratch tables (one per sampler thread): column lookup (-1 between uses), column counts and, for
+    graphs of at most DENSE_COUNTS_MAX nodes, the pinned host mirror of the counts."""
     def __init__(self, num_nodes: int, device):
         self.lookup = torch.full((num_nodes,), -1, dtype=torch.int32, device=device)
         self.counts = torch.zeros(num_nodes, dtype=torch.int32, device=device)
+        self.counts_host = None
+        if num_nodes <= DENSE_COUNTS_MAX:
+            self.counts_host = torch.zeros(num_nodes, dtype=torch.int32).pin_memory()
+            self.counts_np = self.counts_host.numpy()
 
 
 class DeviceGraph:
@@ -56,6 +76,7 @@ class DeviceGraph:
     def __init__(self, indptr: np.ndarray, indices: np.ndarray, device):
         self.device = torch.device(device)
         self.num_nodes = int(indptr.size - 1)
+        self.indptr_host = np.asarray(indptr)      # the caller's array (not copied): slice sizes without a device read
         self.indptr = torch.from_numpy(np.ascontiguousarray(indptr, dtype=np.int64)).to(self.device)
         self.indices = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int32)).to(self.device)
         self._default_scratch = None
@@ -178,6 +199,29 @@ def host_layer_native(mt_state, nz, cnt, skew, scale_factor, previous_nodes, sam
     return after[:n_after], normfact[:n_after], sampled[:n_sampled.value], s_num
 
 
+def host_layer_native_dense(mt_state, counts_dense, skew, scale_factor, previous_nodes, samp_num):
+    """gnn_ladies_layer_host_dense: the same call on the whole count array (``counts_dense[v]`` for every node v)."""
+    import ctypes
+    lib = _native.cabi()
+    cnt = np.ascontiguousarray(counts_dense, dtype=np.int32)
+    prev = np.ascontiguousarray(previous_nodes, dtype=np.int64)
+    cap = min(int(cnt.size), int(samp_num)) + prev.size
+    after = np.empty(cap, dtype=np.int64)
+    normfact = np.empty(cap, dtype=np.float32)
+    sampled = np.empty(prev.size, dtype=np.int64)
+    n_sampled, n_support = ctypes.c_int64(0), ctypes.c_int64(0)
+    vp = ctypes.c_void_p
+    use_skew = skew is not None and scale_factor > 1
+    n_after = lib.gnn_ladies_layer_host_dense(vp(mt_state.ctypes.data), vp(cnt.ctypes.data), cnt.size,
+                                              vp(skew.ctypes.data) if use_skew else None, skew.size if use_skew else 0,
+                                              float(scale_factor), vp(prev.ctypes.data), prev.size, int(samp_num),
+                                              vp(after.ctypes.data), vp(normfact.ctypes.data), vp(sampled.ctypes.data),
+                                              ctypes.byref(n_sampled), ctypes.byref(n_support))
+    if n_after < 0:
+        _native.check(int(n_after), "gnn_ladies_layer_host_dense")
+    return after[:n_after], normfact[:n_after], sampled[:n_sampled.value], min(int(n_support.value), int(samp_num))
+
+
 def host_layer_numpy(rs, nz, cnt, skew, scale_factor, previous_nodes, samp_num):
     """The same host part in the reference's numpy expressions (sampler.py:117-143 restricted to the support of p):
     the readable restatement, and what the tests compare the native call against."""
@@ -221,25 +265,33 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
             adjs.append(None)
             sampled.append([])
             continue
-        prev_dev = torch.from_numpy(np.ascontiguousarray(previous_nodes, dtype=np.int64)).to(dev)
+        prev_np = np.ascontiguousarray(previous_nodes, dtype=np.int64)
+        prev_dev = h2d(prev_np, dev)
         fullrowptr = ext.row_slice_count(graph.indptr, prev_dev)                           # :113-114
-        total = int(fullrowptr[-1].item())
+        total = int((graph.indptr_host[prev_np + 1] - graph.indptr_host[prev_np]).sum())    # == fullrowptr[-1], no device read
         scratch.counts.zero_()
         ucols = ext.row_slice_fill(graph.indptr, graph.indices, prev_dev, fullrowptr, total, scratch.counts)
-        # only the columns that occur at all carry probability: compact them on the device and bring back
-        # (index, count) pairs instead of an N-long array (N = 111 M on the papers100M shape)
-        nz_dev = torch.nonzero(scratch.counts).flatten()
-        nz = nz_dev.cpu().numpy()
-        cnt = scratch.counts[nz_dev].cpu().numpy()                                          # :117 on the support (int32)
         skew = None
         if scale_factor > 1:                                                                # :119-121
             skew = _sorted_skew_set(skewed_sampling_nodes, len(orders1) - d - 1)
-        # :117-143 on the host in one native call (gnn_ladies_layer_host): p, s_num, the legacy weighted draw, the union
-        # with previous_nodes, normfact and the sampled_nodes remap - same bits as the numpy expressions of
-        # host_layer_numpy() below, a third of the time and outside the GIL
-        after_nodes, normfact, sampled_pos, s_num = host_layer_native(mt_state, nz, cnt, skew, scale_factor, previous_nodes,
-                                                                       int(samp_num_list[d]))
-        after_dev = torch.from_numpy(after_nodes.astype(np.int64, copy=False)).to(dev)
+        # :117-143 on the host in one native call (gnn_ladies_layer_host[_dense]): p, s_num, the legacy weighted draw, the
+        # union with previous_nodes, normfact and the sampled_nodes remap - same bits as the numpy expressions of
+        # host_layer_numpy() below, a fraction of the time and outside the GIL
+        if scratch.counts_host is not None:
+            # the whole count array in one transfer into pinned memory, compacted by the native call: one synchronisation
+            scratch.counts_host.copy_(scratch.counts, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            after_nodes, normfact, sampled_pos, s_num = host_layer_native_dense(mt_state, scratch.counts_np, skew, scale_factor,
+                                                                                 prev_np, int(samp_num_list[d]))
+        else:
+            # only the columns that occur at all carry probability: compact them on the device and bring back
+            # (index, count) pairs instead of an N-long array (N = 111 M on the papers100M shape)
+            nz_dev = torch.nonzero(scratch.counts).flatten()
+            nz = nz_dev.cpu().numpy()
+            cnt = scratch.counts[nz_dev].cpu().numpy()                                      # :117 on the support (int32)
+            after_nodes, normfact, sampled_pos, s_num = host_layer_native(mt_state, nz, cnt, skew, scale_factor, prev_np,
+                                                                           int(samp_num_list[d]))
+        after_dev = h2d(after_nodes, dev)
         ext.lookup_set(scratch.lookup, after_dev, True)
         try:
             rowptr = ext.column_slice_count(ucols, fullrowptr, scratch.lookup)                # :133,135
@@ -248,7 +300,7 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
             colidx = ext.column_slice_fill(ucols, fullrowptr, scratch.lookup, rowptr, nnz, use16)  # :136
         finally:
             ext.lookup_set(scratch.lookup, after_dev, False)      # the table must be all -1 for the next minibatch, whatever happened
-        nf_dev = torch.from_numpy(normfact).to(dev)
+        nf_dev = h2d(normfact, dev)
         layer = DeviceLayer(fullrowptr, rowptr, colidx, nf_dev, int(previous_nodes.size), int(after_nodes.size))
         layers.append(layer)
         adjs.append(create_coo_tensor(fullrowptr, rowptr, colidx, nf_dev, layer.nrows, layer.ncols))   # :139

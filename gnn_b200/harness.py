@@ -198,7 +198,8 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
 
 
 def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log, pool_num=4, fused=False,
-                     prebuild_transpose=True, flat_grads=False, skewed_sampling_nodes=None, scale_factor=1.0, tc=False):
+                     prebuild_transpose=True, flat_grads=False, skewed_sampling_nodes=None, scale_factor=1.0, tc=False,
+                     sampler_stream_priority=0):
     """Training with the sampler IN the loop (BASELINE's second minibatches/s number): ``pool_num`` sampler threads
     (reference main.py:77 uses a ThreadPoolExecutor of --pool_num=4 per GPU) run the device LADIES sampler
     (gnn_b200/gpu_sampler.py: numpy draw on the host, array passes on the GPU) and the feature gather on their own
@@ -231,7 +232,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
     def job(i):
         torch.cuda.set_device(device)
         if not hasattr(tls, "stream"):
-            tls.stream = torch.cuda.Stream(device=device)
+            tls.stream = torch.cuda.Stream(device=device, priority=sampler_stream_priority)
             pipeline.reserve_stream_pool(tls.stream, 1 << 30)     # no cudaMalloc in the loop (pipeline.py)
             tls.scratch = dg.scratch()
         with torch.cuda.stream(tls.stream):
@@ -239,10 +240,11 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
                                                   create_coo_tensor=cso.create_coo_tensor, scratch=tls.scratch,
                                                   prebuild_transpose=prebuild_transpose,
                                                   skewed_sampling_nodes=skewed_sampling_nodes, scale_factor=scale_factor)
-            nodes = torch.from_numpy(mb.input_nodes).to(device)
+            # pinned staging for every upload: a pageable source makes the copy synchronise the stream first
+            nodes = gpu_sampler.h2d(mb.input_nodes, device)
             x0 = store.gather(nodes)
-            sn = [torch.from_numpy(np.ascontiguousarray(s_, dtype=np.int64)).to(device) for s_ in mb.sampled_nodes]
-            y = F.one_hot(torch.from_numpy(labels_all[mb.batch_nodes]), shape.num_classes).float().to(device)
+            sn = [gpu_sampler.h2d(np.ascontiguousarray(s_, dtype=np.int64), device) for s_ in mb.sampled_nodes]
+            y = F.one_hot(torch.from_numpy(labels_all[mb.batch_nodes]), shape.num_classes).float().pin_memory().to(device, non_blocking=True)
         tls.stream.synchronize()
         gpu_sampler.record_stream(mb, main_stream)
         for t in [x0, y] + sn:

@@ -384,6 +384,16 @@ int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32
                               int64_t n_prev, int64_t samp_num, int64_t *after_nodes, float *normfact, int64_t *sampled,
                               int64_t *n_sampled);
 
+/* gnn_ladies_layer_host_dense - the same call fed with the WHOLE column-count array of the layer (counts_dense[v] = how many
+ * rows of U = lap_matrix[previous_nodes, :] hold column v, sampler.py:117 before any compaction; num_nodes entries, the
+ * device sampler copies it into pinned memory in one transfer).  The support (ids with a non-zero count) is compacted
+ * on the host in one pass; *n_support (optional) receives its size, which bounds s_num.  after_nodes / normfact need room
+ * for min(num_nodes, samp_num) + n_prev entries.  Outputs are those of gnn_ladies_layer_host on the compacted arrays. */
+int64_t gnn_ladies_layer_host_dense(uint32_t *mt_state, const int32_t *counts_dense, int64_t num_nodes, const int64_t *skew_nodes,
+                                    int64_t n_skew, double scale_factor, const int64_t *previous_nodes, int64_t n_prev,
+                                    int64_t samp_num, int64_t *after_nodes, float *normfact, int64_t *sampled, int64_t *n_sampled,
+                                    int64_t *n_support);
+
 /* ---------------------------------------------------------------------------
  * Feature-shard memory that peers can map (one process per GPU).
  *

@@ -142,9 +142,14 @@ def test_native_host_layer_equals_the_numpy_expressions():
     from gnn_b200 import gpu_sampler as gs
     rng = np.random.Generator(np.random.PCG64(7))
     for trial, (n_nodes, n_nz, samp, scale) in enumerate([(50000, 30000, 8192, 1.0), (50000, 30000, 8192, 2.0), (200000, 9000, 8192, 1.5),
-                                                         (3000, 50, 64, 16.0), (3000, 2000, 10000, 1.0), (100, 1, 5, 1.0)]):
+                                                         (3000, 50, 64, 16.0), (3000, 2000, 10000, 1.0), (100, 1, 5, 1.0),
+                                                         # ids far sparser than the support: the sort/merge branch of the union
+                                                         (3000000, 9000, 4096, 1.5), (5000000, 700, 8192, 1.0),
+                                                         # the support is one contiguous id range (position = id - first id)
+                                                         (30000, 30000, 8192, 1.0)]):
         rs = np.random.RandomState(100 + trial)
         state = gs.mt_state_of(np.random.RandomState(100 + trial))
+        state_dense = state.copy()
         previous = rng.choice(n_nodes, size=min(512, n_nodes // 2), replace=False)
         for layer in range(3):
             nz = np.sort(rng.choice(n_nodes, size=n_nz, replace=False)).astype(np.int64)
@@ -156,6 +161,15 @@ def test_native_host_layer_equals_the_numpy_expressions():
             assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), (trial, layer, "normfact bits")
             assert np.array_equal(a[2], b[2]), (trial, layer, "sampled_nodes")
             assert a[3] == b[3]
+            if n_nodes <= 200000:
+                # the dense-count entry point (whole count array in, support compacted natively) gives the same answer
+                dense = np.zeros(n_nodes, dtype=np.int32)
+                dense[nz] = cnt
+                c = gs.host_layer_native_dense(state_dense, dense, skew, scale, previous, samp)
+                for u, v in zip(a[:3], c[:3]):
+                    assert u.dtype == v.dtype and np.array_equal(u.view(np.uint8), v.view(np.uint8)), (trial, layer, "dense entry")
+                assert a[3] == c[3]
+                assert np.array_equal(state, state_dense)
             previous = a[0]
         # the generator ends in the same state
         assert np.array_equal(state, gs.mt_state_of(rs))
