@@ -907,21 +907,52 @@ __global__ void row_lengths_kernel(const int64_t *__restrict__ indptr, const int
   }
 }
 
-// U = lap_matrix[nodes, :] (structure): copy every row's column ids; optionally count columns (ord=0 column norm)
+// U = lap_matrix[nodes, :] (structure): copy every row's column ids; optionally count columns (ord=0 column norm).
+// Entry-parallel: a CTA takes tiles of kSliceTile consecutive OUTPUT entries, whatever rows they belong to (LADIES draws
+// the high-degree nodes: rows of 20 to 19,000 entries, and a warp per row left the launch waiting for its longest rows).
+// The row of an entry is searched in fullrowptr between the rows of the tile's first and last entry (no step at all
+// inside a long row).
+constexpr int kSliceTile = 2048;     // entries per CTA tile (256 threads x 8)
+
+// last row r in [lo, hi] with fullrowptr[r] <= e  (rows may be empty; e < fullrowptr[M])
+__device__ __forceinline__ int row_of_entry(const int *__restrict__ fullrowptr, int lo, int hi, int e) {
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(fullrowptr + mid) <= e) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(256)
 row_slice_kernel(const int64_t *__restrict__ indptr, const int *__restrict__ indices, const int64_t *__restrict__ nodes, int M,
                  const int *__restrict__ fullrowptr, int *__restrict__ ucols, int *__restrict__ counts) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
-    const int64_t src = indptr[nodes[r]];
-    const int dst = __ldg(fullrowptr + r);
-    const int len = __ldg(fullrowptr + r + 1) - dst;
-    for (int i = lane; i < len; i += 32) {
-      const int c = __ldg(indices + src + i);
-      ucols[dst + i] = c;
-      if (counts) atomicAdd(counts + c, 1);
+  __shared__ int s_row[2];
+  const int total = __ldg(fullrowptr + M);
+  const int tiles = (total + kSliceTile - 1) / kSliceTile;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int t0 = tile * kSliceTile, t1 = min(t0 + kSliceTile, total);
+    if (threadIdx.x < 2) s_row[threadIdx.x] = row_of_entry(fullrowptr, 0, M - 1, threadIdx.x == 0 ? t0 : t1 - 1);
+    __syncthreads();
+    const int r_lo = s_row[0], r_hi = s_row[1];
+    int64_t src[kSliceTile / 256];
+#pragma unroll
+    for (int j = 0; j < kSliceTile / 256; ++j) {
+      const int e = t0 + j * 256 + (int)threadIdx.x;
+      src[j] = -1;
+      if (e < t1) {
+        const int r = row_of_entry(fullrowptr, r_lo, r_hi, e);
+        src[j] = indptr[nodes[r]] + (e - __ldg(fullrowptr + r));
+      }
     }
+#pragma unroll
+    for (int j = 0; j < kSliceTile / 256; ++j) {
+      if (src[j] >= 0) {
+        const int c = __ldg(indices + src[j]);
+        ucols[t0 + j * 256 + (int)threadIdx.x] = c;
+        if (counts) atomicAdd(counts + c, 1);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -931,25 +962,90 @@ __global__ void lookup_set_kernel(int *__restrict__ lookup, const int64_t *__res
 }
 
 // adj = U[:, after_nodes] (structure): keep the entries whose column was sampled, renumbered by lookup.
-// FILL == false: per-row kept counts; FILL == true: write the local column ids at rowptr[r]...
-template <bool FILL, typename ColT>
+// The rows of U lie one after the other in ucols and the kept entries keep their order, so the column slice is an
+// order-preserving stream compaction of the whole array; rowptr[r] is the number of kept entries before fullrowptr[r].
+// Entry-parallel in chunks of kSliceChunk entries per warp (balanced whatever the row lengths):
+//   column_chunk_count   kept entries per chunk              -> exclusive_scan_kernel -> chunk_prefix (its last entry: nnz)
+//   column_rowptr_kernel rowptr[r] = chunk_prefix[chunk of fullrowptr[r]] + kept entries of that chunk before it
+//   column_fill_kernel   colidx[chunk_prefix[c] + rank inside the chunk] = lookup value (ascending entries = ascending
+//                        positions: the same order as the reference's row-wise slice)
+constexpr int kSliceChunk = 1024;    // entries per warp chunk (32 steps of 32)
+
 __global__ void __launch_bounds__(256)
-column_slice_kernel(const int *__restrict__ ucols, const int *__restrict__ fullrowptr, int M, const int *__restrict__ lookup,
-                    int *__restrict__ row_counts, const int *__restrict__ rowptr, ColT *__restrict__ colidx) {
+column_chunk_count_kernel(const int *__restrict__ ucols, int total, const int *__restrict__ lookup, int *__restrict__ chunk_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int chunks = (total + kSliceChunk - 1) / kSliceChunk;
+  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < chunks; c += gridDim.x * wpb) {
+    const int base = c * kSliceChunk;
+    int kept = 0;
+#pragma unroll 4
+    for (int g = 0; g < kSliceChunk / 256; ++g) {
+      int col[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = base + g * 256 + q * 32 + lane;
+        col[q] = i < total ? __ldg(ucols + i) : -1;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) kept += (col[q] >= 0 && __ldg(lookup + col[q]) >= 0) ? 1 : 0;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) kept += __shfl_xor_sync(kFull, kept, off);
+    if (lane == 0) chunk_cnt[c] = kept;
+  }
+}
+
+// one warp per row r in [0, M]; chunk_prefix holds chunks + 1 entries
+__global__ void __launch_bounds__(256)
+column_rowptr_kernel(const int *__restrict__ ucols, int total, const int *__restrict__ fullrowptr, int M,
+                     const int *__restrict__ lookup, const int *__restrict__ chunk_prefix, int *__restrict__ rowptr) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int chunks = (total + kSliceChunk - 1) / kSliceChunk;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r <= M; r += gridDim.x * wpb) {
+    const int e0 = __ldg(fullrowptr + r);
+    if (e0 >= total) {
+      if (lane == 0) rowptr[r] = __ldg(chunk_prefix + chunks);
+      continue;
+    }
+    const int c = e0 / kSliceChunk;
+    int kept = 0;
+    for (int i = c * kSliceChunk + lane; i < e0; i += 32) kept += __ldg(lookup + __ldg(ucols + i)) >= 0 ? 1 : 0;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) kept += __shfl_xor_sync(kFull, kept, off);
+    if (lane == 0) rowptr[r] = __ldg(chunk_prefix + c) + kept;
+  }
+}
+
+template <typename ColT>
+__global__ void __launch_bounds__(256)
+column_fill_kernel(const int *__restrict__ ucols, int total, const int *__restrict__ lookup, const int *__restrict__ chunk_prefix,
+                   ColT *__restrict__ colidx) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
-    const int b = __ldg(fullrowptr + r), e = __ldg(fullrowptr + r + 1);
-    int run = FILL ? __ldg(rowptr + r) : 0;
-    for (int i0 = b; i0 < e; i0 += 32) {
-      const int i = i0 + lane;
-      const int local = i < e ? __ldg(lookup + __ldg(ucols + i)) : -1;
-      const unsigned m = __ballot_sync(kFull, local >= 0);
-      if (FILL && local >= 0) colidx[run + __popc(m & lt)] = (ColT)local;
-      run += __popc(m);
+  const int chunks = (total + kSliceChunk - 1) / kSliceChunk;
+  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < chunks; c += gridDim.x * wpb) {
+    const int base = c * kSliceChunk;
+    int run = __ldg(chunk_prefix + c);
+    for (int g = 0; g < kSliceChunk / 256; ++g) {
+      if (base + g * 256 >= total) break;
+      int local[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = base + g * 256 + q * 32 + lane;
+        local[q] = i < total ? __ldg(ucols + i) : -1;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) local[q] = local[q] >= 0 ? __ldg(lookup + local[q]) : -1;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const unsigned m = __ballot_sync(kFull, local[q] >= 0);
+        if (local[q] >= 0) colidx[run + __popc(m & lt)] = (ColT)local[q];
+        run += __popc(m);
+      }
     }
-    if (!FILL && lane == 0) row_counts[r] = run;
   }
 }
 
@@ -1555,8 +1651,8 @@ int gnn_row_slice_fill(const int64_t *indptr, const int32_t *indices, const int6
   if (M < 0) return GNN_E_BADARG;
   if (M == 0) return 0;
   if (!indptr || !indices || !nodes || !fullrowptr || !out_cols) return GNN_E_BADARG;
-  row_slice_kernel<<<warp_grid(M, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, nodes, (int)M, fullrowptr, out_cols,
-                                                                      col_counts);
+  // the entry count (fullrowptr[M]) lives on the device: a fixed grid walks the tiles
+  row_slice_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(indptr, indices, nodes, (int)M, fullrowptr, out_cols, col_counts);
   GNN_LAUNCH_CHECK();
   return 0;
 }
@@ -1570,32 +1666,42 @@ int gnn_lookup_set(int32_t *lookup, const int64_t *after_nodes, int64_t K, int s
   return 0;
 }
 
-int gnn_column_slice_count(const int32_t *ucols, const int32_t *fullrowptr, int64_t M, const int32_t *lookup,
-                           int32_t *scratch_counts, int32_t *out_rowptr, gnn_stream_t stream) {
-  if (M < 0) return GNN_E_BADARG;
-  if (!out_rowptr || (M > 0 && (!ucols || !fullrowptr || !lookup || !scratch_counts))) return GNN_E_BADARG;
+int64_t gnn_column_slice_chunks(int64_t total) { return total > 0 ? cdiv(total, kSliceChunk) : 0; }
+
+int gnn_column_slice_count(const int32_t *ucols, int64_t total, const int32_t *fullrowptr, int64_t M, const int32_t *lookup,
+                           int32_t *chunk_prefix, int32_t *out_rowptr, gnn_stream_t stream) {
+  if (M < 0 || total < 0) return GNN_E_BADARG;
+  if (total >= (1ll << 31) - kSliceChunk || M >= (1ll << 31) - 1) return GNN_E_RANGE;
+  if (!out_rowptr || !chunk_prefix || (M > 0 && !fullrowptr) || (total > 0 && (!ucols || !lookup))) return GNN_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (M == 0) { GNN_CUDA(cudaMemsetAsync(out_rowptr, 0, sizeof(int), st)); return 0; }
-  column_slice_kernel<false, int><<<warp_grid(M, 8), 256, 0, st>>>(ucols, fullrowptr, (int)M, lookup, scratch_counts, nullptr,
-                                                                   nullptr);
+  const int64_t chunks = gnn_column_slice_chunks(total);
+  if (chunks == 0) {
+    GNN_CUDA(cudaMemsetAsync(chunk_prefix, 0, sizeof(int), st));
+    GNN_CUDA(cudaMemsetAsync(out_rowptr, 0, (size_t)(M + 1) * sizeof(int), st));
+    return 0;
+  }
+  int32_t *chunk_cnt = chunk_prefix + chunks + 1;                                           // second half of the scratch
+  column_chunk_count_kernel<<<warp_grid(chunks, 8), 256, 0, st>>>(ucols, (int)total, lookup, chunk_cnt);
   GNN_LAUNCH_CHECK();
-  exclusive_scan_kernel<<<1, 1024, 0, st>>>(scratch_counts, (int)M, out_rowptr);
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(chunk_cnt, (int)chunks, chunk_prefix);
+  GNN_LAUNCH_CHECK();
+  column_rowptr_kernel<<<warp_grid(M + 1, 8), 256, 0, st>>>(ucols, (int)total, fullrowptr, (int)M, lookup, chunk_prefix, out_rowptr);
   GNN_LAUNCH_CHECK();
   return 0;
 }
 
-int gnn_column_slice_fill(const int32_t *ucols, const int32_t *fullrowptr, int64_t M, const int32_t *lookup,
-                          const int32_t *rowptr, void *out_colidx, int colidx_bytes, gnn_stream_t stream) {
-  if (M < 0 || (colidx_bytes != 2 && colidx_bytes != 4)) return GNN_E_BADARG;
-  if (M == 0) return 0;
-  if (!ucols || !fullrowptr || !lookup || !rowptr || !out_colidx) return GNN_E_BADARG;
+int gnn_column_slice_fill(const int32_t *ucols, int64_t total, const int32_t *lookup, const int32_t *chunk_prefix, void *out_colidx,
+                          int colidx_bytes, gnn_stream_t stream) {
+  if (total < 0 || (colidx_bytes != 2 && colidx_bytes != 4)) return GNN_E_BADARG;
+  if (total >= (1ll << 31) - kSliceChunk) return GNN_E_RANGE;
+  if (total == 0) return 0;
+  if (!ucols || !lookup || !chunk_prefix || !out_colidx) return GNN_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = warp_grid(gnn_column_slice_chunks(total), 8);
   if (colidx_bytes == 2)
-    column_slice_kernel<true, int16_t><<<warp_grid(M, 8), 256, 0, st>>>(ucols, fullrowptr, (int)M, lookup, nullptr, rowptr,
-                                                                        (int16_t *)out_colidx);
+    column_fill_kernel<int16_t><<<grid, 256, 0, st>>>(ucols, (int)total, lookup, chunk_prefix, (int16_t *)out_colidx);
   else
-    column_slice_kernel<true, int><<<warp_grid(M, 8), 256, 0, st>>>(ucols, fullrowptr, (int)M, lookup, nullptr, rowptr,
-                                                                    (int *)out_colidx);
+    column_fill_kernel<int><<<grid, 256, 0, st>>>(ucols, (int)total, lookup, chunk_prefix, (int *)out_colidx);
   GNN_LAUNCH_CHECK();
   return 0;
 }
@@ -1696,7 +1802,7 @@ int gnn_set_blocking_sync(int on) {
   // cudaDeviceScheduleBlockingSync: threads waiting in a synchronise call sleep instead of spinning.  The sampler threads of
   // a rank wait on three small device-to-host reads per layer; with fewer host cores than threads their spinning takes
   // the cores the other threads need (8 ranks x 5 threads on a 32-core host).
-  GNN_CUDA(cudaSetDeviceFlags(on ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto));
+  GNN_CUDA(cudaSetDeviceFlags(on == 1 ? cudaDeviceScheduleBlockingSync : on == 2 ? cudaDeviceScheduleYield : cudaDeviceScheduleAuto));
   return 0;
 }
 
@@ -1928,7 +2034,7 @@ static inline int64_t upper_count(const double *a, int64_t len, double t) {
 static int legacy_choice_core(uint32_t *mt_state, double *pw, int64_t n, int64_t size, int64_t *found) {
   // scratch lives per thread and only grows: fresh multi-megabyte vectors per call cost more in page faults than the draw
   static thread_local std::vector<double> raw, x, coarse;
-  static thread_local std::vector<int32_t> stamp, ends;
+  static thread_local std::vector<int32_t> stamp, ends, start;
   static thread_local std::vector<int64_t> cand;
   static thread_local int32_t epoch = 0;          // stamp[l] == epoch: position l was already drawn in the current round
   const int64_t nc = (n + 63) / 64;
@@ -1942,6 +2048,12 @@ static int legacy_choice_core(uint32_t *mt_state, double *pw, int64_t n, int64_t
     epoch = 0;
   }
   constexpr int kBuckets = 1 << 16;
+  if ((int64_t)ends.size() < kBuckets + 1) ends.resize(kBuckets + 1);
+  if ((int64_t)start.size() < size + 1) start.resize((size_t)size + 1);
+  // thread_local vectors: their addresses stay out of the hot loops
+  double *const rawp = raw.data(), *const xp = x.data(), *const coarsep = coarse.data();
+  int32_t *const stampp = stamp.data(), *const endsp = ends.data(), *const startp = start.data();
+  int64_t *const candp = cand.data();
   int64_t n_uniq = 0, zeroed = 0;
   int round = 0;
   double mass = 1.0;                              // estimate of cdf[-1] of the coming round (exactness does not matter)
@@ -1949,7 +2061,7 @@ static int legacy_choice_core(uint32_t *mt_state, double *pw, int64_t n, int64_t
     const int64_t k = size - n_uniq;
     for (int64_t i = 0; i < k; ++i) {
       const uint32_t a = mt_next(mt_state) >> 5, b = mt_next(mt_state) >> 6;
-      x[(size_t)i] = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+      xp[i] = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
     }
     // p[found[0:n_uniq]] = 0 (earlier ones already are); np.cumsum adds sequentially, so the running sums before the
     // first entry zeroed in this round are the ones of the previous round, bit for bit - restart from there
@@ -1969,57 +2081,66 @@ static int legacy_choice_core(uint32_t *mt_state, double *pw, int64_t n, int64_t
     // 64th sum, L1-resident).
     const bool use_table = k >= 1024 && n >= 4096 && mass > 0.0;
     const double scale = use_table ? (double)kBuckets / mass : 0.0;
-    double run = lo > 0 ? raw[(size_t)lo - 1] : 0.0;
+    double run = lo > 0 ? rawp[lo - 1] : 0.0;
     if (use_table) {
-      if ((int64_t)ends.size() < kBuckets + 1) ends.resize(kBuckets + 1);
-      std::fill(ends.begin(), ends.begin() + kBuckets + 1, 0);
-      int32_t *e = ends.data() + 1;               // e[b] = 1 + the last position whose sum falls into bucket b
+      std::fill(endsp, endsp + kBuckets + 1, 0);
+      int32_t *e = endsp + 1;               // e[b] = 1 + the last position whose sum falls into bucket b
       for (int64_t i = 0; i < lo; ++i) {
-        const double v = raw[(size_t)i] * scale;
+        const double v = rawp[i] * scale;
         e[(v >= 0.0 && v < (double)kBuckets) ? (int)v : kBuckets - 1] = (int32_t)i + 1;
       }
       for (int64_t i = lo; i < n; ++i) {
-        run += pw[(size_t)i];
-        raw[(size_t)i] = run;
+        run += pw[i];
+        rawp[i] = run;
         const double v = run * scale;
         e[(v >= 0.0 && v < (double)kBuckets) ? (int)v : kBuckets - 1] = (int32_t)i + 1;
       }
       int32_t m = 0;                              // ends[b] := positions in buckets < b (running maximum; ends[0] = 0)
-      for (int b = 1; b <= kBuckets; ++b) { m = std::max(m, ends[(size_t)b]); ends[(size_t)b] = m; }
+      for (int b = 1; b <= kBuckets; ++b) { m = std::max(m, endsp[b]); endsp[b] = m; }
     } else {
-      for (int64_t i = lo; i < n; ++i) { run += pw[(size_t)i]; raw[(size_t)i] = run; }
-      for (int64_t c = 0; c < nc; ++c) coarse[(size_t)c] = raw[(size_t)std::min<int64_t>(c * 64 + 63, n - 1)];
+      for (int64_t i = lo; i < n; ++i) { run += pw[i]; rawp[i] = run; }
+      for (int64_t c = 0; c < nc; ++c) coarsep[c] = rawp[std::min<int64_t>(c * 64 + 63, n - 1)];
     }
-    const double last = raw[(size_t)n - 1];
+    const double last = rawp[n - 1];
     if (!(last > 0.0)) return GNN_E_BADARG;                                   // fewer non-zero entries than `size` (numpy raises)
     mass = last;
     ++round;
     ++epoch;
     int64_t got = 0;
-    for (int64_t i = 0; i < k; ++i) {
-      const double xi = x[(size_t)i], t = xi * last;
-      int64_t l;
-      if (use_table) {
-        const double v = t * scale;
-        l = ends[(size_t)((v >= 0.0 && v < (double)kBuckets) ? (int)v : kBuckets - 1)];   // every sum before l is <= t
-        int steps = 0;
-        while (l < n && raw[(size_t)l] <= t) {
-          ++l;
-          if (++steps == 48) { l += upper_count(raw.data() + l, n - l, t); break; }        // a crowded bucket
-        }
-      } else {
-        const int64_t cb = upper_count(coarse.data(), nc, t);                 // blocks whose LAST element is <= t
-        const int64_t b0 = cb * 64, bl = std::min<int64_t>(64, n - b0);
-        l = bl > 0 ? b0 + upper_count(raw.data() + b0, bl, t) : n;
-      }
-      while (l < n && raw[(size_t)l] / last <= xi) ++l;
-      while (l > 0 && raw[(size_t)l - 1] / last > xi) --l;
-      if (stamp[(size_t)l] != epoch) {            // np.unique(return_index=True) + sort: first occurrence, draw order
-        stamp[(size_t)l] = epoch;
-        cand[(size_t)got++] = l;
+    if (use_table) {
+      // table look-ups of all draws first (independent loads), with the lines of `raw` and `stamp` they lead to requested
+      // early: the walk below then finds them in cache instead of paying one miss per draw in sequence
+      for (int64_t i = 0; i < k; ++i) {
+        const double v = xp[i] * last * scale;
+        const int32_t l0 = endsp[((v >= 0.0 && v < (double)kBuckets) ? (int)v : kBuckets - 1)];
+        startp[i] = l0;
+        __builtin_prefetch(rawp + l0);
+        __builtin_prefetch(stampp + l0);
       }
     }
-    for (int64_t i = 0; i < got; ++i) found[n_uniq + i] = cand[(size_t)i];
+    for (int64_t i = 0; i < k; ++i) {
+      const double xi = xp[i], t = xi * last;
+      int64_t l;
+      if (use_table) {
+        l = startp[i];                                                  // every sum before l is <= t
+        int steps = 0;
+        while (l < n && rawp[l] <= t) {
+          ++l;
+          if (++steps == 48) { l += upper_count(rawp + l, n - l, t); break; }        // a crowded bucket
+        }
+      } else {
+        const int64_t cb = upper_count(coarsep, nc, t);                 // blocks whose LAST element is <= t
+        const int64_t b0 = cb * 64, bl = std::min<int64_t>(64, n - b0);
+        l = bl > 0 ? b0 + upper_count(rawp + b0, bl, t) : n;
+      }
+      while (l < n && rawp[l] / last <= xi) ++l;
+      while (l > 0 && rawp[l - 1] / last > xi) --l;
+      if (stampp[l] != epoch) {            // np.unique(return_index=True) + sort: first occurrence, draw order
+        stampp[l] = epoch;
+        candp[got++] = l;
+      }
+    }
+    for (int64_t i = 0; i < got; ++i) found[n_uniq + i] = candp[i];
     n_uniq += got;
   }
   return 0;
@@ -2037,10 +2158,11 @@ int gnn_legacy_choice_f64(uint32_t *mt_state, const double *p, int64_t n, int64_
 // integer column counts, the weighted draw above, after_nodes = unique(drawn + previous), the normalisation factors and
 // the sampled_nodes remap.  Every step is integer arithmetic or the reference's own IEEE expressions, so the outputs
 // equal the numpy code's bit for bit (tests/test_sampler_golden.py compares them).
-int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32_t *counts, int64_t n_nz,
-                              const int64_t *skew_nodes, int64_t n_skew, double scale_factor, const int64_t *previous_nodes,
-                              int64_t n_prev, int64_t samp_num, int64_t *after_nodes, float *normfact, int64_t *sampled,
-                              int64_t *n_sampled) {
+// dense_counts (optional): the count of EVERY node id below num_nodes, so that p[after_nodes] needs no id -> support position map
+static int64_t ladies_layer_host_impl(uint32_t *mt_state, const int64_t *nz, const int32_t *counts, int64_t n_nz,
+                                      const int64_t *skew_nodes, int64_t n_skew, double scale_factor, const int64_t *previous_nodes,
+                                      int64_t n_prev, int64_t samp_num, int64_t *after_nodes, float *normfact, int64_t *sampled,
+                                      int64_t *n_sampled, const int32_t *dense_counts, int64_t num_nodes) {
   if (!mt_state || !nz || !counts || n_nz <= 0 || !previous_nodes || n_prev < 0 || samp_num < 0 || !after_nodes || !normfact ||
       !sampled || !n_sampled)
     return GNN_E_BADARG;
@@ -2072,11 +2194,17 @@ int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32
   const double dtotal = (double)total;
   auto pi_at = [&](int64_t i) -> double { return scaled ? (double)pi[(size_t)i] : (double)counts[i]; };
   p.resize((size_t)n_nz);
-  if (scaled) for (int64_t i = 0; i < n_nz; ++i) p[(size_t)i] = (double)pi[(size_t)i] / dtotal;    // p = pi / np.sum(pi)  (:124)
-  else        for (int64_t i = 0; i < n_nz; ++i) p[(size_t)i] = (double)counts[i] / dtotal;
+  {
+    double *pp = p.data();                                                                         // p = pi / np.sum(pi)  (:124)
+    const int64_t *pi64 = pi.data();
+    if (scaled) for (int64_t i = 0; i < n_nz; ++i) pp[i] = (double)pi64[i] / dtotal;
+    else        for (int64_t i = 0; i < n_nz; ++i) pp[i] = (double)counts[i] / dtotal;
+  }
   const int64_t s_num = std::min(n_pos, samp_num);                                                 // :126
   found.resize((size_t)std::max<int64_t>(s_num, 1));
-  // the draw zeroes the entries it takes in p; p[after_nodes] below is re-derived by the same division
+  // the draw zeroes the entries it takes in p; p[after_nodes] below is re-derived by the same division.  (Evaluating the
+  // division inside the draw's first cumsum pass was measured: scalar divisions on the addition chain cost more than this
+  // vectorised loop.)
   const int rc = legacy_choice_core(mt_state, p.data(), n_nz, s_num, found.data());                 // :128
   if (rc != 0) return rc;
   int64_t max_id = nz[n_nz - 1];
@@ -2099,8 +2227,9 @@ int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32
     for (int64_t i = 0; i < n_prev; ++i) { const int64_t v = previous_nodes[i]; bits[(size_t)(v >> 6)] |= 1ull << (v & 63); }
     // position of a node inside the support: arithmetic when the support is one contiguous id range, else a table
     // (written for every support entry, validated on read: stale contents are harmless)
+    const bool direct = dense_counts && !scaled && range <= num_nodes;
     const bool contiguous = nz[n_nz - 1] - nz[0] == n_nz - 1;
-    if (!contiguous) {
+    if (!direct && !contiguous) {
       if ((int64_t)pos_of.size() < range) pos_of.resize((size_t)range);
       for (int64_t j = 0; j < n_nz; ++j) pos_of[(size_t)nz[j]] = (int32_t)j;
     }
@@ -2111,10 +2240,15 @@ int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32
       while (m) {
         const int64_t node = (w << 6) + __builtin_ctzll(m);
         m &= m - 1;
-        int64_t j = contiguous ? node - nz[0] : (int64_t)pos_of[(size_t)node];
-        const bool in_support = j >= 0 && j < n_nz && nz[j] == node;
-        // normfact = 1 / np.clip(s_num * p[after_nodes], 1e-10, 1).astype(np.float32)   (:137); p is zero off the support
-        double v = (double)s_num * (in_support ? pi_at(j) / dtotal : 0.0);
+        double pa;                                                             // p[node]; zero off the support
+        if (direct) {
+          pa = (double)dense_counts[node] / dtotal;
+        } else {
+          const int64_t j = contiguous ? node - nz[0] : (int64_t)pos_of[(size_t)node];
+          pa = (j >= 0 && j < n_nz && nz[j] == node) ? pi_at(j) / dtotal : 0.0;
+        }
+        // normfact = 1 / np.clip(s_num * p[after_nodes], 1e-10, 1).astype(np.float32)   (:137)
+        double v = (double)s_num * pa;
         v = v < 1e-10 ? 1e-10 : (v > 1.0 ? 1.0 : v);
         after_nodes[n_after] = node;
         normfact[n_after] = 1.0f / (float)v;
@@ -2161,6 +2295,14 @@ int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32
   return n_after;
 }
 
+int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32_t *counts, int64_t n_nz,
+                              const int64_t *skew_nodes, int64_t n_skew, double scale_factor, const int64_t *previous_nodes,
+                              int64_t n_prev, int64_t samp_num, int64_t *after_nodes, float *normfact, int64_t *sampled,
+                              int64_t *n_sampled) {
+  return ladies_layer_host_impl(mt_state, nz, counts, n_nz, skew_nodes, n_skew, scale_factor, previous_nodes, n_prev, samp_num,
+                                after_nodes, normfact, sampled, n_sampled, nullptr, 0);
+}
+
 // Same, fed with the device sampler's whole count array (one D2H copy of num_nodes int32 into pinned memory instead of
 // a device-side compaction with its two extra stream synchronisations): the support is compacted here, in one pass.
 int64_t gnn_ladies_layer_host_dense(uint32_t *mt_state, const int32_t *counts_dense, int64_t num_nodes, const int64_t *skew_nodes,
@@ -2169,20 +2311,35 @@ int64_t gnn_ladies_layer_host_dense(uint32_t *mt_state, const int32_t *counts_de
                                     int64_t *n_support) {
   if (!counts_dense || num_nodes <= 0) return GNN_E_BADARG;
   if (num_nodes > INT32_MAX) return GNN_E_RANGE;
-  static thread_local std::vector<int64_t> nzv;
+  static thread_local std::vector<int64_t> nzv, iota;
   static thread_local std::vector<int32_t> cntv;
+  int64_t support = 0;
+  for (int64_t i = 0; i < num_nodes; ++i) support += counts_dense[i] != 0;
+  if (support == num_nodes) {
+    // every node carries probability (the lower layers of a Reddit-shaped minibatch): ids are 0..N-1, counts lie in place
+    const int64_t have = (int64_t)iota.size();
+    if (have < num_nodes) {
+      iota.resize((size_t)num_nodes);
+      for (int64_t i = have; i < num_nodes; ++i) iota[(size_t)i] = i;
+    }
+    if (n_support) *n_support = num_nodes;
+    return ladies_layer_host_impl(mt_state, iota.data(), counts_dense, num_nodes, skew_nodes, n_skew, scale_factor, previous_nodes,
+                                  n_prev, samp_num, after_nodes, normfact, sampled, n_sampled, counts_dense, num_nodes);
+  }
   if ((int64_t)nzv.size() < num_nodes + 1) { nzv.resize((size_t)num_nodes + 1); cntv.resize((size_t)num_nodes + 1); }
   int64_t m = 0;
+  int64_t *const nzp = nzv.data();
+  int32_t *const cnp = cntv.data();
   for (int64_t i = 0; i < num_nodes; ++i) {                                   // branch-free: write always, advance on non-zero
     const int32_t c = counts_dense[i];
-    nzv[(size_t)m] = i;
-    cntv[(size_t)m] = c;
+    nzp[m] = i;
+    cnp[m] = c;
     m += c != 0;
   }
   if (n_support) *n_support = m;
   if (m == 0) return GNN_E_BADARG;
-  return gnn_ladies_layer_host(mt_state, nzv.data(), cntv.data(), m, skew_nodes, n_skew, scale_factor, previous_nodes, n_prev,
-                               samp_num, after_nodes, normfact, sampled, n_sampled);
+  return ladies_layer_host_impl(mt_state, nzv.data(), cntv.data(), m, skew_nodes, n_skew, scale_factor, previous_nodes, n_prev,
+                                samp_num, after_nodes, normfact, sampled, n_sampled, counts_dense, num_nodes);
 }
 
 }  // extern "C"

@@ -19,6 +19,7 @@
 
 #include <cuda_runtime_api.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -356,28 +357,111 @@ void lookup_set(torch::Tensor lookup, const torch::Tensor &after_nodes, bool set
            "gnn_lookup_set");
 }
 
-torch::Tensor column_slice_count(const torch::Tensor &ucols, const torch::Tensor &fullrowptr, const torch::Tensor &lookup) {
+// -> (rowptr int32 [M+1], chunk_prefix scratch for column_slice_fill)
+std::tuple<torch::Tensor, torch::Tensor> column_slice_count(const torch::Tensor &ucols, const torch::Tensor &fullrowptr,
+                                                            const torch::Tensor &lookup) {
   CHECK_DENSE(ucols); CHECK_DENSE(fullrowptr); CHECK_DENSE(lookup);
+  TORCH_CHECK(ucols.scalar_type() == torch::kInt && fullrowptr.scalar_type() == torch::kInt && lookup.scalar_type() == torch::kInt,
+              "ucols / fullrowptr / lookup must be int32");
   c10::cuda::CUDAGuard g(ucols.device());
-  const int64_t M = fullrowptr.numel() - 1;
-  auto counts = torch::empty({M}, fullrowptr.options());
+  const int64_t M = fullrowptr.numel() - 1, total = ucols.numel();
+  auto chunk_prefix = torch::empty({2 * gnn_column_slice_chunks(total) + 2}, fullrowptr.options());
   auto rowptr = torch::empty({M + 1}, fullrowptr.options());
-  check_rc(gnn_column_slice_count(ucols.data_ptr<int32_t>(), fullrowptr.data_ptr<int32_t>(), M, lookup.data_ptr<int32_t>(),
-                                  counts.data_ptr<int32_t>(), rowptr.data_ptr<int32_t>(), cur_stream()),
+  check_rc(gnn_column_slice_count(ucols.data_ptr<int32_t>(), total, fullrowptr.data_ptr<int32_t>(), M, lookup.data_ptr<int32_t>(),
+                                  chunk_prefix.data_ptr<int32_t>(), rowptr.data_ptr<int32_t>(), cur_stream()),
            "gnn_column_slice_count");
-  return rowptr;
+  return {rowptr, chunk_prefix};
 }
 
-torch::Tensor column_slice_fill(const torch::Tensor &ucols, const torch::Tensor &fullrowptr, const torch::Tensor &lookup,
-                                const torch::Tensor &rowptr, int64_t nnz, bool int16_ids) {
-  CHECK_DENSE(ucols); CHECK_DENSE(fullrowptr); CHECK_DENSE(lookup); CHECK_DENSE(rowptr);
+torch::Tensor column_slice_fill(const torch::Tensor &ucols, const torch::Tensor &lookup, const torch::Tensor &chunk_prefix,
+                                int64_t nnz, bool int16_ids) {
+  CHECK_DENSE(ucols); CHECK_DENSE(lookup); CHECK_DENSE(chunk_prefix);
+  TORCH_CHECK(chunk_prefix.numel() == 2 * gnn_column_slice_chunks(ucols.numel()) + 2, "chunk_prefix does not belong to ucols");
   c10::cuda::CUDAGuard g(ucols.device());
-  const int64_t M = fullrowptr.numel() - 1;
-  auto colidx = torch::empty({nnz}, fullrowptr.options().dtype(int16_ids ? torch::kShort : torch::kInt));
-  check_rc(gnn_column_slice_fill(ucols.data_ptr<int32_t>(), fullrowptr.data_ptr<int32_t>(), M, lookup.data_ptr<int32_t>(),
-                                 rowptr.data_ptr<int32_t>(), colidx.data_ptr(), int16_ids ? 2 : 4, cur_stream()),
+  auto colidx = torch::empty({nnz}, ucols.options().dtype(int16_ids ? torch::kShort : torch::kInt));
+  check_rc(gnn_column_slice_fill(ucols.data_ptr<int32_t>(), ucols.numel(), lookup.data_ptr<int32_t>(), chunk_prefix.data_ptr<int32_t>(),
+                                 colidx.data_ptr(), int16_ids ? 2 : 4, cur_stream()),
            "gnn_column_slice_fill");
   return colidx;
+}
+
+// One whole LADIES layer (reference sampler.py:113-143) in ONE call with the GIL released: the device passes above, the
+// column counts into pinned memory, the host part (gnn_ladies_layer_host_dense: probabilities, legacy weighted draw,
+// union, normfact, remap), the uploads through pinned blocks of torch's caching host allocator, the column slice.
+// The sampler threads of a rank share one interpreter with the training thread; as separate Python-level calls the
+// glue of a layer held the GIL for ~0.4 ms, which - not the host cores - bounded live-sampler training.
+// Two stream synchronisations (counts, kept count).  Returns (fullrowptr, rowptr, colidx, normfact [device],
+// after_nodes int64, sampled positions int64 [host]).
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> ladies_layer_device(
+    const torch::Tensor &indptr, const torch::Tensor &indices, const torch::Tensor &indptr_host, torch::Tensor lookup,
+    torch::Tensor counts, torch::Tensor counts_host, torch::Tensor mt_state, const torch::Tensor &previous_nodes,
+    c10::optional<torch::Tensor> skew_nodes, double scale_factor, int64_t samp_num, bool int16_ids) {
+  CHECK_DENSE(indptr); CHECK_DENSE(indices); CHECK_DENSE(lookup); CHECK_DENSE(counts);
+  TORCH_CHECK(indptr.scalar_type() == torch::kLong && indices.scalar_type() == torch::kInt, "indptr int64, indices int32");
+  TORCH_CHECK(lookup.scalar_type() == torch::kInt && counts.scalar_type() == torch::kInt, "lookup / counts must be int32");
+  TORCH_CHECK(!indptr_host.is_cuda() && indptr_host.scalar_type() == torch::kLong && indptr_host.is_contiguous() &&
+              indptr_host.numel() == indptr.numel(), "indptr_host: the host copy of indptr (int64)");
+  TORCH_CHECK(!counts_host.is_cuda() && counts_host.is_pinned() && counts_host.scalar_type() == torch::kInt &&
+              counts_host.is_contiguous() && counts_host.numel() == counts.numel(), "counts_host: pinned int32 mirror of counts");
+  TORCH_CHECK(!mt_state.is_cuda() && mt_state.is_contiguous() && mt_state.numel() * mt_state.element_size() == 625 * 4,
+              "mt_state: 625 32-bit words on the host");
+  TORCH_CHECK(!previous_nodes.is_cuda() && previous_nodes.scalar_type() == torch::kLong && previous_nodes.is_contiguous(),
+              "previous_nodes: int64 on the host");
+  const int64_t *skew = nullptr;
+  int64_t n_skew = 0;
+  if (skew_nodes.has_value() && scale_factor > 1.0) {
+    TORCH_CHECK(!skew_nodes.value().is_cuda() && skew_nodes.value().scalar_type() == torch::kLong && skew_nodes.value().is_contiguous(),
+                "skew_nodes: int64 on the host");
+    skew = skew_nodes.value().data_ptr<int64_t>();
+    n_skew = skew_nodes.value().numel();
+  }
+  c10::cuda::CUDAGuard g(indptr.device());
+  const auto dev = indptr.device();
+  const int64_t N = counts.numel(), M = previous_nodes.numel();
+  auto pinned = [](torch::ScalarType t) { return torch::TensorOptions().dtype(t).pinned_memory(true); };
+  // U = lap_matrix[previous_nodes, :]  (:113-114) and its column counts (:117)
+  const int64_t *prev = previous_nodes.data_ptr<int64_t>();
+  const int64_t *ip = indptr_host.data_ptr<int64_t>();
+  auto prev_pin = torch::empty({M}, pinned(torch::kLong));
+  int64_t total = 0;
+  for (int64_t i = 0; i < M; ++i) {
+    TORCH_CHECK(prev[i] >= 0 && prev[i] < N, "previous_nodes out of range");
+    total += ip[prev[i] + 1] - ip[prev[i]];
+    prev_pin.data_ptr<int64_t>()[i] = prev[i];
+  }
+  auto prev_dev = prev_pin.to(dev, /*non_blocking=*/true);
+  auto fullrowptr = row_slice_count(indptr, prev_dev);
+  counts.zero_();
+  auto ucols = row_slice_fill(indptr, indices, prev_dev, fullrowptr, total, counts);
+  counts_host.copy_(counts, /*non_blocking=*/true);
+  TORCH_CHECK(cudaStreamSynchronize((cudaStream_t)cur_stream()) == cudaSuccess, "stream synchronise failed");
+  // :117-143 on the host
+  const int64_t cap = std::min<int64_t>(N, samp_num) + M;
+  auto after_pin = torch::empty({cap}, pinned(torch::kLong));
+  auto nf_pin = torch::empty({cap}, pinned(torch::kFloat));
+  auto sampled = torch::empty({M}, torch::TensorOptions().dtype(torch::kLong));
+  int64_t n_sampled = 0, n_support = 0;
+  const int64_t n_after = gnn_ladies_layer_host_dense(reinterpret_cast<uint32_t *>(mt_state.data_ptr()), counts_host.data_ptr<int32_t>(), N,
+                                                      skew, n_skew, scale_factor, prev, M, samp_num, after_pin.data_ptr<int64_t>(),
+                                                      nf_pin.data_ptr<float>(), sampled.data_ptr<int64_t>(), &n_sampled, &n_support);
+  if (n_after < 0) check_rc((int)n_after, "gnn_ladies_layer_host_dense");
+  auto after_host = after_pin.narrow(0, 0, n_after);
+  auto after_dev = after_host.to(dev, /*non_blocking=*/true);
+  auto nf_dev = nf_pin.narrow(0, 0, n_after).to(dev, /*non_blocking=*/true);
+  // adj = U[:, after_nodes]  (:133-136)
+  lookup_set(lookup, after_dev, true);
+  torch::Tensor rowptr, colidx;
+  try {
+    torch::Tensor chunk_prefix;
+    std::tie(rowptr, chunk_prefix) = column_slice_count(ucols, fullrowptr, lookup);
+    const int64_t nnz = rowptr[M].item<int32_t>();
+    colidx = column_slice_fill(ucols, lookup, chunk_prefix, nnz, int16_ids && n_after <= 32768);
+  } catch (...) {
+    lookup_set(lookup, after_dev, false);      // the table must be all -1 for the next minibatch, whatever happened
+    throw;
+  }
+  lookup_set(lookup, after_dev, false);
+  return {fullrowptr, rowptr, colidx, nf_dev, after_host, sampled.narrow(0, 0, n_sampled)};
 }
 
 // ---- fused layer epilogue (models.py:21-25 / :61-64) ---------------------------------------
@@ -576,6 +660,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lookup_set", &lookup_set, "lookup[after_nodes[j]] = j or -1", rel());
   m.def("column_slice_count", &column_slice_count, "rowptr of U[:, after_nodes]", rel());
   m.def("column_slice_fill", &column_slice_fill, "local column ids of U[:, after_nodes]", rel());
+  m.def("ladies_layer_device", &ladies_layer_device, "one LADIES layer: device passes + host draw + uploads, GIL released", rel());
   m.def("elu_rownorm_fwd", &elu_rownorm_fwd, "y, mean, rstd = rownorm(elu(x)) * scale + offset", rel());
   m.def("elu_rownorm_bwd", &elu_rownorm_bwd, "dx, dscale, doffset", rel());
   m.def("linear_split_weights", &linear_split_weights, "W[N,K] -> TF32 hi/lo planes (w_nk, w_kn)", rel());
@@ -595,6 +680,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     return prev;
   });
   m.def("host_gather_ctas", []() { return gnn_host_gather_ctas(); });
-  m.def("set_blocking_sync", [](bool on) { check_rc(gnn_set_blocking_sync(on ? 1 : 0), "gnn_set_blocking_sync"); });
+  m.def("set_blocking_sync", [](int mode) { check_rc(gnn_set_blocking_sync(mode), "gnn_set_blocking_sync"); });
   m.def("abi_version", []() { return gnn_abi_version(); });
 }

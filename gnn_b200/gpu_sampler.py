@@ -7,7 +7,7 @@ own expression).  What moves to the GPU are the passes that cost the reference ~
 
     U = lap_matrix[previous_nodes, :]          (sampler.py:113)   gnn_row_slice_count / _fill
     pi = sp.linalg.norm(U, ord=0, axis=0)      (sampler.py:117)   column counts, fused into the fill pass
-    adj = U[:, after_nodes]                    (sampler.py:133)   gnn_lookup_set + gnn_column_slice_count / _fill
+    adj = U[:, after_nodes]                    (sampler.py:133)   gnn_lookup_set + gnn_column_slice_count / _fill (stream compaction)
     create_coo_tensor(...)                     (sampler.py:139)   gnn_build_adj (unchanged)
 
 Two D2H reads per layer synchronise the stream (the column counts - the whole array into pinned memory when the graph
@@ -77,6 +77,8 @@ class DeviceGraph:
         self.device = torch.device(device)
         self.num_nodes = int(indptr.size - 1)
         self.indptr_host = np.asarray(indptr)      # the caller's array (not copied): slice sizes without a device read
+        self.indptr_host_t = (torch.from_numpy(self.indptr_host) if self.indptr_host.dtype == np.int64 and
+                              self.indptr_host.flags.c_contiguous else None)
         self.indptr = torch.from_numpy(np.ascontiguousarray(indptr, dtype=np.int64)).to(self.device)
         self.indices = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int32)).to(self.device)
         self._default_scratch = None
@@ -244,7 +246,10 @@ def host_layer_numpy(rs, nz, cnt, skew, scale_factor, previous_nodes, samp_num):
 def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], graph: DeviceGraph, orders: Sequence[int],
                          create_coo_tensor=None, int16_ids: bool = True, skewed_sampling_nodes=None,
                          scale_factor: float = 1.0, scratch: Optional[SamplerScratch] = None,
-                         prebuild_transpose: bool = True) -> DeviceMinibatch:
+                         prebuild_transpose: bool = True, one_call_layers: bool = True) -> DeviceMinibatch:
+    """``one_call_layers``: a whole layer runs in one native call with the GIL released (``ladies_layer_device`` of the
+    extension; graphs of at most DENSE_COUNTS_MAX nodes).  False keeps the step-by-step Python sequence below - the same
+    kernels and the same host function, the readable order of operations, and what larger graphs use."""
     ext = _native.extension()
     if create_coo_tensor is None:
         from .custom_sparse_ops import create_coo_tensor
@@ -253,6 +258,7 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
     # == np.random.seed(seed) + the global legacy functions (sampler.py:96), as a private MT19937 state: thread-safe, and
     # the draws of consecutive layers continue one stream like the reference's
     mt_state = mt_state_of(np.random.RandomState(seed))
+    mt_state_t = torch.from_numpy(mt_state.view(np.int32))           # the same 625 words, for the one-call layer
     previous_nodes = np.asarray(batch_nodes)
     batch = previous_nodes
     orders1 = list(orders)[::-1]
@@ -266,14 +272,26 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
             sampled.append([])
             continue
         prev_np = np.ascontiguousarray(previous_nodes, dtype=np.int64)
+        skew = None
+        if scale_factor > 1:                                                                # :119-121
+            skew = _sorted_skew_set(skewed_sampling_nodes, len(orders1) - d - 1)
+        if one_call_layers and scratch.counts_host is not None and graph.indptr_host_t is not None:
+            fullrowptr, rowptr, colidx, nf_dev, after_t, sampled_t = ext.ladies_layer_device(
+                graph.indptr, graph.indices, graph.indptr_host_t, scratch.lookup, scratch.counts, scratch.counts_host, mt_state_t,
+                torch.from_numpy(prev_np), torch.from_numpy(skew) if skew is not None else None, float(scale_factor),
+                int(samp_num_list[d]), bool(int16_ids))
+            after_nodes = after_t.numpy()
+            layer = DeviceLayer(fullrowptr, rowptr, colidx, nf_dev, int(prev_np.size), int(after_nodes.size))
+            layers.append(layer)
+            adjs.append(create_coo_tensor(fullrowptr, rowptr, colidx, nf_dev, layer.nrows, layer.ncols))   # :139
+            sampled.append(sampled_t.numpy())                                               # :143
+            previous_nodes = after_nodes
+            continue
         prev_dev = h2d(prev_np, dev)
         fullrowptr = ext.row_slice_count(graph.indptr, prev_dev)                           # :113-114
         total = int((graph.indptr_host[prev_np + 1] - graph.indptr_host[prev_np]).sum())    # == fullrowptr[-1], no device read
         scratch.counts.zero_()
         ucols = ext.row_slice_fill(graph.indptr, graph.indices, prev_dev, fullrowptr, total, scratch.counts)
-        skew = None
-        if scale_factor > 1:                                                                # :119-121
-            skew = _sorted_skew_set(skewed_sampling_nodes, len(orders1) - d - 1)
         # :117-143 on the host in one native call (gnn_ladies_layer_host[_dense]): p, s_num, the legacy weighted draw, the
         # union with previous_nodes, normfact and the sampled_nodes remap - same bits as the numpy expressions of
         # host_layer_numpy() below, a fraction of the time and outside the GIL
@@ -294,10 +312,10 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
         after_dev = h2d(after_nodes, dev)
         ext.lookup_set(scratch.lookup, after_dev, True)
         try:
-            rowptr = ext.column_slice_count(ucols, fullrowptr, scratch.lookup)                # :133,135
+            rowptr, chunk_prefix = ext.column_slice_count(ucols, fullrowptr, scratch.lookup)  # :133,135
             nnz = int(rowptr[-1].item())
             use16 = int16_ids and after_nodes.size <= 32768
-            colidx = ext.column_slice_fill(ucols, fullrowptr, scratch.lookup, rowptr, nnz, use16)  # :136
+            colidx = ext.column_slice_fill(ucols, scratch.lookup, chunk_prefix, nnz, use16)   # :136
         finally:
             ext.lookup_set(scratch.lookup, after_dev, False)      # the table must be all -1 for the next minibatch, whatever happened
         nf_dev = h2d(normfact, dev)

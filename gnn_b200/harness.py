@@ -217,7 +217,10 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
     dg = gpu_sampler.DeviceGraph(g.indptr, g.indices, device)
     tls = threading.local()
     main_stream = torch.cuda.current_stream(device)
-    steps = max(4, min(args.steps, 24))
+    # sustained rate: the timed region is several times the queue depth, so that neither a full queue at its start nor an
+    # empty one can carry the figure
+    depth = 2 * pool_num
+    steps = max(args.steps, 6 * depth)
     # every sampler thread owns a stream, and the caching allocator keeps one block pool per stream: until each pool
     # has seen the largest adjacency it will hold, jobs hit cudaMalloc (device-synchronising).  Warm up long enough
     # for that (untimed, like any production run's first steps); measured: 4 steps left runs at 19-52 ms/step, then
@@ -229,7 +232,11 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
     own = g.train_nodes[rank * chunk: min((rank + 1) * chunk, g.train_nodes.size)]
     batches = [own[rng.permutation(own.size)[:batch]] for _ in range(total)]
 
+    job_s = [0.0, 0]                                  # seconds spent inside sampler jobs, jobs finished (timed region only)
+    wait_s = [0.0]                                    # seconds the training thread waited for a minibatch
+
     def job(i):
+        t_job = time.perf_counter()
         torch.cuda.set_device(device)
         if not hasattr(tls, "stream"):
             tls.stream = torch.cuda.Stream(device=device, priority=sampler_stream_priority)
@@ -249,13 +256,14 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         gpu_sampler.record_stream(mb, main_stream)
         for t in [x0, y] + sn:
             t.record_stream(main_stream)
+        job_s[0] += time.perf_counter() - t_job       # (unsynchronised adds of a diagnostic: good to a few percent)
+        job_s[1] += 1
         return mb, x0, sn, y
 
     model.train()
     pool = ThreadPoolExecutor(max_workers=pool_num)
     pending = collections.deque()
     nxt = 0
-    depth = 2 * pool_num
 
     def refill():
         nonlocal nxt
@@ -265,7 +273,9 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
 
     def step():
         refill()
+        t_wait = time.perf_counter()
         mb, x0, sn, y = pending.popleft().result()
+        wait_s[0] += time.perf_counter() - t_wait
         refill()
         if flat is not None:
             flat.zero()
@@ -290,6 +300,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
     gc.disable()
     if world > 1:
         dist.barrier()
+    job_s[0], job_s[1], wait_s[0] = 0.0, 0, 0.0
     t0 = time.perf_counter()
     for _ in range(steps):
         loss = step()
@@ -307,6 +318,8 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         wall = float(t.item())
     return {"minibatches_per_s": round(world * steps / wall, 2), "unit": "minibatches/s", "steps": steps,
             "ms_per_step_wall": round(wall / steps * 1e3, 3), "sampler_threads": pool_num, "warmup_steps": warm, "final_loss": round(last, 4),
+            "queue_depth": depth, "sampler_job_ms": round(job_s[0] / max(job_s[1], 1) * 1e3, 2),
+            "trainer_wait_ms_per_step": round(wait_s[0] / steps * 1e3, 3),
             "fused_epilogue": bool(fused), "flat_gradients": bool(flat_grads), "tensor_core_linears": bool(tc), "model": kind,
             "scale_factor": float(scale_factor),
             "note": "live LADIES sampling: numpy draw on the host + device array passes (bit-identical sampled sets), "

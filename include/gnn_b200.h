@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GNN_B200_ABI_VERSION 3
+#define GNN_B200_ABI_VERSION 4
 
 #define GNN_E_BADARG   (-1)   /* null pointer, negative size, unsupported width */
 #define GNN_E_WORKSPACE (-2)  /* workspace missing or too small */
@@ -55,8 +55,8 @@ int64_t gnn_launch_count(void);
 int gnn_set_corunner_ctas(int ctas);
 int gnn_host_gather_ctas(void);
 
-/* Host threads that wait in a stream / event synchronise of the CURRENT device sleep (on != 0, cudaDeviceScheduleBlockingSync)
- * or spin (0, the CUDA default).  For processes that run more waiting threads than they have host cores: the reference's
+/* Host threads that wait in a stream / event synchronise of the CURRENT device sleep (on == 1, cudaDeviceScheduleBlockingSync),
+ * spin but yield their core between polls (on == 2, cudaDeviceScheduleYield) or spin (0, the CUDA default).  For processes that run more waiting threads than they have host cores: the reference's
  * sampler pool (main.py:77, --pool_num threads per GPU) next to the trainer thread. */
 int gnn_set_blocking_sync(int on);
 
@@ -265,19 +265,25 @@ int gnn_index_rows_f32(const float *X, int64_t ldx, const int64_t *idx, int64_t 
  *                        col_counts must be zero on entry.
  * gnn_lookup_set       : lookup[after_nodes[j]] = j (set != 0) or -1 (set == 0) for j < K; lookup is int32 [N],
  *                        -1 everywhere between uses.
- * gnn_column_slice_count / _fill : adj = U[:, after_nodes] (sampler.py:133-136): per-row kept counts and their
- *                        exclusive scan (out_rowptr[M+1]), then the kept entries renumbered to positions inside
- *                        after_nodes, ascending within a row, as int16 (reference hand-off) or int32.
+ * gnn_column_slice_count / _fill : adj = U[:, after_nodes] (sampler.py:133-136).  The rows of U lie one after the other
+ *                        in ucols[total] and kept entries keep their order, so the slice is an order-preserving stream
+ *                        compaction over the whole array, done in chunks of entries (balanced whatever the row lengths):
+ *                        _count fills chunk_prefix (scratch, int32 [2 * gnn_column_slice_chunks(total) + 2]; its first
+ *                        chunks + 1 entries = kept entries before each chunk, the last of them = nnz) and
+ *                        out_rowptr[M+1] (kept entries before every row; out_rowptr[M] = nnz); _fill writes the kept
+ *                        entries renumbered to positions inside after_nodes, ascending within a row, as int16
+ *                        (reference hand-off) or int32, from the same ucols / lookup / chunk_prefix.
  * ------------------------------------------------------------------------- */
 int gnn_row_slice_count(const int64_t *indptr, const int64_t *nodes, int64_t M, int32_t *scratch_lens,
                         int32_t *out_fullrowptr, gnn_stream_t stream);
 int gnn_row_slice_fill(const int64_t *indptr, const int32_t *indices, const int64_t *nodes, int64_t M,
                        const int32_t *fullrowptr, int32_t *out_cols, int32_t *col_counts, gnn_stream_t stream);
 int gnn_lookup_set(int32_t *lookup, const int64_t *after_nodes, int64_t K, int set, gnn_stream_t stream);
-int gnn_column_slice_count(const int32_t *ucols, const int32_t *fullrowptr, int64_t M, const int32_t *lookup,
-                           int32_t *scratch_counts, int32_t *out_rowptr, gnn_stream_t stream);
-int gnn_column_slice_fill(const int32_t *ucols, const int32_t *fullrowptr, int64_t M, const int32_t *lookup,
-                          const int32_t *rowptr, void *out_colidx, int colidx_bytes, gnn_stream_t stream);
+int64_t gnn_column_slice_chunks(int64_t total);
+int gnn_column_slice_count(const int32_t *ucols, int64_t total, const int32_t *fullrowptr, int64_t M, const int32_t *lookup,
+                           int32_t *chunk_prefix, int32_t *out_rowptr, gnn_stream_t stream);
+int gnn_column_slice_fill(const int32_t *ucols, int64_t total, const int32_t *lookup, const int32_t *chunk_prefix, void *out_colidx,
+                          int colidx_bytes, gnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Fused layer epilogue - the elementwise tail of every reference layer,

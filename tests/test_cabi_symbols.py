@@ -36,7 +36,7 @@ def test_header_symbols_exported(built):
 
 def test_abi_version_and_errors(built):
     lib = built.cabi()
-    assert lib.gnn_abi_version() == 3
+    assert lib.gnn_abi_version() == 4
     assert b"workspace" in lib.gnn_error_string(-2)
     assert lib.gnn_error_string(0) == b"success"
     # argument errors are reported before any CUDA call

@@ -1,6 +1,6 @@
 """Live-sampler training rate under a restricted core count, N sampler threads, sampler-stream priority.
 
-  python tools/live_probe.py "<cores>:<threads>:<priority>[:<blocking 0|1>]" ...     e.g. 4:4:0 4:4:-1 16:8:0
+  python tools/live_probe.py "<cores>:<threads>:<priority>[:<sync 0 spin|1 blocking|2 yield>]" ...     e.g. 4:4:0 4:4:-1 16:8:0
 
 One process, one graph: the configurations run back to back (the host-core restriction is sched_setaffinity on the
 whole process, set before the sampler pool of that configuration starts).  Also prints the sampler's own time per
@@ -39,6 +39,17 @@ for i, bn in enumerate(bns):
     torch.cuda.synchronize()
     ts.append(time.perf_counter() - t)
 print(f"sampler alone, idle GPU: median {np.median(ts[4:]) * 1e3:.2f} ms per minibatch (first calls {[round(x * 1e3, 1) for x in ts[:4]]})", flush=True)
+if os.environ.get("LIVE_PROBE_PROFILE"):
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    for i in range(8):
+        gpu_sampler.ladies_sample_device(3000 + i, bns[i], [samp] * 5, dg, bench.ORDERS, create_coo_tensor=cso.create_coo_tensor)
+    torch.cuda.synchronize()
+    pr.disable()
+    print("cProfile of 8 minibatches (sampler alone):")
+    pstats.Stats(pr).sort_stats('tottime').print_stats(22)
 del dg
 
 for spec in sys.argv[1:]:
@@ -50,9 +61,8 @@ for spec in sys.argv[1:]:
             os.sched_setaffinity(int(tid), all_cores[:cores])
         except OSError:
             pass
-    if blocking:
-        cso.spmm_cpp.set_blocking_sync(True)
+    cso.spmm_cpp.set_blocking_sync(blocking)      # 0 spin, 1 blocking, 2 yield
     r = harness.bench_train_live(args, cso, store, shape, g, bench.ORDERS, bench.NHID, samp, batch, device, 0, 1, log, pool_num=threads,
                                  fused=True, flat_grads=True, tc=True, sampler_stream_priority=prio)
     print(f"cores {len(os.sched_getaffinity(0))} threads {threads} priority {prio} blocking {blocking}: {r['minibatches_per_s']} minibatches/s, "
-          f"{r['ms_per_step_wall']} ms/step", flush=True)
+          f"{r['ms_per_step_wall']} ms/step over {r['steps']} steps; sampler job {r['sampler_job_ms']} ms, trainer waits {r['trainer_wait_ms_per_step']} ms/step", flush=True)
