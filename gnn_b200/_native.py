@@ -89,6 +89,8 @@ def cabi() -> ctypes.CDLL:
                 "gnn_linear_wgrad_tf32x3_f32": (ctypes.c_int, [vp, i64, vp, i64, vp, i64, i64, i64, vp, i64, vp, vp, sz, vp]),
                 "gnn_legacy_choice_f64": (ctypes.c_int, [vp, vp, i64, i64, vp]),
                 "gnn_ladies_layer_host": (i64, [vp, vp, vp, i64, vp, i64, ctypes.c_double, vp, i64, i64, vp, vp, vp, vp]),
+                "gnn_ladies_layer_host_ex": (i64, [vp, vp, vp, i64, vp, i64, vp, i64, ctypes.c_double, vp, i64, i64, vp, vp, vp, vp]),
+                "gnn_support_compact": (ctypes.c_int, [vp, i64, vp, vp, vp, vp, vp]),
                 "gnn_ladies_layer_host_dense": (i64, [vp, vp, i64, vp, i64, ctypes.c_double, vp, i64, i64, vp, vp, vp, vp, vp]),
                 "gnn_shard_alloc": (ctypes.c_int, [sz, ctypes.POINTER(vp), ctypes.c_char_p]),
                 "gnn_shard_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(vp)]),

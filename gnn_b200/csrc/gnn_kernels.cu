@@ -1049,6 +1049,61 @@ column_fill_kernel(const int *__restrict__ ucols, int total, const int *__restri
   }
 }
 
+// Support of the layer's column counts (the nodes that carry probability, sampler.py:117/124) compacted on the device:
+// (node id, count) pairs in ascending id order, written straight into pinned host memory (only the support crosses
+// PCIe, and the host does not scan num_nodes counters).  Same chunk-count / scan / fill scheme as the column slice.
+__global__ void __launch_bounds__(256)
+support_chunk_count_kernel(const int *__restrict__ counts, int64_t n, int *__restrict__ chunk_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int64_t chunks = (n + kSliceChunk - 1) / kSliceChunk;
+  for (int64_t c = blockIdx.x * wpb + (threadIdx.x >> 5); c < chunks; c += (int64_t)gridDim.x * wpb) {
+    const int64_t base = c * kSliceChunk;
+    int kept = 0;
+#pragma unroll 8
+    for (int q = 0; q < kSliceChunk / 32; ++q) {
+      const int64_t i = base + q * 32 + lane;
+      kept += (i < n && __ldg(counts + i) != 0) ? 1 : 0;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) kept += __shfl_xor_sync(kFull, kept, off);
+    if (lane == 0) chunk_cnt[c] = kept;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+support_fill_kernel(const int *__restrict__ counts, int64_t n, const int *__restrict__ chunk_prefix, int64_t *__restrict__ nz_out,
+                    int *__restrict__ cnt_out, int64_t *__restrict__ n_support_out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int64_t chunks = (n + kSliceChunk - 1) / kSliceChunk;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_support_out = __ldg(chunk_prefix + chunks);
+  for (int64_t c = blockIdx.x * wpb + (threadIdx.x >> 5); c < chunks; c += (int64_t)gridDim.x * wpb) {
+    const int64_t base = c * kSliceChunk;
+    int run = __ldg(chunk_prefix + c);
+    if (__ldg(chunk_prefix + c + 1) == run) continue;                        // nothing to write (sparse supports: most chunks)
+    for (int g = 0; g < kSliceChunk / 256; ++g) {
+      int v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int64_t i = base + g * 256 + q * 32 + lane;
+        v[q] = i < n ? __ldg(counts + i) : 0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const unsigned m = __ballot_sync(kFull, v[q] != 0);
+        if (v[q] != 0) {
+          const int o = run + __popc(m & lt);
+          nz_out[o] = base + g * 256 + q * 32 + lane;
+          cnt_out[o] = v[q];
+        }
+        run += __popc(m);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Fused layer epilogue: y = rownorm(elu(x)) * scale + offset of reference
 // models.py:21-25 / :61-64  (out = F.elu(feat); mean, var(unbiased=False)+1e-9; (out-mean)*scale*rsqrt(var)+offset).
@@ -1706,6 +1761,22 @@ int gnn_column_slice_fill(const int32_t *ucols, int64_t total, const int32_t *lo
   return 0;
 }
 
+int gnn_support_compact(const int32_t *counts, int64_t num_nodes, int32_t *chunk_scratch, int64_t *nz_out, int32_t *cnt_out,
+                        int64_t *n_support_out, gnn_stream_t stream) {
+  if (num_nodes <= 0 || !counts || !chunk_scratch || !nz_out || !cnt_out || !n_support_out) return GNN_E_BADARG;
+  const int64_t chunks = cdiv(num_nodes, kSliceChunk);
+  if (chunks >= (1ll << 31) - 2) return GNN_E_RANGE;
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t *chunk_cnt = chunk_scratch + chunks + 1;
+  support_chunk_count_kernel<<<warp_grid(chunks, 8), 256, 0, st>>>(counts, num_nodes, chunk_cnt);
+  GNN_LAUNCH_CHECK();
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(chunk_cnt, (int)chunks, chunk_scratch);
+  GNN_LAUNCH_CHECK();
+  support_fill_kernel<<<warp_grid(chunks, 8), 256, 0, st>>>(counts, num_nodes, chunk_scratch, nz_out, cnt_out, n_support_out);
+  GNN_LAUNCH_CHECK();
+  return 0;
+}
+
 size_t gnn_elu_rownorm_workspace_bytes(int64_t C) { return (size_t)2 * kEpiCtas * (size_t)(C > 0 ? C : 1) * sizeof(float); }
 
 int gnn_elu_rownorm_fwd_f32(const float *x, int64_t ldx, int64_t M, int64_t C, const float *scale, const float *offset,
@@ -2301,6 +2372,16 @@ int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32
                               int64_t *n_sampled) {
   return ladies_layer_host_impl(mt_state, nz, counts, n_nz, skew_nodes, n_skew, scale_factor, previous_nodes, n_prev, samp_num,
                                 after_nodes, normfact, sampled, n_sampled, nullptr, 0);
+}
+
+// Same with, optionally, the whole count array beside the compacted support (p[after_nodes] then needs no id -> position map)
+int64_t gnn_ladies_layer_host_ex(uint32_t *mt_state, const int64_t *nz, const int32_t *counts, int64_t n_nz,
+                                 const int32_t *counts_dense, int64_t num_nodes, const int64_t *skew_nodes, int64_t n_skew,
+                                 double scale_factor, const int64_t *previous_nodes, int64_t n_prev, int64_t samp_num,
+                                 int64_t *after_nodes, float *normfact, int64_t *sampled, int64_t *n_sampled) {
+  if (counts_dense && num_nodes <= 0) return GNN_E_BADARG;
+  return ladies_layer_host_impl(mt_state, nz, counts, n_nz, skew_nodes, n_skew, scale_factor, previous_nodes, n_prev, samp_num,
+                                after_nodes, normfact, sampled, n_sampled, counts_dense, counts_dense ? num_nodes : 0);
 }
 
 // Same, fed with the device sampler's whole count array (one D2H copy of num_nodes int32 into pinned memory instead of

@@ -394,15 +394,22 @@ torch::Tensor column_slice_fill(const torch::Tensor &ucols, const torch::Tensor 
 // after_nodes int64, sampled positions int64 [host]).
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> ladies_layer_device(
     const torch::Tensor &indptr, const torch::Tensor &indices, const torch::Tensor &indptr_host, torch::Tensor lookup,
-    torch::Tensor counts, torch::Tensor counts_host, torch::Tensor mt_state, const torch::Tensor &previous_nodes,
-    c10::optional<torch::Tensor> skew_nodes, double scale_factor, int64_t samp_num, bool int16_ids) {
+    torch::Tensor counts, c10::optional<torch::Tensor> counts_host_opt, torch::Tensor mt_state, const torch::Tensor &previous_nodes,
+    c10::optional<torch::Tensor> skew_nodes, double scale_factor, int64_t samp_num, bool int16_ids, int64_t device_compact_min_nodes) {
   CHECK_DENSE(indptr); CHECK_DENSE(indices); CHECK_DENSE(lookup); CHECK_DENSE(counts);
   TORCH_CHECK(indptr.scalar_type() == torch::kLong && indices.scalar_type() == torch::kInt, "indptr int64, indices int32");
   TORCH_CHECK(lookup.scalar_type() == torch::kInt && counts.scalar_type() == torch::kInt, "lookup / counts must be int32");
   TORCH_CHECK(!indptr_host.is_cuda() && indptr_host.scalar_type() == torch::kLong && indptr_host.is_contiguous() &&
               indptr_host.numel() == indptr.numel(), "indptr_host: the host copy of indptr (int64)");
-  TORCH_CHECK(!counts_host.is_cuda() && counts_host.is_pinned() && counts_host.scalar_type() == torch::kInt &&
-              counts_host.is_contiguous() && counts_host.numel() == counts.numel(), "counts_host: pinned int32 mirror of counts");
+  const bool have_dense = counts_host_opt.has_value() && counts_host_opt.value().defined();
+  const bool device_compact = counts.numel() >= device_compact_min_nodes;
+  TORCH_CHECK(have_dense || device_compact, "without a pinned mirror of the counts the support must be compacted on the device");
+  torch::Tensor counts_host;
+  if (have_dense) {
+    counts_host = counts_host_opt.value();
+    TORCH_CHECK(!counts_host.is_cuda() && counts_host.is_pinned() && counts_host.scalar_type() == torch::kInt &&
+                counts_host.is_contiguous() && counts_host.numel() == counts.numel(), "counts_host: pinned int32 mirror of counts");
+  }
   TORCH_CHECK(!mt_state.is_cuda() && mt_state.is_contiguous() && mt_state.numel() * mt_state.element_size() == 625 * 4,
               "mt_state: 625 32-bit words on the host");
   TORCH_CHECK(!previous_nodes.is_cuda() && previous_nodes.scalar_type() == torch::kLong && previous_nodes.is_contiguous(),
@@ -433,18 +440,45 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
   auto fullrowptr = row_slice_count(indptr, prev_dev);
   counts.zero_();
   auto ucols = row_slice_fill(indptr, indices, prev_dev, fullrowptr, total, counts);
-  counts_host.copy_(counts, /*non_blocking=*/true);
+  // the column counts come to the host: small graphs as the whole array (the native call compacts it in one pass); larger
+  // ones compacted by the device, (id, count) pairs written straight into pinned memory - only the support crosses PCIe
+  // and the host scans nothing - plus the whole array while it is small enough to be worth it (p[after_nodes] lookups)
+  torch::Tensor nz_pin, cnt_pin, nsup_pin, chunk_scratch;
+  if (device_compact) {
+    const int64_t sup_cap = std::max<int64_t>(std::min<int64_t>(N, total), 1);
+    nz_pin = torch::empty({sup_cap}, pinned(torch::kLong));
+    cnt_pin = torch::empty({sup_cap}, pinned(torch::kInt));
+    nsup_pin = torch::empty({1}, pinned(torch::kLong));
+    chunk_scratch = torch::empty({2 * gnn_column_slice_chunks(N) + 2}, counts.options());
+    void *d_nz = nullptr, *d_cnt = nullptr, *d_ns = nullptr;            // device-side addresses of the pinned blocks
+    TORCH_CHECK(cudaHostGetDevicePointer(&d_nz, nz_pin.data_ptr(), 0) == cudaSuccess &&
+                cudaHostGetDevicePointer(&d_cnt, cnt_pin.data_ptr(), 0) == cudaSuccess &&
+                cudaHostGetDevicePointer(&d_ns, nsup_pin.data_ptr(), 0) == cudaSuccess, "pinned memory is not device-accessible");
+    check_rc(gnn_support_compact(counts.data_ptr<int32_t>(), N, chunk_scratch.data_ptr<int32_t>(), (int64_t *)d_nz, (int32_t *)d_cnt,
+                                 (int64_t *)d_ns, cur_stream()),
+             "gnn_support_compact");
+  }
+  if (have_dense) counts_host.copy_(counts, /*non_blocking=*/true);
   TORCH_CHECK(cudaStreamSynchronize((cudaStream_t)cur_stream()) == cudaSuccess, "stream synchronise failed");
   // :117-143 on the host
   const int64_t cap = std::min<int64_t>(N, samp_num) + M;
   auto after_pin = torch::empty({cap}, pinned(torch::kLong));
   auto nf_pin = torch::empty({cap}, pinned(torch::kFloat));
   auto sampled = torch::empty({M}, torch::TensorOptions().dtype(torch::kLong));
-  int64_t n_sampled = 0, n_support = 0;
-  const int64_t n_after = gnn_ladies_layer_host_dense(reinterpret_cast<uint32_t *>(mt_state.data_ptr()), counts_host.data_ptr<int32_t>(), N,
-                                                      skew, n_skew, scale_factor, prev, M, samp_num, after_pin.data_ptr<int64_t>(),
-                                                      nf_pin.data_ptr<float>(), sampled.data_ptr<int64_t>(), &n_sampled, &n_support);
-  if (n_after < 0) check_rc((int)n_after, "gnn_ladies_layer_host_dense");
+  int64_t n_sampled = 0, n_support = 0, n_after = 0;
+  if (device_compact) {
+    n_support = nsup_pin.data_ptr<int64_t>()[0];
+    TORCH_CHECK(n_support > 0 && n_support <= nz_pin.numel(), "device support compaction returned ", n_support, " entries");
+    n_after = gnn_ladies_layer_host_ex(reinterpret_cast<uint32_t *>(mt_state.data_ptr()), nz_pin.data_ptr<int64_t>(),
+                                       cnt_pin.data_ptr<int32_t>(), n_support, have_dense ? counts_host.data_ptr<int32_t>() : nullptr, N,
+                                       skew, n_skew, scale_factor, prev, M, samp_num, after_pin.data_ptr<int64_t>(),
+                                       nf_pin.data_ptr<float>(), sampled.data_ptr<int64_t>(), &n_sampled);
+  } else {
+    n_after = gnn_ladies_layer_host_dense(reinterpret_cast<uint32_t *>(mt_state.data_ptr()), counts_host.data_ptr<int32_t>(), N,
+                                          skew, n_skew, scale_factor, prev, M, samp_num, after_pin.data_ptr<int64_t>(),
+                                          nf_pin.data_ptr<float>(), sampled.data_ptr<int64_t>(), &n_sampled, &n_support);
+  }
+  if (n_after < 0) check_rc((int)n_after, "gnn_ladies_layer_host");
   auto after_host = after_pin.narrow(0, 0, n_after);
   auto after_dev = after_host.to(dev, /*non_blocking=*/true);
   auto nf_dev = nf_pin.narrow(0, 0, n_after).to(dev, /*non_blocking=*/true);

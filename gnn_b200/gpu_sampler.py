@@ -47,7 +47,10 @@ class DeviceMinibatch:
     batch_nodes: np.ndarray
 
 
-DENSE_COUNTS_MAX = 1 << 22      # up to this many nodes the whole count array crosses PCIe (16 MiB) instead of being compacted
+DENSE_COUNTS_MAX = 1 << 22      # up to this many nodes the whole count array crosses PCIe (16 MiB) into pinned memory
+DEVICE_COMPACT_MIN_NODES = 1 << 20   # from this many nodes on the device compacts the support (gnn_support_compact): the
+                                     # host pass over every counter costs more than the extra kernels (measured: 4.7 ms
+                                     # per layer on a products-shaped graph, 0.1 ms on a Reddit-shaped one)
 
 
 def h2d(arr: np.ndarray, device) -> torch.Tensor:
@@ -177,8 +180,9 @@ def _sorted_skew_set(skewed_sampling_nodes, layer: int) -> np.ndarray:
     return hit[1]
 
 
-def host_layer_native(mt_state, nz, cnt, skew, scale_factor, previous_nodes, samp_num):
-    """gnn_ladies_layer_host through ctypes -> (after_nodes int64, normfact float32, sampled positions int64, s_num)."""
+def host_layer_native(mt_state, nz, cnt, skew, scale_factor, previous_nodes, samp_num, counts_dense=None):
+    """gnn_ladies_layer_host through ctypes -> (after_nodes int64, normfact float32, sampled positions int64, s_num).
+    With ``counts_dense`` (the count of every node id): gnn_ladies_layer_host_ex, same outputs."""
     import ctypes
     lib = _native.cabi()
     nz = np.ascontiguousarray(nz, dtype=np.int64)
@@ -192,10 +196,19 @@ def host_layer_native(mt_state, nz, cnt, skew, scale_factor, previous_nodes, sam
     n_sampled = ctypes.c_int64(0)
     vp = ctypes.c_void_p
     use_skew = skew is not None and scale_factor > 1
-    n_after = lib.gnn_ladies_layer_host(vp(mt_state.ctypes.data), vp(nz.ctypes.data), vp(cnt.ctypes.data), nz.size,
-                                        vp(skew.ctypes.data) if use_skew else None, skew.size if use_skew else 0,
-                                        float(scale_factor), vp(prev.ctypes.data), prev.size, int(samp_num), vp(after.ctypes.data),
-                                        vp(normfact.ctypes.data), vp(sampled.ctypes.data), ctypes.byref(n_sampled))
+    if counts_dense is not None:
+        dense = np.ascontiguousarray(counts_dense, dtype=np.int32)
+        n_after = lib.gnn_ladies_layer_host_ex(vp(mt_state.ctypes.data), vp(nz.ctypes.data), vp(cnt.ctypes.data), nz.size,
+                                               vp(dense.ctypes.data), dense.size,
+                                               vp(skew.ctypes.data) if use_skew else None, skew.size if use_skew else 0,
+                                               float(scale_factor), vp(prev.ctypes.data), prev.size, int(samp_num),
+                                               vp(after.ctypes.data), vp(normfact.ctypes.data), vp(sampled.ctypes.data),
+                                               ctypes.byref(n_sampled))
+    else:
+        n_after = lib.gnn_ladies_layer_host(vp(mt_state.ctypes.data), vp(nz.ctypes.data), vp(cnt.ctypes.data), nz.size,
+                                            vp(skew.ctypes.data) if use_skew else None, skew.size if use_skew else 0,
+                                            float(scale_factor), vp(prev.ctypes.data), prev.size, int(samp_num), vp(after.ctypes.data),
+                                            vp(normfact.ctypes.data), vp(sampled.ctypes.data), ctypes.byref(n_sampled))
     if n_after < 0:
         _native.check(int(n_after), "gnn_ladies_layer_host")
     return after[:n_after], normfact[:n_after], sampled[:n_sampled.value], s_num
@@ -275,11 +288,12 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
         skew = None
         if scale_factor > 1:                                                                # :119-121
             skew = _sorted_skew_set(skewed_sampling_nodes, len(orders1) - d - 1)
-        if one_call_layers and scratch.counts_host is not None and graph.indptr_host_t is not None:
+        if (one_call_layers and graph.indptr_host_t is not None and
+                (scratch.counts_host is not None or n >= DEVICE_COMPACT_MIN_NODES)):
             fullrowptr, rowptr, colidx, nf_dev, after_t, sampled_t = ext.ladies_layer_device(
                 graph.indptr, graph.indices, graph.indptr_host_t, scratch.lookup, scratch.counts, scratch.counts_host, mt_state_t,
                 torch.from_numpy(prev_np), torch.from_numpy(skew) if skew is not None else None, float(scale_factor),
-                int(samp_num_list[d]), bool(int16_ids))
+                int(samp_num_list[d]), bool(int16_ids), int(DEVICE_COMPACT_MIN_NODES))
             after_nodes = after_t.numpy()
             layer = DeviceLayer(fullrowptr, rowptr, colidx, nf_dev, int(prev_np.size), int(after_nodes.size))
             layers.append(layer)

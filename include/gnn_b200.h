@@ -273,6 +273,10 @@ int gnn_index_rows_f32(const float *X, int64_t ldx, const int64_t *idx, int64_t 
  *                        out_rowptr[M+1] (kept entries before every row; out_rowptr[M] = nnz); _fill writes the kept
  *                        entries renumbered to positions inside after_nodes, ascending within a row, as int16
  *                        (reference hand-off) or int32, from the same ucols / lookup / chunk_prefix.
+ * gnn_support_compact  : the support of the column counts (ids v with counts[v] != 0, sampler.py:117 / :124) as
+ *                        (nz_out[j] = v ascending, cnt_out[j] = counts[v]) and *n_support_out = their number; the three
+ *                        outputs may be pinned host memory (device-accessible pointers): only the support crosses
+ *                        PCIe.  chunk_scratch: int32 [2 * gnn_column_slice_chunks(num_nodes) + 2] on the device.
  * ------------------------------------------------------------------------- */
 int gnn_row_slice_count(const int64_t *indptr, const int64_t *nodes, int64_t M, int32_t *scratch_lens,
                         int32_t *out_fullrowptr, gnn_stream_t stream);
@@ -280,6 +284,8 @@ int gnn_row_slice_fill(const int64_t *indptr, const int32_t *indices, const int6
                        const int32_t *fullrowptr, int32_t *out_cols, int32_t *col_counts, gnn_stream_t stream);
 int gnn_lookup_set(int32_t *lookup, const int64_t *after_nodes, int64_t K, int set, gnn_stream_t stream);
 int64_t gnn_column_slice_chunks(int64_t total);
+int gnn_support_compact(const int32_t *counts, int64_t num_nodes, int32_t *chunk_scratch, int64_t *nz_out, int32_t *cnt_out,
+                        int64_t *n_support_out, gnn_stream_t stream);
 int gnn_column_slice_count(const int32_t *ucols, int64_t total, const int32_t *fullrowptr, int64_t M, const int32_t *lookup,
                            int32_t *chunk_prefix, int32_t *out_rowptr, gnn_stream_t stream);
 int gnn_column_slice_fill(const int32_t *ucols, int64_t total, const int32_t *lookup, const int32_t *chunk_prefix, void *out_colidx,
@@ -389,6 +395,14 @@ int64_t gnn_ladies_layer_host(uint32_t *mt_state, const int64_t *nz, const int32
                               const int64_t *skew_nodes, int64_t n_skew, double scale_factor, const int64_t *previous_nodes,
                               int64_t n_prev, int64_t samp_num, int64_t *after_nodes, float *normfact, int64_t *sampled,
                               int64_t *n_sampled);
+
+/* gnn_ladies_layer_host_ex - gnn_ladies_layer_host with, optionally, the whole column-count array (counts_dense[v] for every
+ * v < num_nodes, or NULL) beside the compacted support: p[after_nodes] is then read from it directly instead of through
+ * an id -> support-position map.  Same outputs. */
+int64_t gnn_ladies_layer_host_ex(uint32_t *mt_state, const int64_t *nz, const int32_t *counts, int64_t n_nz,
+                                 const int32_t *counts_dense, int64_t num_nodes, const int64_t *skew_nodes, int64_t n_skew,
+                                 double scale_factor, const int64_t *previous_nodes, int64_t n_prev, int64_t samp_num,
+                                 int64_t *after_nodes, float *normfact, int64_t *sampled, int64_t *n_sampled);
 
 /* gnn_ladies_layer_host_dense - the same call fed with the WHOLE column-count array of the layer (counts_dense[v] = how many
  * rows of U = lap_matrix[previous_nodes, :] hold column v, sampler.py:117 before any compaction; num_nodes entries, the

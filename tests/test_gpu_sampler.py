@@ -20,13 +20,16 @@ def gs():
     return gpu_sampler
 
 
-@pytest.mark.parametrize("one_call", [True, False], ids=["one_call_layers", "stepwise_layers"])
+@pytest.mark.parametrize("one_call", [True, "device_compact", False],
+                         ids=["one_call_layers", "one_call_device_compacted_support", "stepwise_layers"])
 @pytest.mark.parametrize("shape_name,orders,samp,batch,seeds", [
     ("small", [1, 1, 1], 2048, 256, [4321, 7]),
     ("tiny", [1, 0, 1], 64, 16, [11]),
     ("cora", [1, 1], 512, 256, [1234, 1235]),
 ])
-def test_device_sampler_bit_identical_to_host(gs, shape_name, orders, samp, batch, seeds, one_call):
+def test_device_sampler_bit_identical_to_host(gs, shape_name, orders, samp, batch, seeds, one_call, monkeypatch):
+    if one_call == "device_compact":      # the path graphs of a million nodes and more take: gnn_support_compact on the device
+        monkeypatch.setattr(gs, "DEVICE_COMPACT_MIN_NODES", 0)
     shape = graphgen.SHAPES[shape_name]
     g = graphgen.generate(shape, seed=0)
     dg = gs.DeviceGraph(g.indptr, g.indices, "cuda")
@@ -34,7 +37,7 @@ def test_device_sampler_bit_identical_to_host(gs, shape_name, orders, samp, batc
     for seed in seeds:
         bn = g.train_nodes[rng.permutation(g.train_nodes.size)[:batch]]
         ref = sampler.ladies_sample(seed, bn, [samp] * 5, shape.num_nodes, g.indptr, g.indices, orders)
-        got = gs.ladies_sample_device(seed, bn, [samp] * 5, dg, orders, one_call_layers=one_call)
+        got = gs.ladies_sample_device(seed, bn, [samp] * 5, dg, orders, one_call_layers=bool(one_call))
         assert np.array_equal(got.input_nodes, ref.input_nodes)
         assert len(got.layers) == len(ref.layers)
         for li, (a, b) in enumerate(zip(got.layers, ref.layers)):

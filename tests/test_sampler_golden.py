@@ -150,6 +150,7 @@ def test_native_host_layer_equals_the_numpy_expressions():
         rs = np.random.RandomState(100 + trial)
         state = gs.mt_state_of(np.random.RandomState(100 + trial))
         state_dense = state.copy()
+        state_ex = state.copy()
         previous = rng.choice(n_nodes, size=min(512, n_nodes // 2), replace=False)
         for layer in range(3):
             nz = np.sort(rng.choice(n_nodes, size=n_nz, replace=False)).astype(np.int64)
@@ -170,6 +171,11 @@ def test_native_host_layer_equals_the_numpy_expressions():
                     assert u.dtype == v.dtype and np.array_equal(u.view(np.uint8), v.view(np.uint8)), (trial, layer, "dense entry")
                 assert a[3] == c[3]
                 assert np.array_equal(state, state_dense)
+                # and the entry that takes the compacted support AND the whole array (device-compacted supports)
+                e = gs.host_layer_native(state_ex, nz, cnt, skew, scale, previous, samp, counts_dense=dense)
+                for u, v in zip(a[:3], e[:3]):
+                    assert u.dtype == v.dtype and np.array_equal(u.view(np.uint8), v.view(np.uint8)), (trial, layer, "ex entry")
+                assert np.array_equal(state, state_ex)
             previous = a[0]
         # the generator ends in the same state
         assert np.array_equal(state, gs.mt_state_of(rs))

@@ -65,4 +65,4 @@ for spec in sys.argv[1:]:
     r = harness.bench_train_live(args, cso, store, shape, g, bench.ORDERS, bench.NHID, samp, batch, device, 0, 1, log, pool_num=threads,
                                  fused=True, flat_grads=True, tc=True, sampler_stream_priority=prio)
     print(f"cores {len(os.sched_getaffinity(0))} threads {threads} priority {prio} blocking {blocking}: {r['minibatches_per_s']} minibatches/s, "
-          f"{r['ms_per_step_wall']} ms/step over {r['steps']} steps; sampler job {r['sampler_job_ms']} ms, trainer waits {r['trainer_wait_ms_per_step']} ms/step", flush=True)
+          f"{r['ms_per_step_wall']} ms/step over {r['steps']} steps; sampler job {r['sampler_job_ms']} ms, trainer waits {r['trainer_wait_ms_per_step']} ms/step, cudaMallocs {r['cuda_mallocs_in_timed_region']}, repeated {r['timed_region_repeated_after_allocator_growth']}", flush=True)
