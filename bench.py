@@ -1036,17 +1036,18 @@ def run_products_locality(args, cso, gmod, device, rank, world, flush_buf, log):
                     "parity_ok": bool(err_max <= GATE_TOL and gather_ok), "gather_bit_exact": gather_ok}
     out["sampling"] = src
     # GCN training with the device sampler in the loop, locality sampling on
+    pool = 4              # the reference's default --pool_num (main.py:77)
     try:
         targs = argparse.Namespace(steps=min(args.steps, 12))
         out["train_gcn_live_locality"] = harness.bench_train_live(targs, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log,
-                                                                   pool_num=4, fused=True, flat_grads=True, skewed_sampling_nodes=skew,
+                                                                   pool_num=pool, fused=True, flat_grads=True, skewed_sampling_nodes=skew,
                                                                    scale_factor=scale_factor)
     except Exception as exc:
         out["train_gcn_live_locality"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     try:                  # the same with the GCN layers' linears on the tensor cores (3xTF32)
         targs = argparse.Namespace(steps=min(args.steps, 12))
         out["train_gcn_live_locality_tensor_core_linears"] = harness.bench_train_live(
-            targs, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log, pool_num=4, fused=True, flat_grads=True,
+            targs, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log, pool_num=pool, fused=True, flat_grads=True,
             skewed_sampling_nodes=skew, scale_factor=scale_factor, tc=True)
     except Exception as exc:
         out["train_gcn_live_locality_tensor_core_linears"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}

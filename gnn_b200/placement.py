@@ -136,3 +136,33 @@ def locality_sampling_sets(indptr: np.ndarray, indices: np.ndarray, has_self_loo
         v = nxt
         sets.append(np.argsort(-1 * v)[:top])
     return sets
+
+
+class ScaleFactorController:
+    """The per-epoch adjustment of the locality-sampling ``scale_factor`` that the reference keeps - switched off, inside
+    a string literal - at main.py:200-212: while the input-feature movement takes a fifth or more of the epoch the factor
+    doubles (up to 16); once it falls under a tenth the factor settles halfway between the last two values; anything in
+    between ends the search.  Same branches, same order, same constants; ``update`` is called once per epoch with the
+    two times the reference accumulates (main.py:140-145 ``data_movement_time``, ``execution_time``) and returns the
+    factor for the next epoch's ``prepare_data`` calls (main.py:117)."""
+
+    def __init__(self, scale_factor: float = 1.0):
+        self.scale_factor = float(scale_factor)
+        self.factor_increase = True
+        self.factor_before = float(scale_factor)
+        self.factor_after = float(scale_factor)
+
+    def update(self, data_movement_time: float, execution_time: float) -> float:
+        if self.factor_increase:
+            ratio = data_movement_time / execution_time
+            if self.scale_factor >= 16:
+                self.factor_increase = False
+            elif ratio >= 0.2:
+                self.factor_before = self.scale_factor
+                self.scale_factor *= 2
+            elif ratio < 0.1 and self.scale_factor != 1:
+                self.factor_after = self.scale_factor
+                self.scale_factor = (self.factor_before + self.factor_after) / 2
+            else:
+                self.factor_increase = False
+        return self.scale_factor

@@ -50,3 +50,34 @@ def test_scaled_sampler_matches_reference(z, tag):
                 assert np.array_equal(getattr(layer, k), z[c + f"l{li}_{k}"]), (tag, ci, li, k)
             assert np.array_equal(layer.normfact.view(np.uint32), z[c + f"l{li}_normfact"].view(np.uint32)), (tag, ci, li)
             assert np.array_equal(mb.sampled_nodes[li], z[c + f"l{li}_sampled_nodes"])
+
+
+def test_scale_factor_controller_follows_the_reference_branches():
+    """placement.ScaleFactorController against a literal transcription of the (disabled) loop of reference main.py:200-212,
+    driven by the same sequences of (data movement, execution) times."""
+    from gnn_b200.placement import ScaleFactorController
+
+    def reference_trace(ratios, scale_factor=1.0):
+        factor_increase, factor_before, factor_after, out = True, scale_factor, scale_factor, []
+        for r in ratios:
+            if factor_increase == True:          # noqa: E712  (the reference's spelling)
+                if scale_factor >= 16:
+                    factor_increase = False
+                elif r >= 0.2:
+                    factor_before = scale_factor
+                    scale_factor *= 2
+                elif r < 0.1 and scale_factor != 1:
+                    factor_after = scale_factor
+                    scale_factor = (factor_before + factor_after) / 2
+                else:
+                    factor_increase = False
+            out.append(scale_factor)
+        return out
+
+    rng = np.random.Generator(np.random.PCG64(3))
+    cases = [[0.5, 0.4, 0.3, 0.05, 0.05, 0.3], [0.5] * 8, [0.05, 0.5], [0.15, 0.5], [0.3, 0.15, 0.5], [0.25, 0.25, 0.05, 0.05, 0.05]]
+    cases += [list(rng.uniform(0.0, 0.4, 10)) for _ in range(20)]
+    for ratios in cases:
+        c = ScaleFactorController(1.0)
+        got = [c.update(r * 7.0, 7.0) for r in ratios]
+        assert got == reference_trace(ratios), ratios
