@@ -124,6 +124,18 @@ class FeatureStore:
             self.check_all_resident(counts)
         return self.ext.gather_rows(xrows, self.feat_dim, self.ld)
 
+    def gather_co_running(self, input_nodes: torch.Tensor) -> torch.Tensor:
+        """:meth:`gather` for callers that run NEXT TO the training step's kernels (sampler threads): rows in HBM / on
+        peers by a full-size launch, host rows by the small PCIe-bound grid that :meth:`begin_co_running` reserved -
+        the same two launches :meth:`prefetch` issues, on the current stream.  Same bytes as :meth:`gather`."""
+        if self.host is None:
+            return self.gather(input_nodes)
+        src_dev, _, xrows, _ = self.remap(input_nodes)
+        buf = torch.empty((input_nodes.numel(), self.ld), dtype=torch.float32, device=self.device)
+        self.ext.gather_rows_src(xrows, src_dev, -100, self.feat_dim, buf)      # GNN_SRC_DEVICES: HBM / NVLink rows
+        self.ext.gather_rows_src(xrows, src_dev, -1, self.feat_dim, buf)        # host rows: small grid, PCIe-bound
+        return buf[:, :self.feat_dim]
+
     def begin_co_running(self):
         """Declare that host-row gathers of this store will run on side streams NEXT TO SpMMs (prefetch of the next
         minibatch): the SpMM planner then keeps the gather's CTA slots out of its one-wave grid

@@ -199,7 +199,7 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
 
 def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log, pool_num=4, fused=False,
                      prebuild_transpose=True, flat_grads=False, skewed_sampling_nodes=None, scale_factor=1.0, tc=False,
-                     sampler_stream_priority=0):
+                     sampler_stream_priority=0, co_split=True):
     """Training with the sampler IN the loop (BASELINE's second minibatches/s number): ``pool_num`` sampler threads
     (reference main.py:77 uses a ThreadPoolExecutor of --pool_num=4 per GPU) run the device LADIES sampler
     (gnn_b200/gpu_sampler.py: native legacy draw on the host, array passes on the GPU) and the feature gather on their own
@@ -249,7 +249,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
                                                   skewed_sampling_nodes=skewed_sampling_nodes, scale_factor=scale_factor)
             # pinned staging for every upload: a pageable source makes the copy synchronise the stream first
             nodes = gpu_sampler.h2d(mb.input_nodes, device)
-            x0 = store.gather(nodes)
+            x0 = store.gather_co_running(nodes) if co_split else store.gather(nodes)
             sn = [gpu_sampler.h2d(np.ascontiguousarray(s_, dtype=np.int64), device) for s_ in mb.sampled_nodes]
             y = F.one_hot(torch.from_numpy(labels_all[mb.batch_nodes]), shape.num_classes).float().pin_memory().to(device, non_blocking=True)
         tls.stream.synchronize()

@@ -1,6 +1,6 @@
 """Live-sampler training rate under a restricted core count, N sampler threads, sampler-stream priority.
 
-  python tools/live_probe.py "<cores>:<threads>:<priority>[:<sync 0 spin|1 blocking|2 yield>]" ...     e.g. 4:4:0 4:4:-1 16:8:0
+  python tools/live_probe.py "<cores>:<threads>:<priority>[:<sync 0 spin|1 blocking|2 yield>[:<split gather 0|1>]]" ...     e.g. 4:4:0 4:4:-1 16:8:0
 
 One process, one graph: the configurations run back to back (the host-core restriction is sched_setaffinity on the
 whole process, set before the sampler pool of that configuration starts).  Also prints the sampler's own time per
@@ -56,6 +56,7 @@ for spec in sys.argv[1:]:
     f = spec.split(':')
     cores, threads, prio = int(f[0]), int(f[1]), int(f[2])
     blocking = int(f[3]) if len(f) > 3 else 0
+    co_split = bool(int(f[4])) if len(f) > 4 else True
     for tid in os.listdir('/proc/self/task'):          # every existing thread (autograd engine, CUDA workers), new ones inherit
         try:
             os.sched_setaffinity(int(tid), all_cores[:cores])
@@ -63,6 +64,6 @@ for spec in sys.argv[1:]:
             pass
     cso.spmm_cpp.set_blocking_sync(blocking)      # 0 spin, 1 blocking, 2 yield
     r = harness.bench_train_live(args, cso, store, shape, g, bench.ORDERS, bench.NHID, samp, batch, device, 0, 1, log, pool_num=threads,
-                                 fused=True, flat_grads=True, tc=True, sampler_stream_priority=prio)
-    print(f"cores {len(os.sched_getaffinity(0))} threads {threads} priority {prio} blocking {blocking}: {r['minibatches_per_s']} minibatches/s, "
+                                 fused=True, flat_grads=True, tc=True, sampler_stream_priority=prio, co_split=co_split)
+    print(f"cores {len(os.sched_getaffinity(0))} threads {threads} priority {prio} blocking {blocking} split-gather {int(co_split)}: {r['minibatches_per_s']} minibatches/s, "
           f"{r['ms_per_step_wall']} ms/step over {r['steps']} steps; sampler job {r['sampler_job_ms']} ms, trainer waits {r['trainer_wait_ms_per_step']} ms/step, cudaMallocs {r['cuda_mallocs_in_timed_region']}, repeated {r['timed_region_repeated_after_allocator_growth']}", flush=True)
