@@ -73,10 +73,10 @@ def cabi() -> ctypes.CDLL:
                 "gnn_index_rows_f32": (ctypes.c_int, [vp, i64, vp, i64, i64, vp, i64, vp]),
                 "gnn_row_slice_count": (ctypes.c_int, [vp, vp, i64, vp, vp, vp]),
                 "gnn_row_slice_fill": (ctypes.c_int, [vp, vp, vp, i64, vp, vp, vp, vp]),
-                "gnn_lookup_set": (ctypes.c_int, [vp, vp, i64, ctypes.c_int, vp]),
+                "gnn_member_set": (ctypes.c_int, [vp, vp, vp, i64, ctypes.c_int, vp]),
                 "gnn_column_slice_chunks": (i64, [i64]),
                 "gnn_column_slice_count": (ctypes.c_int, [vp, i64, vp, i64, vp, vp, vp, vp]),
-                "gnn_column_slice_fill": (ctypes.c_int, [vp, i64, vp, vp, vp, ctypes.c_int, vp]),
+                "gnn_column_slice_fill": (ctypes.c_int, [vp, i64, vp, vp, vp, vp, ctypes.c_int, vp]),
                 "gnn_elu_rownorm_workspace_bytes": (sz, [i64]),
                 "gnn_elu_rownorm_fwd_f32": (ctypes.c_int, [vp, i64, i64, i64, vp, vp, vp, i64, vp, vp, vp]),
                 "gnn_elu_rownorm_bwd_f32": (ctypes.c_int, [vp, i64, vp, i64, i64, i64, vp, vp, vp, vp, i64, vp, vp, vp, sz, vp]),

@@ -956,23 +956,36 @@ row_slice_kernel(const int64_t *__restrict__ indptr, const int *__restrict__ ind
   }
 }
 
-__global__ void lookup_set_kernel(int *__restrict__ lookup, const int64_t *__restrict__ after_nodes, int K, int set) {
+// Membership of the sampled columns: one bit per node id plus, for every 32-bit word that holds a bit, the position of
+// its first member inside after_nodes (ascending, distinct: np.unique output).  The local column id of a kept entry is
+// rank0[word] + popcount(bits below it) - 4 bytes of tables per 32 node ids (58 KB on the Reddit shape: L1-resident)
+// instead of a 4-byte lookup word per node id gathered from L2 (one 32-byte sector per entry).
+__global__ void member_set_kernel(unsigned *__restrict__ bits, int *__restrict__ rank0, const int64_t *__restrict__ after_nodes,
+                                  int K, int set) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < K) lookup[after_nodes[j]] = set ? j : -1;
+  if (j >= K) return;
+  const int64_t v = after_nodes[j];
+  if (!set) { bits[v >> 5] = 0u; return; }                                  // (all writers of a word store the same zero)
+  atomicOr(bits + (v >> 5), 1u << (v & 31));
+  if (j == 0 || (after_nodes[j - 1] >> 5) != (v >> 5)) rank0[v >> 5] = j;
 }
 
-// adj = U[:, after_nodes] (structure): keep the entries whose column was sampled, renumbered by lookup.
+__device__ __forceinline__ bool is_member(const unsigned *__restrict__ bits, int c) {
+  return (__ldg(bits + (c >> 5)) >> (c & 31)) & 1u;
+}
+
+// adj = U[:, after_nodes] (structure): keep the entries whose column was sampled, renumbered to positions in after_nodes.
 // The rows of U lie one after the other in ucols and the kept entries keep their order, so the column slice is an
 // order-preserving stream compaction of the whole array; rowptr[r] is the number of kept entries before fullrowptr[r].
 // Entry-parallel in chunks of kSliceChunk entries per warp (balanced whatever the row lengths):
 //   column_chunk_count   kept entries per chunk              -> exclusive_scan_kernel -> chunk_prefix (its last entry: nnz)
 //   column_rowptr_kernel rowptr[r] = chunk_prefix[chunk of fullrowptr[r]] + kept entries of that chunk before it
-//   column_fill_kernel   colidx[chunk_prefix[c] + rank inside the chunk] = lookup value (ascending entries = ascending
+//   column_fill_kernel   colidx[chunk_prefix[c] + rank inside the chunk] = local column id (ascending entries = ascending
 //                        positions: the same order as the reference's row-wise slice)
 constexpr int kSliceChunk = 1024;    // entries per warp chunk (32 steps of 32)
 
 __global__ void __launch_bounds__(256)
-column_chunk_count_kernel(const int *__restrict__ ucols, int total, const int *__restrict__ lookup, int *__restrict__ chunk_cnt) {
+column_chunk_count_kernel(const int *__restrict__ ucols, int total, const unsigned *__restrict__ bits, int *__restrict__ chunk_cnt) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int chunks = (total + kSliceChunk - 1) / kSliceChunk;
@@ -988,7 +1001,7 @@ column_chunk_count_kernel(const int *__restrict__ ucols, int total, const int *_
         col[q] = i < total ? __ldg(ucols + i) : -1;
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) kept += (col[q] >= 0 && __ldg(lookup + col[q]) >= 0) ? 1 : 0;
+      for (int q = 0; q < 8; ++q) kept += (col[q] >= 0 && is_member(bits, col[q])) ? 1 : 0;
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) kept += __shfl_xor_sync(kFull, kept, off);
@@ -999,7 +1012,7 @@ column_chunk_count_kernel(const int *__restrict__ ucols, int total, const int *_
 // one warp per row r in [0, M]; chunk_prefix holds chunks + 1 entries
 __global__ void __launch_bounds__(256)
 column_rowptr_kernel(const int *__restrict__ ucols, int total, const int *__restrict__ fullrowptr, int M,
-                     const int *__restrict__ lookup, const int *__restrict__ chunk_prefix, int *__restrict__ rowptr) {
+                     const unsigned *__restrict__ bits, const int *__restrict__ chunk_prefix, int *__restrict__ rowptr) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int chunks = (total + kSliceChunk - 1) / kSliceChunk;
@@ -1011,7 +1024,7 @@ column_rowptr_kernel(const int *__restrict__ ucols, int total, const int *__rest
     }
     const int c = e0 / kSliceChunk;
     int kept = 0;
-    for (int i = c * kSliceChunk + lane; i < e0; i += 32) kept += __ldg(lookup + __ldg(ucols + i)) >= 0 ? 1 : 0;
+    for (int i = c * kSliceChunk + lane; i < e0; i += 32) kept += is_member(bits, __ldg(ucols + i)) ? 1 : 0;
 #pragma unroll
     for (int off = 16; off; off >>= 1) kept += __shfl_xor_sync(kFull, kept, off);
     if (lane == 0) rowptr[r] = __ldg(chunk_prefix + c) + kept;
@@ -1020,8 +1033,8 @@ column_rowptr_kernel(const int *__restrict__ ucols, int total, const int *__rest
 
 template <typename ColT>
 __global__ void __launch_bounds__(256)
-column_fill_kernel(const int *__restrict__ ucols, int total, const int *__restrict__ lookup, const int *__restrict__ chunk_prefix,
-                   ColT *__restrict__ colidx) {
+column_fill_kernel(const int *__restrict__ ucols, int total, const unsigned *__restrict__ bits, const int *__restrict__ rank0,
+                   const int *__restrict__ chunk_prefix, ColT *__restrict__ colidx) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
@@ -1038,7 +1051,13 @@ column_fill_kernel(const int *__restrict__ ucols, int total, const int *__restri
         local[q] = i < total ? __ldg(ucols + i) : -1;
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) local[q] = local[q] >= 0 ? __ldg(lookup + local[q]) : -1;
+      for (int q = 0; q < 8; ++q) {
+        const int c = local[q];
+        if (c >= 0) {
+          const unsigned w = __ldg(bits + (c >> 5)), b = 1u << (c & 31);
+          local[q] = (w & b) ? __ldg(rank0 + (c >> 5)) + __popc(w & (b - 1u)) : -1;
+        }
+      }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const unsigned m = __ballot_sync(kFull, local[q] >= 0);
@@ -1712,22 +1731,22 @@ int gnn_row_slice_fill(const int64_t *indptr, const int32_t *indices, const int6
   return 0;
 }
 
-int gnn_lookup_set(int32_t *lookup, const int64_t *after_nodes, int64_t K, int set, gnn_stream_t stream) {
+int gnn_member_set(uint32_t *bits, int32_t *rank0, const int64_t *after_nodes, int64_t K, int set, gnn_stream_t stream) {
   if (K < 0 || K >= (1ll << 31)) return GNN_E_BADARG;
   if (K == 0) return 0;
-  if (!lookup || !after_nodes) return GNN_E_BADARG;
-  lookup_set_kernel<<<(unsigned)cdiv(K, 256), 256, 0, (cudaStream_t)stream>>>(lookup, after_nodes, (int)K, set);
+  if (!bits || !rank0 || !after_nodes) return GNN_E_BADARG;
+  member_set_kernel<<<(unsigned)cdiv(K, 256), 256, 0, (cudaStream_t)stream>>>(bits, rank0, after_nodes, (int)K, set);
   GNN_LAUNCH_CHECK();
   return 0;
 }
 
 int64_t gnn_column_slice_chunks(int64_t total) { return total > 0 ? cdiv(total, kSliceChunk) : 0; }
 
-int gnn_column_slice_count(const int32_t *ucols, int64_t total, const int32_t *fullrowptr, int64_t M, const int32_t *lookup,
+int gnn_column_slice_count(const int32_t *ucols, int64_t total, const int32_t *fullrowptr, int64_t M, const uint32_t *bits,
                            int32_t *chunk_prefix, int32_t *out_rowptr, gnn_stream_t stream) {
   if (M < 0 || total < 0) return GNN_E_BADARG;
   if (total >= (1ll << 31) - kSliceChunk || M >= (1ll << 31) - 1) return GNN_E_RANGE;
-  if (!out_rowptr || !chunk_prefix || (M > 0 && !fullrowptr) || (total > 0 && (!ucols || !lookup))) return GNN_E_BADARG;
+  if (!out_rowptr || !chunk_prefix || (M > 0 && !fullrowptr) || (total > 0 && (!ucols || !bits))) return GNN_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t chunks = gnn_column_slice_chunks(total);
   if (chunks == 0) {
@@ -1736,27 +1755,27 @@ int gnn_column_slice_count(const int32_t *ucols, int64_t total, const int32_t *f
     return 0;
   }
   int32_t *chunk_cnt = chunk_prefix + chunks + 1;                                           // second half of the scratch
-  column_chunk_count_kernel<<<warp_grid(chunks, 8), 256, 0, st>>>(ucols, (int)total, lookup, chunk_cnt);
+  column_chunk_count_kernel<<<warp_grid(chunks, 8), 256, 0, st>>>(ucols, (int)total, bits, chunk_cnt);
   GNN_LAUNCH_CHECK();
   exclusive_scan_kernel<<<1, 1024, 0, st>>>(chunk_cnt, (int)chunks, chunk_prefix);
   GNN_LAUNCH_CHECK();
-  column_rowptr_kernel<<<warp_grid(M + 1, 8), 256, 0, st>>>(ucols, (int)total, fullrowptr, (int)M, lookup, chunk_prefix, out_rowptr);
+  column_rowptr_kernel<<<warp_grid(M + 1, 8), 256, 0, st>>>(ucols, (int)total, fullrowptr, (int)M, bits, chunk_prefix, out_rowptr);
   GNN_LAUNCH_CHECK();
   return 0;
 }
 
-int gnn_column_slice_fill(const int32_t *ucols, int64_t total, const int32_t *lookup, const int32_t *chunk_prefix, void *out_colidx,
-                          int colidx_bytes, gnn_stream_t stream) {
+int gnn_column_slice_fill(const int32_t *ucols, int64_t total, const uint32_t *bits, const int32_t *rank0, const int32_t *chunk_prefix,
+                          void *out_colidx, int colidx_bytes, gnn_stream_t stream) {
   if (total < 0 || (colidx_bytes != 2 && colidx_bytes != 4)) return GNN_E_BADARG;
   if (total >= (1ll << 31) - kSliceChunk) return GNN_E_RANGE;
   if (total == 0) return 0;
-  if (!ucols || !lookup || !chunk_prefix || !out_colidx) return GNN_E_BADARG;
+  if (!ucols || !bits || !rank0 || !chunk_prefix || !out_colidx) return GNN_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = warp_grid(gnn_column_slice_chunks(total), 8);
   if (colidx_bytes == 2)
-    column_fill_kernel<int16_t><<<grid, 256, 0, st>>>(ucols, (int)total, lookup, chunk_prefix, (int16_t *)out_colidx);
+    column_fill_kernel<int16_t><<<grid, 256, 0, st>>>(ucols, (int)total, bits, rank0, chunk_prefix, (int16_t *)out_colidx);
   else
-    column_fill_kernel<int><<<grid, 256, 0, st>>>(ucols, (int)total, lookup, chunk_prefix, (int *)out_colidx);
+    column_fill_kernel<int><<<grid, 256, 0, st>>>(ucols, (int)total, bits, rank0, chunk_prefix, (int *)out_colidx);
   GNN_LAUNCH_CHECK();
   return 0;
 }

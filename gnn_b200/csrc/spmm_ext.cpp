@@ -349,38 +349,44 @@ torch::Tensor row_slice_fill(const torch::Tensor &indptr, const torch::Tensor &i
   return ucols;
 }
 
-void lookup_set(torch::Tensor lookup, const torch::Tensor &after_nodes, bool set) {
-  CHECK_DENSE(lookup); CHECK_DENSE(after_nodes);
-  TORCH_CHECK(lookup.scalar_type() == torch::kInt && after_nodes.scalar_type() == torch::kLong, "lookup int32, after_nodes int64");
-  c10::cuda::CUDAGuard g(lookup.device());
-  check_rc(gnn_lookup_set(lookup.data_ptr<int32_t>(), after_nodes.data_ptr<int64_t>(), after_nodes.numel(), set ? 1 : 0, cur_stream()),
-           "gnn_lookup_set");
+void member_set(torch::Tensor bits, torch::Tensor rank0, const torch::Tensor &after_nodes, bool set) {
+  CHECK_DENSE(bits); CHECK_DENSE(rank0); CHECK_DENSE(after_nodes);
+  TORCH_CHECK(bits.scalar_type() == torch::kInt && rank0.scalar_type() == torch::kInt && bits.numel() == rank0.numel() &&
+              after_nodes.scalar_type() == torch::kLong, "bits / rank0 int32 [ceil(N/32)], after_nodes int64");
+  c10::cuda::CUDAGuard g(bits.device());
+  check_rc(gnn_member_set(reinterpret_cast<uint32_t *>(bits.data_ptr<int32_t>()), rank0.data_ptr<int32_t>(),
+                          after_nodes.data_ptr<int64_t>(), after_nodes.numel(), set ? 1 : 0, cur_stream()),
+           "gnn_member_set");
 }
 
 // -> (rowptr int32 [M+1], chunk_prefix scratch for column_slice_fill)
 std::tuple<torch::Tensor, torch::Tensor> column_slice_count(const torch::Tensor &ucols, const torch::Tensor &fullrowptr,
-                                                            const torch::Tensor &lookup) {
-  CHECK_DENSE(ucols); CHECK_DENSE(fullrowptr); CHECK_DENSE(lookup);
-  TORCH_CHECK(ucols.scalar_type() == torch::kInt && fullrowptr.scalar_type() == torch::kInt && lookup.scalar_type() == torch::kInt,
-              "ucols / fullrowptr / lookup must be int32");
+                                                            const torch::Tensor &bits) {
+  CHECK_DENSE(ucols); CHECK_DENSE(fullrowptr); CHECK_DENSE(bits);
+  TORCH_CHECK(ucols.scalar_type() == torch::kInt && fullrowptr.scalar_type() == torch::kInt && bits.scalar_type() == torch::kInt,
+              "ucols / fullrowptr / bits must be int32");
   c10::cuda::CUDAGuard g(ucols.device());
   const int64_t M = fullrowptr.numel() - 1, total = ucols.numel();
   auto chunk_prefix = torch::empty({2 * gnn_column_slice_chunks(total) + 2}, fullrowptr.options());
   auto rowptr = torch::empty({M + 1}, fullrowptr.options());
-  check_rc(gnn_column_slice_count(ucols.data_ptr<int32_t>(), total, fullrowptr.data_ptr<int32_t>(), M, lookup.data_ptr<int32_t>(),
-                                  chunk_prefix.data_ptr<int32_t>(), rowptr.data_ptr<int32_t>(), cur_stream()),
+  check_rc(gnn_column_slice_count(ucols.data_ptr<int32_t>(), total, fullrowptr.data_ptr<int32_t>(), M,
+                                  reinterpret_cast<const uint32_t *>(bits.data_ptr<int32_t>()), chunk_prefix.data_ptr<int32_t>(),
+                                  rowptr.data_ptr<int32_t>(), cur_stream()),
            "gnn_column_slice_count");
   return {rowptr, chunk_prefix};
 }
 
-torch::Tensor column_slice_fill(const torch::Tensor &ucols, const torch::Tensor &lookup, const torch::Tensor &chunk_prefix,
-                                int64_t nnz, bool int16_ids) {
-  CHECK_DENSE(ucols); CHECK_DENSE(lookup); CHECK_DENSE(chunk_prefix);
+torch::Tensor column_slice_fill(const torch::Tensor &ucols, const torch::Tensor &bits, const torch::Tensor &rank0,
+                                const torch::Tensor &chunk_prefix, int64_t nnz, bool int16_ids) {
+  CHECK_DENSE(ucols); CHECK_DENSE(bits); CHECK_DENSE(rank0); CHECK_DENSE(chunk_prefix);
+  TORCH_CHECK(bits.scalar_type() == torch::kInt && rank0.scalar_type() == torch::kInt && bits.numel() == rank0.numel(),
+              "bits / rank0 must be int32 tables of the same size");
   TORCH_CHECK(chunk_prefix.numel() == 2 * gnn_column_slice_chunks(ucols.numel()) + 2, "chunk_prefix does not belong to ucols");
   c10::cuda::CUDAGuard g(ucols.device());
   auto colidx = torch::empty({nnz}, ucols.options().dtype(int16_ids ? torch::kShort : torch::kInt));
-  check_rc(gnn_column_slice_fill(ucols.data_ptr<int32_t>(), ucols.numel(), lookup.data_ptr<int32_t>(), chunk_prefix.data_ptr<int32_t>(),
-                                 colidx.data_ptr(), int16_ids ? 2 : 4, cur_stream()),
+  check_rc(gnn_column_slice_fill(ucols.data_ptr<int32_t>(), ucols.numel(), reinterpret_cast<const uint32_t *>(bits.data_ptr<int32_t>()),
+                                 rank0.data_ptr<int32_t>(), chunk_prefix.data_ptr<int32_t>(), colidx.data_ptr(), int16_ids ? 2 : 4,
+                                 cur_stream()),
            "gnn_column_slice_fill");
   return colidx;
 }
@@ -393,12 +399,14 @@ torch::Tensor column_slice_fill(const torch::Tensor &ucols, const torch::Tensor 
 // Two stream synchronisations (counts, kept count).  Returns (fullrowptr, rowptr, colidx, normfact [device],
 // after_nodes int64, sampled positions int64 [host]).
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> ladies_layer_device(
-    const torch::Tensor &indptr, const torch::Tensor &indices, const torch::Tensor &indptr_host, torch::Tensor lookup,
-    torch::Tensor counts, c10::optional<torch::Tensor> counts_host_opt, torch::Tensor mt_state, const torch::Tensor &previous_nodes,
+    const torch::Tensor &indptr, const torch::Tensor &indices, const torch::Tensor &indptr_host, torch::Tensor bits,
+    torch::Tensor rank0, torch::Tensor counts, c10::optional<torch::Tensor> counts_host_opt, torch::Tensor mt_state, const torch::Tensor &previous_nodes,
     c10::optional<torch::Tensor> skew_nodes, double scale_factor, int64_t samp_num, bool int16_ids, int64_t device_compact_min_nodes) {
-  CHECK_DENSE(indptr); CHECK_DENSE(indices); CHECK_DENSE(lookup); CHECK_DENSE(counts);
+  CHECK_DENSE(indptr); CHECK_DENSE(indices); CHECK_DENSE(bits); CHECK_DENSE(rank0); CHECK_DENSE(counts);
   TORCH_CHECK(indptr.scalar_type() == torch::kLong && indices.scalar_type() == torch::kInt, "indptr int64, indices int32");
-  TORCH_CHECK(lookup.scalar_type() == torch::kInt && counts.scalar_type() == torch::kInt, "lookup / counts must be int32");
+  TORCH_CHECK(bits.scalar_type() == torch::kInt && rank0.scalar_type() == torch::kInt && counts.scalar_type() == torch::kInt,
+              "bits / rank0 / counts must be int32");
+  TORCH_CHECK(bits.numel() == (counts.numel() + 31) / 32 && rank0.numel() == bits.numel(), "bits / rank0: ceil(N / 32) words");
   TORCH_CHECK(!indptr_host.is_cuda() && indptr_host.scalar_type() == torch::kLong && indptr_host.is_contiguous() &&
               indptr_host.numel() == indptr.numel(), "indptr_host: the host copy of indptr (int64)");
   const bool have_dense = counts_host_opt.has_value() && counts_host_opt.value().defined();
@@ -483,18 +491,18 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
   auto after_dev = after_host.to(dev, /*non_blocking=*/true);
   auto nf_dev = nf_pin.narrow(0, 0, n_after).to(dev, /*non_blocking=*/true);
   // adj = U[:, after_nodes]  (:133-136)
-  lookup_set(lookup, after_dev, true);
+  member_set(bits, rank0, after_dev, true);
   torch::Tensor rowptr, colidx;
   try {
     torch::Tensor chunk_prefix;
-    std::tie(rowptr, chunk_prefix) = column_slice_count(ucols, fullrowptr, lookup);
+    std::tie(rowptr, chunk_prefix) = column_slice_count(ucols, fullrowptr, bits);
     const int64_t nnz = rowptr[M].item<int32_t>();
-    colidx = column_slice_fill(ucols, lookup, chunk_prefix, nnz, int16_ids && n_after <= 32768);
+    colidx = column_slice_fill(ucols, bits, rank0, chunk_prefix, nnz, int16_ids && n_after <= 32768);
   } catch (...) {
-    lookup_set(lookup, after_dev, false);      // the table must be all -1 for the next minibatch, whatever happened
+    member_set(bits, rank0, after_dev, false);      // the bitmap must be all zero for the next minibatch, whatever happened
     throw;
   }
-  lookup_set(lookup, after_dev, false);
+  member_set(bits, rank0, after_dev, false);
   return {fullrowptr, rowptr, colidx, nf_dev, after_host, sampled.narrow(0, 0, n_sampled)};
 }
 
@@ -691,7 +699,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("index_rows", &index_rows, "out[i] = X[idx[i]]", rel());
   m.def("row_slice_count", &row_slice_count, "fullrowptr of lap_matrix[nodes, :]", rel());
   m.def("row_slice_fill", &row_slice_fill, "column ids of lap_matrix[nodes, :] (+ column counts)", rel());
-  m.def("lookup_set", &lookup_set, "lookup[after_nodes[j]] = j or -1", rel());
+  m.def("member_set", &member_set, "membership bitmap + word ranks of after_nodes (set) / cleared again (unset)", rel());
   m.def("column_slice_count", &column_slice_count, "rowptr of U[:, after_nodes]", rel());
   m.def("column_slice_fill", &column_slice_fill, "local column ids of U[:, after_nodes]", rel());
   m.def("ladies_layer_device", &ladies_layer_device, "one LADIES layer: device passes + host draw + uploads, GIL released", rel());

@@ -7,7 +7,7 @@ own expression).  What moves to the GPU are the passes that cost the reference ~
 
     U = lap_matrix[previous_nodes, :]          (sampler.py:113)   gnn_row_slice_count / _fill
     pi = sp.linalg.norm(U, ord=0, axis=0)      (sampler.py:117)   column counts, fused into the fill pass
-    adj = U[:, after_nodes]                    (sampler.py:133)   gnn_lookup_set + gnn_column_slice_count / _fill (stream compaction)
+    adj = U[:, after_nodes]                    (sampler.py:133)   gnn_member_set + gnn_column_slice_count / _fill (stream compaction)
     create_coo_tensor(...)                     (sampler.py:139)   gnn_build_adj (unchanged)
 
 Two D2H reads per layer synchronise the stream (the column counts - the whole array into pinned memory when the graph
@@ -63,10 +63,13 @@ def h2d(arr: np.ndarray, device) -> torch.Tensor:
 
 
 class SamplerScratch:
-    """Per-caller scratch tables (one per sampler thread): column lookup (-1 between uses), column counts and, for
-    graphs of at most DENSE_COUNTS_MAX nodes, the pinned host mirror of the counts."""
+    """Per-caller scratch tables (one per sampler thread): membership bitmap of the sampled columns (all zero between
+    uses) with its word ranks (gnn_member_set), column counts and, for graphs of at most DENSE_COUNTS_MAX nodes, the pinned
+    host mirror of the counts."""
     def __init__(self, num_nodes: int, device):
-        self.lookup = torch.full((num_nodes,), -1, dtype=torch.int32, device=device)
+        words = (num_nodes + 31) // 32
+        self.member_bits = torch.zeros(words, dtype=torch.int32, device=device)
+        self.member_rank0 = torch.zeros(words, dtype=torch.int32, device=device)
         self.counts = torch.zeros(num_nodes, dtype=torch.int32, device=device)
         self.counts_host = None
         if num_nodes <= DENSE_COUNTS_MAX:
@@ -90,8 +93,8 @@ class DeviceGraph:
         return SamplerScratch(self.num_nodes, self.device)
 
     @property
-    def lookup(self):
-        return self.default_scratch().lookup
+    def member_bits(self):
+        return self.default_scratch().member_bits
 
     def default_scratch(self) -> SamplerScratch:
         if self._default_scratch is None:
@@ -291,7 +294,8 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
         if (one_call_layers and graph.indptr_host_t is not None and
                 (scratch.counts_host is not None or n >= DEVICE_COMPACT_MIN_NODES)):
             fullrowptr, rowptr, colidx, nf_dev, after_t, sampled_t = ext.ladies_layer_device(
-                graph.indptr, graph.indices, graph.indptr_host_t, scratch.lookup, scratch.counts, scratch.counts_host, mt_state_t,
+                graph.indptr, graph.indices, graph.indptr_host_t, scratch.member_bits, scratch.member_rank0, scratch.counts,
+                scratch.counts_host, mt_state_t,
                 torch.from_numpy(prev_np), torch.from_numpy(skew) if skew is not None else None, float(scale_factor),
                 int(samp_num_list[d]), bool(int16_ids), int(DEVICE_COMPACT_MIN_NODES))
             after_nodes = after_t.numpy()
@@ -324,14 +328,14 @@ def ladies_sample_device(seed: int, batch_nodes, samp_num_list: Sequence[int], g
             after_nodes, normfact, sampled_pos, s_num = host_layer_native(mt_state, nz, cnt, skew, scale_factor, prev_np,
                                                                            int(samp_num_list[d]))
         after_dev = h2d(after_nodes, dev)
-        ext.lookup_set(scratch.lookup, after_dev, True)
+        ext.member_set(scratch.member_bits, scratch.member_rank0, after_dev, True)
         try:
-            rowptr, chunk_prefix = ext.column_slice_count(ucols, fullrowptr, scratch.lookup)  # :133,135
+            rowptr, chunk_prefix = ext.column_slice_count(ucols, fullrowptr, scratch.member_bits)  # :133,135
             nnz = int(rowptr[-1].item())
             use16 = int16_ids and after_nodes.size <= 32768
-            colidx = ext.column_slice_fill(ucols, scratch.lookup, chunk_prefix, nnz, use16)   # :136
+            colidx = ext.column_slice_fill(ucols, scratch.member_bits, scratch.member_rank0, chunk_prefix, nnz, use16)   # :136
         finally:
-            ext.lookup_set(scratch.lookup, after_dev, False)      # the table must be all -1 for the next minibatch, whatever happened
+            ext.member_set(scratch.member_bits, scratch.member_rank0, after_dev, False)   # all zero again for the next minibatch, whatever happened
         nf_dev = h2d(normfact, dev)
         layer = DeviceLayer(fullrowptr, rowptr, colidx, nf_dev, int(previous_nodes.size), int(after_nodes.size))
         layers.append(layer)

@@ -15,6 +15,7 @@ here with the same math, only to drive the hot path in its real calling pattern:
 from __future__ import annotations
 
 import gc
+import os
 import time
 
 import numpy as np
@@ -260,6 +261,11 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         job_s[1] += 1
         return mb, x0, sn, y
 
+    # GNN_B200_SYNC_MODE: how host threads wait in a stream synchronise (0 spin = CUDA default, 1 blocking, 2 spin + yield);
+    # an experiment switch - see profiles/README.md for what was measured
+    sync_mode = os.environ.get("GNN_B200_SYNC_MODE")
+    if sync_mode is not None:
+        cso.spmm_cpp.set_blocking_sync(int(sync_mode))
     model.train()
     pool = ThreadPoolExecutor(max_workers=pool_num)
     pending = collections.deque()

@@ -263,8 +263,12 @@ int gnn_index_rows_f32(const float *X, int64_t ldx, const int64_t *idx, int64_t 
  * gnn_row_slice_fill   : column ids of every selected row into out_cols[fullrowptr[M]]; when col_counts != NULL
  *                        also col_counts[c] += 1 per entry = sp.linalg.norm(U, ord=0, axis=0) (sampler.py:117);
  *                        col_counts must be zero on entry.
- * gnn_lookup_set       : lookup[after_nodes[j]] = j (set != 0) or -1 (set == 0) for j < K; lookup is int32 [N],
- *                        -1 everywhere between uses.
+ * gnn_member_set       : membership tables of after_nodes (ASCENDING and distinct: np.unique output, sampler.py:131) over
+ *                        the node ids: bits[v >> 5] bit (v & 31) set for every member v, rank0[w] = position inside
+ *                        after_nodes of the first member of word w (written only for words that hold a member);
+ *                        set == 0 clears the words again.  bits: uint32 [ceil(N / 32)], all zero between uses;
+ *                        rank0: int32 [ceil(N / 32)].  The local column id of node v is
+ *                        rank0[v >> 5] + popcount(bits[v >> 5] & ((1 << (v & 31)) - 1)).
  * gnn_column_slice_count / _fill : adj = U[:, after_nodes] (sampler.py:133-136).  The rows of U lie one after the other
  *                        in ucols[total] and kept entries keep their order, so the slice is an order-preserving stream
  *                        compaction over the whole array, done in chunks of entries (balanced whatever the row lengths):
@@ -272,7 +276,7 @@ int gnn_index_rows_f32(const float *X, int64_t ldx, const int64_t *idx, int64_t 
  *                        chunks + 1 entries = kept entries before each chunk, the last of them = nnz) and
  *                        out_rowptr[M+1] (kept entries before every row; out_rowptr[M] = nnz); _fill writes the kept
  *                        entries renumbered to positions inside after_nodes, ascending within a row, as int16
- *                        (reference hand-off) or int32, from the same ucols / lookup / chunk_prefix.
+ *                        (reference hand-off) or int32, from the same ucols / membership tables / chunk_prefix.
  * gnn_support_compact  : the support of the column counts (ids v with counts[v] != 0, sampler.py:117 / :124) as
  *                        (nz_out[j] = v ascending, cnt_out[j] = counts[v]) and *n_support_out = their number; the three
  *                        outputs may be pinned host memory (device-accessible pointers): only the support crosses
@@ -282,14 +286,14 @@ int gnn_row_slice_count(const int64_t *indptr, const int64_t *nodes, int64_t M, 
                         int32_t *out_fullrowptr, gnn_stream_t stream);
 int gnn_row_slice_fill(const int64_t *indptr, const int32_t *indices, const int64_t *nodes, int64_t M,
                        const int32_t *fullrowptr, int32_t *out_cols, int32_t *col_counts, gnn_stream_t stream);
-int gnn_lookup_set(int32_t *lookup, const int64_t *after_nodes, int64_t K, int set, gnn_stream_t stream);
+int gnn_member_set(uint32_t *bits, int32_t *rank0, const int64_t *after_nodes, int64_t K, int set, gnn_stream_t stream);
 int64_t gnn_column_slice_chunks(int64_t total);
 int gnn_support_compact(const int32_t *counts, int64_t num_nodes, int32_t *chunk_scratch, int64_t *nz_out, int32_t *cnt_out,
                         int64_t *n_support_out, gnn_stream_t stream);
-int gnn_column_slice_count(const int32_t *ucols, int64_t total, const int32_t *fullrowptr, int64_t M, const int32_t *lookup,
+int gnn_column_slice_count(const int32_t *ucols, int64_t total, const int32_t *fullrowptr, int64_t M, const uint32_t *bits,
                            int32_t *chunk_prefix, int32_t *out_rowptr, gnn_stream_t stream);
-int gnn_column_slice_fill(const int32_t *ucols, int64_t total, const int32_t *lookup, const int32_t *chunk_prefix, void *out_colidx,
-                          int colidx_bytes, gnn_stream_t stream);
+int gnn_column_slice_fill(const int32_t *ucols, int64_t total, const uint32_t *bits, const int32_t *rank0, const int32_t *chunk_prefix,
+                          void *out_colidx, int colidx_bytes, gnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Fused layer epilogue - the elementwise tail of every reference layer,

@@ -54,8 +54,8 @@ def test_device_sampler_bit_identical_to_host(gs, shape_name, orders, samp, batc
             adj = got.adjs[li]
             assert np.array_equal(adj._indices().cpu().numpy(), np.stack([rows, cols]))
             assert np.array_equal(adj._values().cpu().numpy().view(np.uint32), vals.view(np.uint32))
-        # the lookup / count scratch tables are left clean for the next call
-        assert int((dg.lookup != -1).sum().item()) == 0
+        # the membership bitmap is left clean for the next call
+        assert int((dg.member_bits != 0).sum().item()) == 0
 
 
 def test_device_sampler_matches_reference_golden(gs, golden_dir):
