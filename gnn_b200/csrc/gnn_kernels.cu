@@ -2258,21 +2258,62 @@ static int64_t ladies_layer_host_impl(uint32_t *mt_state, const int64_t *nz, con
     return GNN_E_BADARG;
   if (n_nz > INT32_MAX) return GNN_E_RANGE;
   static thread_local std::vector<int64_t> pi, found, all, prev;
+  static thread_local std::vector<int32_t> pi32;
   static thread_local std::vector<double> p;
-  static thread_local std::vector<uint64_t> bits;
+  static thread_local std::vector<uint64_t> bits, skewbits;
   static thread_local std::vector<int32_t> rank0, pos_of;
   // pi = column counts (sampler.py:117); locality sampling scales the counts of the nodes cached on this GPU and the
   // reference stores the scaled values back into an int64 array (:119-121): truncation.  Without scaling the int32 counts
   // are read where they lie.
   const bool scaled = scale_factor > 1.0 && skew_nodes && n_skew > 0;
+  if (nz[0] < 0) return GNN_E_BADARG;
+  // scaled counts: membership in the locality set is a bit test (the set as a bitmap over the support's id range, built
+  // per call) and the values stay int32 while the largest count * scale fits, so that this loop and the division below
+  // vectorise; sets over ids far sparser than the support, or huge factors,
+  // keep the merge of two ascending lists into int64 values.
+  const int64_t nz_max = nz[n_nz - 1];
+  const bool skew_by_bits = scaled && nz_max + 1 <= 64 * (n_nz + n_skew) + (1 << 20);
+  int32_t max_count = 0;
+  if (scaled && skew_by_bits) for (int64_t i = 0; i < n_nz; ++i) max_count = std::max(max_count, counts[i]);
+  const bool narrow = scaled && skew_by_bits && (double)max_count * scale_factor < 2.0e9;
+  auto scaled_count = [scale_factor](int64_t v) -> int64_t { return (int64_t)((double)v * scale_factor); };
+  auto in_skew = [&](int64_t node) -> bool { return node <= nz_max && ((skewbits[(size_t)(node >> 6)] >> (node & 63)) & 1ull); };
   int64_t total = 0, n_pos = 0;
-  if (scaled) {
+  if (scaled && skew_by_bits) {
+    skewbits.assign((size_t)((nz_max >> 6) + 1), 0);
+    for (int64_t j = 0; j < n_skew; ++j) {
+      const int64_t v = skew_nodes[j];
+      if (v >= 0 && v <= nz_max) skewbits[(size_t)(v >> 6)] |= 1ull << (v & 63);
+    }
+    const uint64_t *sb = skewbits.data();
+    if (narrow) {
+      pi32.resize((size_t)n_nz);
+      int32_t *q = pi32.data();
+      for (int64_t i = 0; i < n_nz; ++i) {
+        const int64_t node = nz[i];
+        const int32_t c = counts[i], sc = (int32_t)(int64_t)((double)c * scale_factor);
+        const int32_t v = ((sb[node >> 6] >> (node & 63)) & 1ull) ? sc : c;
+        q[i] = v;
+        total += v;
+        n_pos += v > 0;
+      }
+    } else {
+      pi.resize((size_t)n_nz);
+      for (int64_t i = 0; i < n_nz; ++i) {
+        const int64_t node = nz[i];
+        const int64_t v = ((sb[node >> 6] >> (node & 63)) & 1ull) ? scaled_count(counts[i]) : (int64_t)counts[i];
+        pi[(size_t)i] = v;
+        total += v;
+        n_pos += v > 0;
+      }
+    }
+  } else if (scaled) {
     pi.resize((size_t)n_nz);
     int64_t j = 0;
     for (int64_t i = 0; i < n_nz; ++i) {                                     // both ascending: merge
       int64_t v = counts[i];
       while (j < n_skew && skew_nodes[j] < nz[i]) ++j;
-      if (j < n_skew && skew_nodes[j] == nz[i]) v = (int64_t)((double)v * scale_factor);
+      if (j < n_skew && skew_nodes[j] == nz[i]) v = scaled_count(v);
       pi[(size_t)i] = v;
       total += v;
       n_pos += v > 0;
@@ -2282,13 +2323,15 @@ static int64_t ladies_layer_host_impl(uint32_t *mt_state, const int64_t *nz, con
   }
   if (total <= 0) return GNN_E_BADARG;
   const double dtotal = (double)total;
-  auto pi_at = [&](int64_t i) -> double { return scaled ? (double)pi[(size_t)i] : (double)counts[i]; };
+  auto pi_at = [&](int64_t i) -> double {
+    return !scaled ? (double)counts[i] : narrow ? (double)pi32[(size_t)i] : (double)pi[(size_t)i];
+  };
   p.resize((size_t)n_nz);
   {
     double *pp = p.data();                                                                         // p = pi / np.sum(pi)  (:124)
-    const int64_t *pi64 = pi.data();
-    if (scaled) for (int64_t i = 0; i < n_nz; ++i) pp[i] = (double)pi64[i] / dtotal;
-    else        for (int64_t i = 0; i < n_nz; ++i) pp[i] = (double)counts[i] / dtotal;
+    if (!scaled)     for (int64_t i = 0; i < n_nz; ++i) pp[i] = (double)counts[i] / dtotal;
+    else if (narrow) { const int32_t *q = pi32.data(); for (int64_t i = 0; i < n_nz; ++i) pp[i] = (double)q[i] / dtotal; }
+    else             { const int64_t *q = pi.data();   for (int64_t i = 0; i < n_nz; ++i) pp[i] = (double)q[i] / dtotal; }
   }
   const int64_t s_num = std::min(n_pos, samp_num);                                                 // :126
   found.resize((size_t)std::max<int64_t>(s_num, 1));
@@ -2304,7 +2347,6 @@ static int64_t ladies_layer_host_impl(uint32_t *mt_state, const int64_t *nz, con
     max_id = std::max(max_id, previous_nodes[i]);
     prev_sorted = prev_sorted && (i == 0 || previous_nodes[i - 1] < previous_nodes[i]);            // strictly: distinct too
   }
-  if (nz[0] < 0) return GNN_E_BADARG;
   const int64_t range = max_id + 1;
   int64_t n_after = 0, ns = 0;
   if (range <= 16 * (n_nz + n_prev) + 65536 && range < INT32_MAX) {
@@ -2317,7 +2359,7 @@ static int64_t ladies_layer_host_impl(uint32_t *mt_state, const int64_t *nz, con
     for (int64_t i = 0; i < n_prev; ++i) { const int64_t v = previous_nodes[i]; bits[(size_t)(v >> 6)] |= 1ull << (v & 63); }
     // position of a node inside the support: arithmetic when the support is one contiguous id range, else a table
     // (written for every support entry, validated on read: stale contents are harmless)
-    const bool direct = dense_counts && !scaled && range <= num_nodes;
+    const bool direct = dense_counts && (!scaled || skew_by_bits) && range <= num_nodes;
     const bool contiguous = nz[n_nz - 1] - nz[0] == n_nz - 1;
     if (!direct && !contiguous) {
       if ((int64_t)pos_of.size() < range) pos_of.resize((size_t)range);
@@ -2332,7 +2374,8 @@ static int64_t ladies_layer_host_impl(uint32_t *mt_state, const int64_t *nz, con
         m &= m - 1;
         double pa;                                                             // p[node]; zero off the support
         if (direct) {
-          pa = (double)dense_counts[node] / dtotal;
+          const int64_t c = dense_counts[node];                                // p of a node straight from the whole count array
+          pa = (double)((scaled && in_skew(node)) ? scaled_count(c) : c) / dtotal;
         } else {
           const int64_t j = contiguous ? node - nz[0] : (int64_t)pos_of[(size_t)node];
           pa = (j >= 0 && j < n_nz && nz[j] == node) ? pi_at(j) / dtotal : 0.0;

@@ -179,3 +179,26 @@ def test_native_host_layer_equals_the_numpy_expressions():
             previous = a[0]
         # the generator ends in the same state
         assert np.array_equal(state, gs.mt_state_of(rs))
+
+
+def test_native_host_layer_scaling_variants():
+    """The three ways gnn_ladies_layer_host applies the locality scaling (sampler.py:119-121) - int32 values with a bitmap
+    of the set, int64 values when count * scale would not fit, and the merge of two ascending lists for ids far sparser
+    than the support - against the numpy expressions."""
+    from gnn_b200 import gpu_sampler as gs
+    rng = np.random.Generator(np.random.PCG64(11))
+    for trial, (n_nodes, n_nz, n_skew_in, n_skew_out, scale) in enumerate([(60000, 20000, 3000, 3000, 3.0),           # bitmap, int32
+                                                                            (60000, 20000, 3000, 3000, 2.0e6),         # bitmap, int64
+                                                                            (400000000, 600, 80, 40, 2.5)]):           # merge
+        rs = np.random.RandomState(300 + trial)
+        state = gs.mt_state_of(np.random.RandomState(300 + trial))
+        nz = np.sort(rng.choice(n_nodes, size=n_nz, replace=False)).astype(np.int64)
+        cnt = rng.zipf(1.7, n_nz).clip(max=4000).astype(np.int32)
+        skew = np.unique(np.concatenate((rng.choice(nz, size=n_skew_in, replace=False),
+                                         rng.choice(n_nodes, size=n_skew_out, replace=False)))).astype(np.int64)
+        previous = rng.choice(nz, size=min(300, n_nz // 2), replace=False)
+        a = gs.host_layer_native(state, nz, cnt, skew, scale, previous, 256)
+        b = gs.host_layer_numpy(rs, nz, cnt, skew, scale, previous, 256)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and a[3] == b[3], trial
+        assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), trial
+        assert np.array_equal(state, gs.mt_state_of(rs)), trial
