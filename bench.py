@@ -1036,7 +1036,8 @@ def run_products_locality(args, cso, gmod, device, rank, world, flush_buf, log):
                     "parity_ok": bool(err_max <= GATE_TOL and gather_ok), "gather_bit_exact": gather_ok}
     out["sampling"] = src
     # GCN training with the device sampler in the loop, locality sampling on
-    pool = 4              # the reference's default --pool_num (main.py:77)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
+    pool = 8 if cores // max(world, 1) >= 16 else 4      # like the Reddit-shaped live legs: the reference's default --pool_num is 4
     try:
         targs = argparse.Namespace(steps=min(args.steps, 12))
         out["train_gcn_live_locality"] = harness.bench_train_live(targs, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log,

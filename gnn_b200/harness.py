@@ -198,6 +198,22 @@ def bench_train(args, cso, store, shape, g, mbs, orders, nhid, device, rank, wor
                     "allreduce(sum) + Adam on pre-sampled minibatches (host LADIES sampling and adjacency upload excluded)"}
 
 
+_SAMPLER_STREAMS = {}
+
+
+def _sampler_stream(device, priority, index, pipeline):
+    """The ``index``-th sampler stream of a device, created once per process with its allocator pool sized up front
+    (pipeline.reserve_stream_pool) and reused by every later run: torch hands out streams from a pool of 32 per priority
+    and wraps around, and every fresh stream would reserve its gigabyte again."""
+    key = (str(device), int(priority), int(index))
+    st = _SAMPLER_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device, priority=priority)
+        pipeline.reserve_stream_pool(st, 1 << 30)     # no cudaMalloc in the loop (pipeline.py)
+        _SAMPLER_STREAMS[key] = st
+    return st
+
+
 def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, device, rank, world, log, pool_num=4, fused=False,
                      prebuild_transpose=True, flat_grads=False, skewed_sampling_nodes=None, scale_factor=1.0, tc=False,
                      sampler_stream_priority=0, co_split=True):
@@ -233,6 +249,8 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
     own = g.train_nodes[rank * chunk: min((rank + 1) * chunk, g.train_nodes.size)]
     batches = [own[rng.permutation(own.size)[:batch]] for _ in range(total)]
 
+    import itertools
+    thread_ids = itertools.count()                    # (next() on a count is atomic under the GIL)
     job_s = [0.0, 0]                                  # seconds spent inside sampler jobs, jobs finished (timed region only)
     wait_s = [0.0]                                    # seconds the training thread waited for a minibatch
 
@@ -240,8 +258,7 @@ def bench_train_live(args, cso, store, shape, g, orders, nhid, samp, batch, devi
         t_job = time.perf_counter()
         torch.cuda.set_device(device)
         if not hasattr(tls, "stream"):
-            tls.stream = torch.cuda.Stream(device=device, priority=sampler_stream_priority)
-            pipeline.reserve_stream_pool(tls.stream, 1 << 30)     # no cudaMalloc in the loop (pipeline.py)
+            tls.stream = _sampler_stream(device, sampler_stream_priority, next(thread_ids), pipeline)
             tls.scratch = dg.scratch()
         with torch.cuda.stream(tls.stream):
             mb = gpu_sampler.ladies_sample_device(5000 + 1000 * rank + i, batches[i], [samp] * 5, dg, orders,
