@@ -2166,29 +2166,26 @@ static int legacy_choice_core(uint32_t *mt_state, double *pw, int64_t n, int64_t
     // numpy applies to the whole array; rounding keeps it monotone) is <= x.  Located without dividing n numbers:
     // a division-free approximate position for x * last, then the exact quotient test on the neighbours decides.
     // Many draws (the first rounds): a 65,536-bucket table of positions; bucket = floor(running sum * scale), the same
-    // monotone map for the sums and for x * last, filled by the cumsum loop itself (the loop is bound by the latency of
-    // its dependent additions, the bucket arithmetic rides along).  Few draws: a two-level binary search (coarse = every
-    // 64th sum, L1-resident).
+    // monotone map for the sums and for x * last.  Few draws: a two-level binary search (coarse = every 64th sum,
+    // L1-resident).
     const bool use_table = k >= 1024 && n >= 4096 && mass > 0.0;
     const double scale = use_table ? (double)kBuckets / mass : 0.0;
     double run = lo > 0 ? rawp[lo - 1] : 0.0;
+    for (int64_t i = lo; i < n; ++i) { run += pw[i]; rawp[i] = run; }     // bound by the latency of the dependent additions
     if (use_table) {
+      // every kTableStride-th running sum enters the table: e[b] = 1 + the last SAMPLED position whose sum falls into
+      // bucket b, a lower bound of the true one - the walk below is a few entries longer, the table costs an eighth
+      // (bucketing every sum inside the cumsum loop more than doubled the loop's time: measured)
+      constexpr int kTableStride = 8;
       std::fill(endsp, endsp + kBuckets + 1, 0);
-      int32_t *e = endsp + 1;               // e[b] = 1 + the last position whose sum falls into bucket b
-      for (int64_t i = 0; i < lo; ++i) {
+      int32_t *e = endsp + 1;
+      for (int64_t i = kTableStride - 1; i < n; i += kTableStride) {
         const double v = rawp[i] * scale;
         e[(v >= 0.0 && v < (double)kBuckets) ? (int)v : kBuckets - 1] = (int32_t)i + 1;
       }
-      for (int64_t i = lo; i < n; ++i) {
-        run += pw[i];
-        rawp[i] = run;
-        const double v = run * scale;
-        e[(v >= 0.0 && v < (double)kBuckets) ? (int)v : kBuckets - 1] = (int32_t)i + 1;
-      }
-      int32_t m = 0;                              // ends[b] := positions in buckets < b (running maximum; ends[0] = 0)
+      int32_t m = 0;                              // ends[b] := sampled positions in buckets < b (running maximum; ends[0] = 0)
       for (int b = 1; b <= kBuckets; ++b) { m = std::max(m, endsp[b]); endsp[b] = m; }
     } else {
-      for (int64_t i = lo; i < n; ++i) { run += pw[i]; rawp[i] = run; }
       for (int64_t c = 0; c < nc; ++c) coarsep[c] = rawp[std::min<int64_t>(c * 64 + 63, n - 1)];
     }
     const double last = rawp[n - 1];
