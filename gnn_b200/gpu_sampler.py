@@ -1,7 +1,8 @@
 """LADIES layer sampler with the array work on the device.
 
 Same outputs as the reference ``ladies_sampler`` (sampler.py:90-160) bit for bit, because the only random step -
-``np.random.choice(num_nodes, s_num, p=p, replace=False)`` (sampler.py:128) - still runs in numpy on the host, on the
+``np.random.choice(num_nodes, s_num, p=p, replace=False)`` (sampler.py:128) - runs on the host as numpy's own legacy
+algorithm restated in C on the same MT19937 stream (gnn_legacy_choice_f64, checked against ``RandomState.choice``), on the
 exact same probabilities (integer column counts come back from the device; ``p = pi / np.sum(pi)`` is the reference's
 own expression).  What moves to the GPU are the passes that cost the reference ~1.9 s per Reddit-shaped minibatch:
 

@@ -253,9 +253,9 @@ int gnn_index_rows_f32(const float *X, int64_t ldx, const int64_t *idx, int64_t 
 
 /* ---------------------------------------------------------------------------
  * LADIES layer construction on the device - the array work of the sampler.
- * The weighted draw without replacement stays numpy on the host (np.random.choice on the exact same
- * probabilities), so sampled node sets remain bit-identical to the reference; these entry points replace
- * the scipy/numpy array passes around it.  The graph structure (indptr int64 [N+1], indices int32 [nnz])
+ * The weighted draw without replacement stays on the host (numpy's legacy np.random.choice algorithm on the same
+ * MT19937 stream and the exact same probabilities: gnn_legacy_choice_f64 / gnn_ladies_layer_host below), so sampled
+ * node sets remain bit-identical to the reference; these entry points replace the scipy/numpy array passes around it.  The graph structure (indptr int64 [N+1], indices int32 [nnz])
  * is resident on the device.
  *
  * gnn_row_slice_count  : U = lap_matrix[nodes, :]  (sampler.py:113-114): out_fullrowptr[M+1] = row pointer of
