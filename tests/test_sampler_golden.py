@@ -202,3 +202,27 @@ def test_native_host_layer_scaling_variants():
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and a[3] == b[3], trial
         assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), trial
         assert np.array_equal(state, gs.mt_state_of(rs)), trial
+
+
+def test_native_host_layer_with_repeated_and_unsorted_previous_nodes():
+    """A batch may repeat nodes and comes in any order (np.unique / np.in1d of sampler.py:131,143 do not care): dense and
+    sparse id ranges, with and without the whole count array."""
+    from gnn_b200 import gpu_sampler as gs
+    rng = np.random.Generator(np.random.PCG64(21))
+    for trial, (n_nodes, n_nz) in enumerate([(40000, 25000), (300000000, 900)]):
+        nz = np.sort(rng.choice(n_nodes, size=n_nz, replace=False)).astype(np.int64)
+        cnt = rng.zipf(1.8, n_nz).clip(max=3000).astype(np.int32)
+        base = rng.choice(nz, size=200, replace=False)
+        previous = np.concatenate((base, base[:50], rng.choice(n_nodes, size=20, replace=False)))     # repeats + ids off the support
+        previous = previous[rng.permutation(previous.size)]
+        rs = np.random.RandomState(500 + trial)
+        state = gs.mt_state_of(np.random.RandomState(500 + trial))
+        a = gs.host_layer_native(state, nz, cnt, None, 1.0, previous, 512)
+        b = gs.host_layer_numpy(rs, nz, cnt, None, 1.0, previous, 512)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and a[3] == b[3], trial
+        assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), trial
+        if n_nodes <= 100000:
+            dense = np.zeros(n_nodes, dtype=np.int32)
+            dense[nz] = cnt
+            c = gs.host_layer_native_dense(gs.mt_state_of(np.random.RandomState(500 + trial)), dense, None, 1.0, previous, 512)
+            assert all(np.array_equal(u.view(np.uint8), v.view(np.uint8)) for u, v in zip(a[:3], c[:3])), trial
